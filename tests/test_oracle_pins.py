@@ -1,0 +1,176 @@
+"""Pins the oracle against every known answer the reference tree holds for this path.
+
+Restated from /root/reference/ferminet/tests/hamiltonian_test.py:62-149,
+ferminet/tests/network_blocks_test.py:27-46 and the quadrature facts quoted at
+AIQMCrelease3/pseudopotential/pseudopotential.py:181-225 (Mitas-Shirley-Ceperley rule).
+"""
+import math
+
+import numpy as np
+import pytest
+import scipy.special
+import torch
+
+from oracle import aiqmc_oracle as O
+
+torch.set_default_dtype(torch.float64)
+
+
+def h_atom_log_psi_signed(params, pos, spins=None, atoms=None, charges=None):
+    # ferminet/tests/hamiltonian_test.py:29-33: log psi = -|x|
+    return torch.ones_like(pos[..., 0]), -torch.sqrt(torch.sum(pos ** 2, dim=-1))
+
+
+@pytest.mark.parametrize("sizes,expected", [([], []), ([3], []), ([3, 0], [3]), ([3, 6], [3]),
+                                            ([3, 6, 0], [3, 9]), ([2, 0, 6], [2, 2])])
+def test_array_partitions(sizes, expected):
+    assert O.array_partitions(sizes) == expected
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (10, 2, 2), (10, 3, 3)])
+def test_slogdet_vs_numpy(shape):
+    a = np.random.default_rng(0).normal(size=shape).astype(np.float32)
+    s1, ld1 = O.slogdet(torch.tensor(a))
+    s2, ld2 = np.linalg.slogdet(a)
+    np.testing.assert_allclose(s1.numpy(), s2, atol=1e-5, rtol=1e-5)
+    np.testing.assert_allclose(ld1.numpy(), ld2, atol=1e-5, rtol=1e-5)
+
+
+def test_complex_slogdet_vs_numpy():
+    rng = np.random.default_rng(1)
+    a = rng.normal(size=(7, 5, 5)) + 1j * rng.normal(size=(7, 5, 5))
+    phase, logabs = O.logdet_matmul([torch.tensor(a)])
+    s2, ld2 = np.linalg.slogdet(a)
+    np.testing.assert_allclose(logabs.numpy(), ld2, rtol=1e-12)
+    np.testing.assert_allclose(phase.numpy(), np.angle(s2), atol=1e-12)
+
+
+def test_local_kinetic_energy_h_like():
+    rng = np.random.default_rng(2)
+    xs = torch.tensor(rng.normal(size=(3,)))
+    data = O.AINetData(positions=xs, spins=torch.ones(1), atoms=torch.tensor(rng.normal(size=(1, 3))),
+                       charges=2 * torch.ones(1))
+    ke = O.local_kinetic_energy(h_atom_log_psi_signed)({}, data)
+    expected = -(1 - 2 / np.abs(np.linalg.norm(xs.numpy()))) / 2
+    np.testing.assert_allclose(ke.numpy(), expected, rtol=1e-5)
+
+
+def test_potential_energy_null():
+    xs = torch.tensor(np.random.default_rng(3).normal(size=(1, 3)))
+    r_ae = torch.linalg.norm(xs, dim=-1)[..., None, None]
+    v = O.potential_energy(r_ae, torch.ones(1, 1, 1), torch.zeros(1, 3), torch.zeros(1))
+    np.testing.assert_allclose(v.numpy(), 0.0, atol=1e-12)
+
+
+def test_potential_energy_ee():
+    xs = np.random.default_rng(4).normal(size=(5, 3))
+    r_ee = np.linalg.norm(xs[None, ...] - xs[:, None, :], axis=-1)
+    mask = ~np.eye(5, dtype=bool)
+    expected = 0.5 * np.sum(1.0 / r_ee[mask])
+    r_ae = torch.tensor(np.linalg.norm(xs, axis=-1))[:, None, None]
+    v = O.potential_energy(r_ae, torch.tensor(r_ee)[..., None], torch.zeros(1, 3), torch.zeros(1))
+    np.testing.assert_allclose(v.numpy(), expected, rtol=1e-5)
+
+
+def test_potential_energy_he2_ion():
+    xs = np.random.default_rng(5).normal(size=(1, 3))
+    atoms = np.array([[0, 0, -1.0], [0, 0, 1.0]])
+    charges = np.array([2.0, 2.0])
+    r_ae = np.linalg.norm(xs - atoms, axis=-1)
+    expected = -np.sum(charges / r_ae) + np.prod(charges) / 2.0
+    ae, ee, r_ae_t, r_ee_t = O.construct_input_features(torch.tensor(xs.reshape(-1)), torch.tensor(atoms))
+    v = O.potential_electron_nuclear(torch.tensor(charges), r_ae_t) + O.potential_nuclear_nuclear(
+        torch.tensor(charges), torch.tensor(atoms))
+    np.testing.assert_allclose(v.numpy(), expected, rtol=1e-5)
+
+
+def test_local_energy_hydrogen_is_minus_half():
+    xs = torch.tensor(np.random.default_rng(6).normal(size=(100, 3)))
+    le = O.local_energy_ae(h_atom_log_psi_signed, charges=np.ones(1))
+    data = O.AINetData(positions=xs, spins=torch.ones(1), atoms=torch.zeros(1, 3), charges=torch.ones(1))
+    e, _ = le({}, None, data)
+    np.testing.assert_allclose(e.numpy(), -0.5 * np.ones(100), rtol=1e-5)
+
+
+def test_laplacian_equals_hessian_trace():
+    # ferminet/tests/hamiltonian_test.py:154-181 on the AIQMC network itself
+    net, params, pos, spins, atoms = _tiny_net(n=4, natoms=2, seed=7)
+    f = lambda x: net.apply(params, x, spins, atoms)[1]
+    x = pos[0]
+    hess = torch.autograd.functional.hessian(f, x)
+    grad = torch.autograd.functional.jacobian(f, x)
+    expected = -0.5 * (torch.trace(hess) + (grad ** 2).sum())
+    data = O.AINetData(positions=x, spins=spins, atoms=atoms, charges=None)
+    ke = O.local_kinetic_energy(net.apply)(params, data)
+    np.testing.assert_allclose(ke.numpy(), expected.numpy(), rtol=1e-10)
+
+
+def _tiny_net(n, natoms, seed, spins=None):
+    rng = np.random.default_rng(seed)
+    spins = np.array(spins if spins is not None else [1.0] * (n // 2) + [-1.0] * (n - n // 2))
+    atoms = rng.normal(size=(natoms, 3))
+    charges = np.full(natoms, float(n) / natoms)
+    par, anti, npar, nanti = O.jastrow_indices_ee(spins, n)
+    up, dn = O.spin_indices_h(spins)
+    net = O.make_ai_net(nspins=(len(up), len(dn)), charges=charges, parallel_indices=par,
+                        antiparallel_indices=anti, spin_up_indices=up, spin_down_indices=dn,
+                        n_parallel=npar, n_antiparallel=nanti, ndim=3, natoms=natoms, nelectrons=n)
+    params = net.init(rng, randomize_all=True)
+    pos = torch.tensor(rng.normal(size=(5, 3 * n)))
+    return net, params, pos, torch.tensor(spins), torch.tensor(atoms)
+
+
+def test_param_tree_shapes_match_reference():
+    # nn.py:203-278,370-407 with hidden_dims=((4,4),)*3, hidden_dims_Ynlm=(6,6,6)
+    n, a = 8, 2
+    net, params, *_ = _tiny_net(n, a, 8)
+    st = params['layers']['streams']
+    assert st[0]['convolutional']['w'].shape == (n, 12 * a + 8)
+    assert st[0]['convolutional']['b'].shape == (n, 3 * a + 2)
+    assert st[0]['single']['w'].shape == (3 * a + 2, 4)
+    assert st[1]['convolutional']['w'].shape == (n, 20) and st[2]['single']['w'].shape == (5, 4)
+    assert 'double' in st[0] and 'double' in st[1] and 'double' not in st[2]
+    assert params['layers']['streams_y'][0]['single_Ynlm']['w'].shape == (4 * a + 2, 6)
+    assert params['orbitals'][0]['w'].shape == (4, 2 * n) and params['y'][0]['w'].shape == (6, n)
+    assert params['jastrow_ee']['ee_par'].numel() + params['jastrow_ee']['ee_anti'].numel() == n * (n - 1) // 2
+    assert params['jastrow_ae']['ae'].shape == (n, a) and len(params['envelope']) == n
+
+
+def test_antisymmetry_under_same_spin_exchange_is_not_assumed_but_batching_is_consistent():
+    net, params, pos, spins, atoms = _tiny_net(6, 1, 9)
+    ph_b, la_b = net.apply(params, pos, spins, atoms)
+    for k in range(pos.shape[0]):
+        ph, la = net.apply(params, pos[k], spins, atoms)
+        np.testing.assert_allclose(la.numpy(), la_b[k].numpy(), rtol=1e-13)
+        np.testing.assert_allclose(ph.numpy(), ph_b[k].numpy(), atol=1e-13)
+
+
+def test_quadrature_weights_sum_to_one_and_integrate_ylm():
+    pts, wts = O.quadrature_table()
+    assert pts.shape == (50, 3)
+    np.testing.assert_allclose(wts.sum(), 1.0, rtol=1e-12)
+    np.testing.assert_allclose(np.linalg.norm(pts, axis=1), 1.0, atol=2e-8)   # 8-digit literals
+    theta = np.arccos(np.clip(pts[:, 2], -1, 1))
+    phi = np.arctan2(pts[:, 1], pts[:, 0])
+    for l in range(1, 12):                                                    # exact to l <= 11
+        for m in range(-l, l + 1):
+            y = scipy.special.sph_harm_y(l, m, theta, phi)
+            assert abs(np.sum(wts * y)) < 5e-8, (l, m)
+
+
+def test_P_l_matches_legendre():
+    x = torch.linspace(-1, 1, 11)
+    out = O.P_l(x, 3)
+    for l in range(4):
+        ref = (2 * l + 1) / (4 * math.pi) * scipy.special.eval_legendre(l, x.numpy())
+        np.testing.assert_allclose(out[l].numpy(), ref, atol=1e-14)
+
+
+def test_branch_comb_counts_dyadic_weights():
+    # dyadic-rational weights: cumsum is exact in any association order
+    w = torch.tensor([0.5, 2.0, 0.25, 1.25, 0.0, 1.0, 2.5, 0.5])
+    new_w, inds = O.branch(w, 0.3125)
+    counts = np.bincount(inds.numpy(), minlength=8)
+    assert counts.sum() == 8 and abs(float(new_w) - 1.0) < 1e-15
+    assert np.all(np.abs(counts - w.numpy()) < 1.0 + 1e-12)      # systematic comb: |n_i - w_i/wbar| < 1
+    assert counts[4] == 0
