@@ -1,0 +1,158 @@
+/* aiqmc_b200.h -- C ABI of the B200-native AIQMC walker engine.
+ *
+ * The reference (Yongda1/...-Quantum-Monte-Carlo, AIQMCrelease3) has no native interface:
+ * its boundary is a set of Python closures over jax.numpy.  Every entry
+ * point below replaces one of those closures, is natively batched over walkers, takes raw
+ * DEVICE pointers (float64 unless noted) + a cudaStream_t passed as void*, never allocates
+ * behind the caller's back (workspace size queries + caller-provided workspace) and returns
+ * an int status: 0 = ok, <0 = AIQMC_E_* below.  No torch / jax types appear here; the XLA
+ * FFI shim and the torch/ctypes harness both sit on top of these symbols.
+ *
+ * Citations are file:line under /root/reference/AIQMCrelease3/.
+ */
+#ifndef AIQMC_B200_H_
+#define AIQMC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AIQMC_MAX_ELEC 32
+#define AIQMC_MAX_ATOMS 16
+#define AIQMC_ECP_MAX_L 4    /* l = 0..3, P_l table of pseudopotential.py:250-269 */
+#define AIQMC_ECP_MAX_K 4    /* gaussians per channel */
+#define AIQMC_NQUAD 50       /* 6+12+8+24 octahedral points, pseudopotential.py:181-225 */
+
+enum {
+  AIQMC_OK = 0,
+  AIQMC_E_UNSUPPORTED = -1,  /* (n_elec, n_atoms) pair has no compiled instantiation */
+  AIQMC_E_BADARG = -2,
+  AIQMC_E_CUDA = -3,         /* a CUDA runtime call failed; aiqmc_last_cuda_error() has the code */
+  AIQMC_E_WORKSPACE = -4     /* workspace too small */
+};
+
+/* Static description of the molecule + spin layout.  Mirrors the arguments of
+ * make_ai_net (wavefunction_Ynlm/nn.py:511-526) and the index tables of spin_indices.py:5-46. */
+typedef struct AiqmcSystem {
+  int32_t n_elec;       /* N, nelectrons */
+  int32_t n_atoms;      /* A, natoms */
+  int32_t n_up;         /* nspins[0]: electrons [0,n_up) form the first symmetric-feature block */
+  int32_t n_dn;         /* nspins[1] (nn.py:142-153) */
+  int32_t n_up_rows;    /* len(spin_up_indices): rows [0,n_up_rows) use params['orbitals'][0] */
+  int32_t sigma[AIQMC_MAX_ELEC]; /* orbital-matrix row k reads h_one of electron sigma[k]
+                                    (spin_up_indices then spin_down_indices, nn.py:432-474) */
+} AiqmcSystem;
+
+/* ccECP tables, shapes as in example/single_atom_C/single_atom_C.py:13-23 (padded). */
+typedef struct AiqmcEcp {
+  int32_t k_loc;                 /* gaussians in the local channel */
+  int32_t n_l;                   /* list_l + 1 angular channels actually summed */
+  int32_t k_nl;                  /* gaussians per non-local channel */
+  int32_t pad_;
+  double rn_local[AIQMC_MAX_ATOMS][AIQMC_ECP_MAX_K];      /* Rn_local (used as r^(n-2), pseudopotential.py:95) */
+  double local_coes[AIQMC_MAX_ATOMS][AIQMC_ECP_MAX_K];
+  double local_exps[AIQMC_MAX_ATOMS][AIQMC_ECP_MAX_K];
+  double rn_non_local[AIQMC_MAX_ATOMS][AIQMC_ECP_MAX_L][AIQMC_ECP_MAX_K];  /* used as r^n, :150 */
+  double non_local_coes[AIQMC_MAX_ATOMS][AIQMC_ECP_MAX_L][AIQMC_ECP_MAX_K];
+  double non_local_exps[AIQMC_MAX_ATOMS][AIQMC_ECP_MAX_L][AIQMC_ECP_MAX_K];
+  double quad_pts[AIQMC_NQUAD][3];   /* unrotated points, order OA,OB,OC,OD */
+  double quad_wts[AIQMC_NQUAD];      /* 4/315, 64/2835, 27/1280, 14641/725760 per group */
+} AiqmcEcp;
+
+/* ---- parameter packing --------------------------------------------------------------- */
+/* Offsets (in doubles) of every leaf of the reference parameter pytree (nn.py:203-278,
+ * 370-407) inside the single packed buffer the kernels read.  Filled by aiqmc_param_layout. */
+typedef struct AiqmcLayout {
+  int32_t conv_w[3], conv_b[3];      /* streams[l].convolutional  w (N,d_l)  b (N,d_l/4) */
+  int32_t sing_w[3], sing_b[3];      /* streams[l].single         w (d_l/4,4) b (4)      */
+  int32_t dbl_w[2], dbl_b[2];        /* streams[l].double         w (4,4) b (4), l=0,1   */
+  int32_t yn_w[3], yn_b[3];          /* streams_y[l].single_Ynlm  w (k_l,6) b (6)        */
+  int32_t orb_w[2], orb_b[2];        /* orbitals[s]               w (4,2N) b (2N)        */
+  int32_t y_w;                       /* y[0].w (6,N), row-normalised as at nn.py:449-451  */
+  int32_t jas_alpha, jas_cusp;       /* (N,N) i<j tables built from ee_par/ee_anti + spin_indices.py */
+  int32_t jas_beta;                  /* jastrow_ae.ae (N,A) */
+  int32_t jas_c34, jas_c14;          /* (2Z)^(3/4), (2Z)^(1/4) per atom (Jastrow.py:84) */
+  int32_t env_pi, env_sx;            /* envelope[i].pi (A,3); sigma*xi (A,3) */
+  int32_t env_alpha, env_beta;       /* envelope[i].alpha (1) ; beta (A) */
+  int32_t atoms, charges;            /* (A,3), (A) */
+  int32_t total;                     /* total number of doubles */
+} AiqmcLayout;
+
+int aiqmc_param_layout(int32_t n_elec, int32_t n_atoms, AiqmcLayout* out);
+/* 1 if (n_elec,n_atoms) has a compiled kernel instantiation, else 0. */
+int aiqmc_supported(int32_t n_elec, int32_t n_atoms);
+int aiqmc_last_cuda_error(void);
+const char* aiqmc_version(void);
+
+/* ---- wavefunction: replaces Network.apply == signed_network (nn.py:545-551) ------------ */
+/* pos (n_cfg,3N) -> phase (n_cfg) [angle of the determinant], logabs (n_cfg) [log|psi|]. */
+int aiqmc_psi_fwd(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_cfg,
+                  double* phase, double* logabs, void* stream);
+/* + grad (n_cfg,3N) = d log|psi| / d pos: replaces jax.grad(logabs_f, argnums=1)
+ * (VMC/VMCmcstep.py:41, Energy/hamiltonian.py:104). */
+int aiqmc_psi_grad(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_cfg,
+                   double* phase, double* logabs, double* grad, void* stream);
+/* + lap (n_cfg) = sum_i d^2 log|psi| / d pos_i^2 by forward Laplacian: replaces
+ * jax.linearize(grad) + the fori_loop of 3N jvps (Energy/pphamiltonian.py:74-106). */
+int aiqmc_psi_fwdlap(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_cfg,
+                     double* phase, double* logabs, double* grad, double* lap, void* stream);
+
+/* ---- VMC: replaces walkers_update (VMC/VMCmcstep.py:28-111) ---------------------------- */
+int64_t aiqmc_vmc_workspace_bytes(const AiqmcSystem* sys, int64_t n_walkers);
+/* One drift-diffusion Metropolis sweep over the whole per-device batch, in place.
+ *  gauss1 (B,3N), gauss2 (B,N,3N): sqrt(tstep)*N(0,1); rnd (B,N): U[0,1)  (parity mode inputs,
+ *  the arrays the reference draws at VMCmcstep.py:58,83 and :19-20).
+ *  accept (B,N) uint8 out (may be NULL); signed_ratio!=0 gives the DMC variant
+ *  (DMC/drift_diffusion.py:87-89).  aux_out (may be NULL): [0]=sum(x_new), [1]=sum(x_proposed)
+ *  for tdamp (drift_diffusion.py:21), [2]=v2 of grad(x1), [3]=v2 of grad(x2) (limdrift sums, quirk Q6).
+ *  grad_eff_old (B,3N) out may be NULL (drift_diffusion.py:45). */
+int aiqmc_vmc_sweep(const AiqmcSystem* sys, const double* params, double* pos, const double* gauss1,
+                    const double* gauss2, const double* rnd, int64_t n_walkers, double tstep,
+                    double acyrus, int32_t signed_ratio, uint8_t* accept, double* grad_eff_old,
+                    double* aux_out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- local energy: replaces _e_l (Energy/hamiltonian.py:248-258, pphamiltonian.py:177-188)
+ *      wrapped in jax.vmap over walkers (Loss/pploss.py:145-153) ---------------------------- */
+int64_t aiqmc_energy_workspace_bytes(const AiqmcSystem* sys, int64_t n_walkers, int32_t with_ecp);
+/* All-electron: E_L = V_ee + V_en + V_nn + KE (real).  e_l (B). */
+int aiqmc_local_energy_ae(const AiqmcSystem* sys, const double* params, const double* pos,
+                          int64_t n_walkers, double* e_l, void* workspace, int64_t workspace_bytes,
+                          void* stream);
+/* ccECP: E_L = V_ee + V_nn + KE + local channel + non-local 50-point quadrature (complex,
+ * quirk Q25).  rot (B,3,3) is the per-walker rotation jax.random.orthogonal would have drawn
+ * (pseudopotential.py:233-235).  e_l (B,2) interleaved (re,im). */
+int aiqmc_local_energy_ecp(const AiqmcSystem* sys, const AiqmcEcp* ecp, const double* params,
+                           const double* pos, const double* rot, int64_t n_walkers, double* e_l,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+/* Block-reduced [sum Re E, sum Im E, sum |E|^2, count] -> stats[4] (device), the partials of
+ * pmean(mean(e_l)) and the variance at Loss/pploss.py:165-167; all-reduced over GPUs by the host
+ * (NCCL sum of 4 doubles).  e_l_stride = 1 (real) or 2 (complex interleaved). */
+int aiqmc_energy_stats(const double* e_l, int32_t e_l_stride, int64_t n_walkers, double* stats,
+                       void* stream);
+
+/* ---- DMC: replaces DMC/drift_diffusion.py, S_matrix.py, dmc.py:86-92, branch.py ---------- */
+/* S = E_T - E_est + e_cut / (1 + (v2*tau/N)^2), e_cut clamped by the batch-global min of
+ * |E_est - E_L| and branchcut (quirk Q20).  v2_in (B,3N) holds the limited drift (its square is
+ * summed here).  global_min_io: device scalar; pass NULL to reduce over this device only, or a
+ * pointer pre-filled with the cross-GPU min. */
+int aiqmc_dmc_s(const double* e_l, int32_t e_l_stride, const double* drift, int64_t n_walkers,
+                int32_t n_elec, double e_trial, double e_est, const double* branchcut, double tau,
+                double* s_out, void* stream);
+/* weights *= exp(tau * tdamp * 0.5 * (S_new + S_old))   (dmc.py:91-92). */
+int aiqmc_dmc_weights(double* weights, const double* s_old, const double* s_new, int64_t n_walkers,
+                      double tau, double tdamp, void* stream);
+/* Systematic comb (branch.py:17-23): newinds (B) int32, new_weight (device scalar) = wtot/B.
+ * u in [0,1) is the uniform the reference draws at branch.py:21. */
+int64_t aiqmc_branch_workspace_bytes(int64_t n_walkers);
+int aiqmc_branch_comb(const double* weights, int64_t n_walkers, double u, int32_t* newinds,
+                      double* new_weight, void* workspace, int64_t workspace_bytes, void* stream);
+/* Gather walkers by index: pos_out[b] = pos_in[newinds[b]]  (HBM-bound, 24N+4 B/walker). */
+int aiqmc_gather_walkers(const double* pos_in, const int32_t* newinds, int64_t n_walkers,
+                         int32_t row_doubles, double* pos_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AIQMC_B200_H_ */

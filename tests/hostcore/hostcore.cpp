@@ -1,0 +1,35 @@
+// TEST-ONLY host build of the per-configuration core (psi_core.cuh) so that the kernel
+// arithmetic can be checked against the oracle on a CPU-only box.  Never loaded by the
+// product package; the product path is the CUDA library and fails loudly without it.
+#include "../../ab-initio-flexible-gaussian-basis-neural-network-quantum-monte-carlo_b200/csrc/psi_core.cuh"
+#include "../../ab-initio-flexible-gaussian-basis-neural-network-quantum-monte-carlo_b200/csrc/dispatch.h"
+
+using namespace aiqmc;
+
+template <int NE, int NA>
+static void run(const AiqmcSystem* sys, const double* P, const double* pos, long n, int mode, double* phase,
+                double* logabs, double* grad, double* lap) {
+#pragma omp parallel for schedule(dynamic, 4)
+  for (long t = 0; t < n; ++t) {
+    const double* x = pos + t * 3 * NE;
+    if (mode == 0) {
+      Psi<NE, NA>::eval_value(*sys, P, x, phase[t], logabs[t]);
+    } else if (mode == 1) {
+      double dummy;
+      Psi<NE, NA>::template eval_deriv<false>(*sys, P, x, phase[t], logabs[t], grad + t * 3 * NE, dummy);
+    } else {
+      Psi<NE, NA>::template eval_deriv<true>(*sys, P, x, phase[t], logabs[t], grad + t * 3 * NE, lap[t]);
+    }
+  }
+}
+
+extern "C" int hc_layout(int n, int a, AiqmcLayout* out) { *out = make_layout(n, a); return 0; }
+
+extern "C" int hc_psi(const AiqmcSystem* sys, const double* P, const double* pos, long n, int mode, double* phase,
+                      double* logabs, double* grad, double* lap) {
+#define X(NE, NA) \
+  if (sys->n_elec == NE && sys->n_atoms == NA) { run<NE, NA>(sys, P, pos, n, mode, phase, logabs, grad, lap); return 0; }
+  AIQMC_FOR_EACH_SYSTEM(X)
+#undef X
+  return -1;
+}
