@@ -1,0 +1,253 @@
+"""Drop-in mirrors of the reference's Python closures for the walker hot path.
+
+Same factory names, argument meaning and return conventions as
+  AIQMCrelease3/wavefunction_Ynlm/nn.py:511-553      make_ai_net -> Network(init, apply, orbitals)
+  AIQMCrelease3/VMC/VMCmcstep.py:121-140             main_monte_carlo -> mc_step(params, data, key)
+  AIQMCrelease3/Energy/hamiltonian.py:236-260        local_energy    -> _e_l(params, key, data)
+  AIQMCrelease3/Energy/pphamiltonian.py:130-190      local_energy (ccECP)
+  AIQMCrelease3/DMC/{drift_diffusion,S_matrix,branch,dmc}.py
+but natively batched over walkers (the reference wraps them in jax.vmap / jax.pmap) and backed by
+the sm_100a kernels.  Differences a caller sees:
+  * arrays are torch CUDA float64 tensors (numpy / float32 inputs are converted);
+  * `key` is either a dict of explicit random arrays (parity mode: the arrays the reference draws
+    from its PRNGKey) or an int seed (throughput mode: torch's device Philox generator);
+  * `params` may be the reference pytree (packed on every call) or a PackedParams handle.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, replace
+from typing import Any, Callable, Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .engine import WalkerEngine
+from .system import SystemSpec, make_ecp
+
+
+@dataclass
+class AINetData:
+    """nn.py:20-25.  positions (B,3N); spins/atoms/charges may be per-walker replicas (B,...) as in
+    main_pp_adam_muti_GPU.py:80-94 -- only row 0 is read, like VMCmcstep.py:42-44."""
+    positions: Any
+    spins: Any
+    atoms: Any
+    charges: Any
+
+
+class PackedParams:
+    """Parameters already flattened and resident on the device."""
+
+    def __init__(self, engine: WalkerEngine, tree):
+        engine.set_params(tree)
+        self.engine = engine
+        self.tree = tree
+
+
+@dataclass
+class Network:
+    init: Callable
+    apply: Callable
+    orbitals: Optional[Callable]
+    pack: Callable
+    engine_for: Callable
+
+
+def _first(x, ndim):
+    x = torch.as_tensor(x) if not isinstance(x, torch.Tensor) else x
+    return x.reshape(-1, *x.shape[-ndim:])[0] if x.dim() > ndim else x
+
+
+def make_ai_net(nspins, charges, parallel_indices, antiparallel_indices, spin_up_indices, spin_down_indices,
+                n_parallel: int, n_antiparallel: int, ndim: int, natoms: int, nelectrons: int,
+                determinants: int = 1, bias_orbitals: bool = True, rescale_inputs: bool = False,
+                hidden_dims=((4, 4), (4, 4), (4, 4)), hidden_dims_Ynlm=(6, 6, 6), device=None) -> Network:
+    """nn.py:511-553.  Only the configuration every reference driver uses is compiled:
+    ndim=3, determinants=1, rescale_inputs=False, hidden_dims=((4,4),)*3, hidden_dims_Ynlm=(6,6,6)."""
+    if ndim != 3 or determinants != 1 or rescale_inputs or tuple(map(tuple, hidden_dims)) != ((4, 4),) * 3 \
+            or tuple(hidden_dims_Ynlm) != (6, 6, 6):
+        raise NotImplementedError("aiqmc_b200 compiles the reference's default architecture only")
+    charges_np = np.asarray(charges.cpu() if hasattr(charges, "cpu") else charges, dtype=np.float64).reshape(-1)
+    engines: Dict[bytes, WalkerEngine] = {}
+
+    def engine_for(atoms) -> WalkerEngine:
+        at = np.asarray(atoms.detach().cpu() if hasattr(atoms, "detach") else atoms, dtype=np.float64).reshape(-1, 3)
+        key = at.tobytes()
+        if key not in engines:
+            spec = SystemSpec(nelectrons, natoms, tuple(nspins), at, charges_np,
+                              np.asarray(spin_up_indices).reshape(-1), np.asarray(spin_down_indices).reshape(-1),
+                              np.asarray(parallel_indices).reshape(2, -1), np.asarray(antiparallel_indices).reshape(2, -1))
+            engines[key] = WalkerEngine(spec, device=device)
+        return engines[key]
+
+    def init(key):
+        """Same leaf shapes / scales as nn.py:203-278,370-407; `key` is an int seed or numpy Generator."""
+        rng = key if isinstance(key, np.random.Generator) else np.random.default_rng(int(key))
+
+        def lin(i, o, bias=True):
+            p = {'w': rng.standard_normal((i, o)) / math.sqrt(float(i))}
+            if bias:
+                p['b'] = rng.standard_normal((o,))
+            return p
+        layers, layers_y = [], []
+        d_one, d_y = 4 * natoms, 4 * natoms + 2
+        for i in range(3):
+            d_in = 3 * d_one + 8
+            lp = {'convolutional': {'w': rng.standard_normal((nelectrons, d_in)) / math.sqrt(float(nelectrons)),
+                                    'b': rng.standard_normal((nelectrons, d_in // 4))},
+                  'single': lin(d_in // 4, 4)}
+            if i < 2:
+                lp['double'] = lin(4, 4)
+            layers.append(lp)
+            layers_y.append({'single_Ynlm': lin(d_y, 6)})
+            d_one, d_y = 4, 6
+        one = np.ones
+        return {'layers': {'input': {}, 'streams': layers, 'streams_y': layers_y},
+                'orbitals': [lin(4, 2 * nelectrons) for _ in range(2)],
+                'y': [lin(6, nelectrons, bias=False)],
+                'jastrow_ee': {'ee_par': one(n_parallel), 'ee_anti': one(n_antiparallel)},
+                'jastrow_ae': {'ae': one((nelectrons, natoms))},
+                'envelope': [{'pi': one((natoms, 3)), 'sigma': one((natoms, 3)), 'alpha': one(1), 'beta': one(natoms),
+                              'xi': one(1), 'eplion': one((natoms, 3)), 'mu': one(natoms), 'nu': one(natoms)}
+                             for _ in range(nelectrons)]}
+
+    def pack(params, atoms) -> PackedParams:
+        return PackedParams(engine_for(atoms), params)
+
+    def _bind(params, atoms) -> WalkerEngine:
+        if isinstance(params, PackedParams):
+            return params.engine
+        eng = engine_for(_first(atoms, 2))
+        eng.set_params(params)
+        return eng
+
+    def apply(params, pos, spins=None, atoms=None, charges=None):
+        """signed_network(params, pos, spins, atoms, charges) -> (phase, log|psi|); pos (..., 3N)."""
+        eng = _bind(params, atoms)
+        return eng.psi(pos, mode=0)
+
+    net = Network(init=init, apply=apply, orbitals=None, pack=pack, engine_for=engine_for)
+    apply.network = net
+    apply.bind = _bind
+    return net
+
+
+def _engine_of(f, params, data) -> WalkerEngine:
+    if not hasattr(f, "bind"):
+        raise TypeError("f must be the `apply` of aiqmc_b200.make_ai_net (the kernels are not a generic autodiff)")
+    return f.bind(params, data.atoms)
+
+
+def _positions(eng: WalkerEngine, data: AINetData) -> torch.Tensor:
+    p = torch.as_tensor(data.positions).to(device=eng.device, dtype=torch.float64)
+    return p.reshape(-1, 3 * eng.n).contiguous()
+
+
+def _sweep_rand(eng: WalkerEngine, key, B: int, tstep: float, step: int):
+    n = eng.n
+    if isinstance(key, (list, tuple)):
+        key = key[step]
+    if isinstance(key, dict):
+        cv = lambda a: torch.as_tensor(a).to(device=eng.device, dtype=torch.float64).contiguous()
+        return cv(key['gauss1']), cv(key['gauss2']), cv(key['rnd'])
+    gen = torch.Generator(device=eng.device)
+    gen.manual_seed(int(key) * 1000003 + step)
+    g1 = torch.randn((B, 3 * n), generator=gen, device=eng.device, dtype=torch.float64) * math.sqrt(tstep)
+    g2 = torch.randn((B, n, 3 * n), generator=gen, device=eng.device, dtype=torch.float64) * math.sqrt(tstep)
+    u = torch.rand((B, n), generator=gen, device=eng.device, dtype=torch.float64)
+    return g1, g2, u
+
+
+def main_monte_carlo(f, tstep: float, ndim: int, nelectrons: int, nsteps: int, batch_size: int):
+    """VMCmcstep.py:121-140 -> mc_step(params, data, key) -> data (nsteps sweeps, in place on a copy)."""
+    def mc_step(params, data: AINetData, key):
+        eng = _engine_of(f, params, data)
+        pos = _positions(eng, data).clone()
+        for i in range(nsteps):
+            g1, g2, u = _sweep_rand(eng, key, pos.shape[0], tstep, i)
+            eng.vmc_sweep(pos, g1, g2, u, tstep, want_accept=False)
+        return replace(data, positions=pos)
+    return mc_step
+
+
+def local_energy(f, charges, nspins=None, use_scan: bool = False, complex_output: bool = False, lognetwork=None,
+                 rn_local=None, local_coes=None, local_exps=None, rn_non_local=None, non_local_coes=None,
+                 non_local_exps=None, natoms: Optional[int] = None, nelectrons: Optional[int] = None,
+                 ndim: int = 3, list_l: Optional[int] = None):
+    """hamiltonian.py:236-260 (no ECP tables) / pphamiltonian.py:130-190 (with ECP tables).
+
+    Returns _e_l(params, key, data) -> (E_L (B,), None).  For the ECP flavour `key` is the per-walker
+    rotation (B,3,3) the reference draws at pp_energy_test.py:75, or an int seed.
+    """
+    if complex_output:
+        raise NotImplementedError("no reference caller sets complex_output=True (quirk Q11)")
+    ecp = None
+    if rn_local is not None:
+        ecp = make_ecp(natoms, rn_local, local_coes, local_exps, rn_non_local, non_local_coes, non_local_exps, list_l)
+
+    def _e_l(params, key, data: AINetData):
+        eng = _engine_of(f, params, data)
+        eng.ecp = ecp
+        pos = _positions(eng, data)
+        rot = None
+        if ecp is not None:
+            rot = key if not isinstance(key, (int, np.integer)) else random_rotations(pos.shape[0], int(key), eng.device)
+        return eng.local_energy(pos, rot), None
+    _e_l.engine_of = lambda params, data: _engine_of(f, params, data)
+    return _e_l
+
+
+def random_rotations(n: int, seed: int, device) -> torch.Tensor:
+    """Haar-random 3x3 orthogonal matrices (stand-in for jax.random.orthogonal, pseudopotential.py:234)."""
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    q, r = torch.linalg.qr(torch.randn((n, 3, 3), generator=gen, device=device, dtype=torch.float64))
+    return q * torch.sign(torch.diagonal(r, dim1=-2, dim2=-1))[:, None, :]
+
+
+def total_energy(local_energy_fn, process_group=None):
+    """Loss/pploss.py:157-167 / DMC/total_energy.py:9-32 forward part: E_L per walker, mean and variance;
+    the two pmean's become ONE 4-double all-reduce (NCCL) when a process group is given."""
+    def _total(params, key, data: AINetData):
+        e_l, _ = local_energy_fn(params, key, data)
+        eng = local_energy_fn.engine_of(params, data)
+        stats = eng.energy_stats(e_l)
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            torch.distributed.all_reduce(stats, group=process_group)
+        cnt = stats[3]
+        mean = torch.complex(stats[0], stats[1]) / cnt
+        variance = stats[2] / cnt - (mean.real ** 2 + mean.imag ** 2)
+        return e_l, mean, variance
+    return _total
+
+
+# ---- DMC -------------------------------------------------------------------------------
+def propose_drift_diffusion(f, tstep: float, ndim: int, nelectrons: int, batch_size: int):
+    """DMC/drift_diffusion.py:25-107 -> (new_data, tdamp, grad_eff_old, grad_new_eff_s).
+    `f` is signed_network's apply; key as in main_monte_carlo (one sweep)."""
+    def drift_diffusion(params, key, data: AINetData):
+        eng = _engine_of(f, params, data)
+        pos = _positions(eng, data).clone()
+        g1, g2, u = _sweep_rand(eng, key, pos.shape[0], tstep, 0)
+        out = eng.vmc_sweep(pos, g1, g2, u, tstep, signed_ratio=True, want_accept=True, want_drift=True,
+                            want_aux=True)
+        tdamp = out['aux'][0] / out['aux'][1]                                 # quirk Q19
+        _, _, g_s = eng.psi(pos, mode=1)
+        v2 = torch.sum(g_s ** 2)
+        taueff = (torch.sqrt(1 + 2 * tstep * 0.25 * v2) - 1) / (0.25 * v2)     # limdrift, batch-global (Q6)
+        return replace(data, positions=pos), tdamp, out['grad_eff_old'], g_s * taueff, out['accept']
+    return drift_diffusion
+
+
+def comput_S(engine: WalkerEngine, e_trial, e_est, branchcut, drift, tau, eloc, process_group=None):
+    """DMC/S_matrix.py:4-25; `drift` is the limited drift whose square the reference passes as v2."""
+    m = engine.dmc_ecut_min(eloc, float(e_est), branchcut)
+    if process_group is not None:
+        torch.distributed.all_reduce(m, op=torch.distributed.ReduceOp.MIN, group=process_group)   # quirk Q20
+    return engine.dmc_s(eloc, drift, float(e_trial), float(e_est), m, tau)
+
+
+def branch(engine: WalkerEngine, weights: torch.Tensor, key):
+    """DMC/branch.py:10-34 -> (new weight scalar, newinds); `key` is the uniform u in [0,1)."""
+    return engine.branch_comb(weights, float(key))

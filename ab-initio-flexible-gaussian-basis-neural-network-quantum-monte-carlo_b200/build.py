@@ -1,0 +1,80 @@
+"""Builds libaiqmc_b200.so (sm_100a) in-tree: one translation unit per (n_elec, n_atoms)
+instantiation, compiled in parallel with nvcc, linked into a plain CUDA-runtime shared
+library that exports the C ABI of include/aiqmc_b200.h."""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import hashlib
+import os
+import re
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+BUILD = os.path.join(CSRC, "build")
+LIB = os.path.join(HERE, "libaiqmc_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+
+def systems():
+    txt = open(os.path.join(CSRC, "dispatch.h")).read()
+    body = txt[txt.index("#define AIQMC_FOR_EACH_SYSTEM"):]
+    return [(int(a), int(b)) for a, b in re.findall(r"X\((\d+),\s*(\d+)\)", body)]
+
+
+def _sources_digest():
+    h = hashlib.sha256()
+    for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
+        for name in sorted(os.listdir(root)):
+            p = os.path.join(root, name)
+            if os.path.isfile(p) and name.endswith((".cu", ".cuh", ".h")):
+                h.update(name.encode())
+                h.update(open(p, "rb").read())
+    h.update(" ".join(FLAGS + ARCH).encode())
+    return h.hexdigest()
+
+
+def _compile(src, obj, log):
+    cmd = [NVCC] + ARCH + FLAGS + ["-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    with open(log, "w") as f:
+        f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+    return obj
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(BUILD, exist_ok=True)
+    digest = _sources_digest()
+    stamp = os.path.join(BUILD, "stamp.txt")
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
+        return LIB
+    jobs = []
+    for n, a in systems():
+        src = os.path.join(BUILD, f"inst_{n}_{a}.cu")
+        with open(src, "w") as f:
+            f.write('#include "../engine_impl.cuh"\n'
+                    f'extern "C" const aiqmc::OpsTable* aiqmc_ops_{n}_{a}() {{ return aiqmc::Launch<{n}, {a}>::table(); }}\n')
+        jobs.append((src, os.path.join(BUILD, f"inst_{n}_{a}.o"), os.path.join(BUILD, f"inst_{n}_{a}.log")))
+    for name in ("abi", "wsizes"):
+        jobs.append((os.path.join(CSRC, name + ".cu"), os.path.join(BUILD, name + ".o"),
+                     os.path.join(BUILD, name + ".log")))
+    with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(lambda j: _compile(*j), jobs))
+    cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(stamp, "w") as f:
+        f.write(digest)
+    if verbose:
+        print("built", LIB, file=sys.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)

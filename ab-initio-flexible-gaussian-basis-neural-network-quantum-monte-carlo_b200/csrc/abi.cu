@@ -1,0 +1,289 @@
+// abi.cu -- extern "C" entry points declared in include/aiqmc_b200.h: dispatch on
+// (n_elec, n_atoms) into the per-system translation units, plus the system-size independent
+// kernels (energy statistics, DMC S / weights / comb / gather).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include "../../include/aiqmc_b200.h"
+#include "dispatch.h"
+#include "ops_table.h"
+#include "psi_core.cuh"
+
+namespace aiqmc {
+int g_last_cuda_error = 0;
+
+int64_t sweep_ws_bytes_rt(int n, int64_t B);
+int64_t energy_ws_bytes_rt(int n, int a, int64_t B, int with_ecp);
+}  // namespace aiqmc
+
+#define X(NE, NA) extern "C" const aiqmc::OpsTable* aiqmc_ops_##NE##_##NA();
+AIQMC_FOR_EACH_SYSTEM(X)
+#undef X
+
+using aiqmc::g_last_cuda_error;
+
+static const aiqmc::OpsTable* find_ops(int n, int a) {
+#define X(NE, NA) if (n == NE && a == NA) return aiqmc_ops_##NE##_##NA();
+  AIQMC_FOR_EACH_SYSTEM(X)
+#undef X
+  return nullptr;
+}
+
+#define AQ_CUDA_OK(call)                                   \
+  do {                                                     \
+    cudaError_t e_ = (call);                               \
+    if (e_ != cudaSuccess) { g_last_cuda_error = (int)e_; return AIQMC_E_CUDA; } \
+  } while (0)
+
+static bool sys_ok(const AiqmcSystem* s) {
+  if (!s || s->n_elec < 2 || s->n_elec > AIQMC_MAX_ELEC || s->n_atoms < 1 || s->n_atoms > AIQMC_MAX_ATOMS) return false;
+  if (s->n_up <= 0 || s->n_dn <= 0 || s->n_up + s->n_dn != s->n_elec) return false;
+  if (s->n_up_rows < 0 || s->n_up_rows > s->n_elec) return false;
+  for (int k = 0; k < s->n_elec; ++k)
+    if (s->sigma[k] < 0 || s->sigma[k] >= s->n_elec) return false;
+  return true;
+}
+
+// ------------------------------------------------------------------ generic kernels
+namespace {
+constexpr int kBig = 1024;
+
+__device__ __forceinline__ double wsum(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double wmin(double v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// [sum Re E, sum Im E, sum |E|^2, count]; single CTA, fixed summation order (deterministic)
+__global__ void __launch_bounds__(kBig) k_energy_stats(const double* __restrict__ e, int stride, int64_t B,
+                                                       double* __restrict__ out) {
+  __shared__ double red[3][kBig / 32];
+  double sr = 0.0, si = 0.0, s2 = 0.0;
+  for (int64_t b = threadIdx.x; b < B; b += kBig) {
+    const double re = e[b * stride], im = stride > 1 ? e[b * stride + 1] : 0.0;
+    sr += re; si += im; s2 += re * re + im * im;
+  }
+  sr = wsum(sr); si = wsum(si); s2 = wsum(s2);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sr; red[1][threadIdx.x >> 5] = si; red[2][threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b2 = 0, c = 0;
+    for (int i = 0; i < kBig / 32; ++i) { a += red[0][i]; b2 += red[1][i]; c += red[2][i]; }
+    out[0] = a; out[1] = b2; out[2] = c; out[3] = (double)B;
+  }
+}
+
+__global__ void __launch_bounds__(kBig) k_ecut_min(const double* __restrict__ e, int stride, int64_t B, double e_est,
+                                                   const double* __restrict__ branchcut, double* __restrict__ out) {
+  __shared__ double red[kBig / 32];
+  double m = INFINITY;
+  for (int64_t b = threadIdx.x; b < B; b += kBig) m = fmin(m, fmin(fabs(e_est - e[b * stride]), branchcut[b]));
+  m = wmin(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r = INFINITY;
+    for (int i = 0; i < kBig / 32; ++i) r = fmin(r, red[i]);
+    out[0] = r;
+  }
+}
+
+__global__ void k_dmc_s(const double* __restrict__ e, int stride, const double* __restrict__ drift, int64_t B, int n,
+                        double e_trial, double e_est, const double* __restrict__ ecut_min, double tau,
+                        double* __restrict__ s_out) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double v2 = 0.0;
+  for (int k = 0; k < 3 * n; ++k) { const double g = drift[b * 3 * n + k]; v2 += g * g; }
+  const double diff = e_est - e[b * stride];
+  const double sgn = diff > 0.0 ? 1.0 : (diff < 0.0 ? -1.0 : 0.0);
+  const double q = v2 * tau / n;
+  s_out[b] = e_trial - e_est + (ecut_min[0] * sgn) / (1.0 + q * q);   // S_matrix.py:23-25
+}
+
+__global__ void k_dmc_weights(double* __restrict__ w, const double* __restrict__ so, const double* __restrict__ sn,
+                              int64_t B, double tau, double tdamp) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) w[b] = exp(tau * tdamp * (0.5 * sn[b] + 0.5 * so[b])) * w[b];   // dmc.py:91-92
+}
+
+// inclusive cumsum by one CTA: per-thread contiguous chunks + scan of chunk totals
+__global__ void __launch_bounds__(kBig) k_cumsum(const double* __restrict__ w, int64_t B, double* __restrict__ cum) {
+  __shared__ double tot[kBig];
+  const int64_t chunk = (B + kBig - 1) / kBig;
+  const int64_t lo = (int64_t)threadIdx.x * chunk, hi = lo + chunk < B ? lo + chunk : B;
+  double s = 0.0;
+  for (int64_t b = lo; b < hi; ++b) s += w[b];
+  tot[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double run = 0.0;
+    for (int i = 0; i < kBig; ++i) { const double t = tot[i]; tot[i] = run; run += t; }
+  }
+  __syncthreads();
+  double run = tot[threadIdx.x];
+  for (int64_t b = lo; b < hi; ++b) { run += w[b]; cum[b] = run; }
+}
+
+// newinds = searchsorted(cum, (u*wtot + k*wtot/B) mod wtot), side='left'  (branch.py:21-23)
+__global__ void k_comb(const double* __restrict__ cum, int64_t B, double u, int32_t* __restrict__ newinds,
+                       double* __restrict__ new_weight) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= B) return;
+  const double wtot = cum[B - 1];
+  const double base = u * wtot;
+  double v = base + (double)k * (wtot / (double)B);
+  v = fmod(v, wtot);
+  if (v < 0.0) v += wtot;
+  int64_t lo = 0, hi = B;
+  while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (cum[mid] < v) lo = mid + 1; else hi = mid; }
+  newinds[k] = (int32_t)lo;
+  if (k == 0) new_weight[0] = wtot / (double)B;
+}
+
+__global__ void k_gather(const double* __restrict__ in, const int32_t* __restrict__ idx, int64_t B, int row,
+                         double* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * row) return;
+  const int64_t b = t / row;
+  const int c = (int)(t - b * row);
+  out[t] = in[(int64_t)idx[b] * row + c];
+}
+}  // namespace
+
+// ------------------------------------------------------------------ C ABI
+extern "C" {
+
+int aiqmc_param_layout(int32_t n_elec, int32_t n_atoms, AiqmcLayout* out) {
+  if (!out || n_elec < 1 || n_elec > AIQMC_MAX_ELEC || n_atoms < 1 || n_atoms > AIQMC_MAX_ATOMS) return AIQMC_E_BADARG;
+  *out = aiqmc::make_layout(n_elec, n_atoms);
+  return AIQMC_OK;
+}
+int aiqmc_supported(int32_t n_elec, int32_t n_atoms) { return find_ops(n_elec, n_atoms) != nullptr; }
+int aiqmc_last_cuda_error(void) { return g_last_cuda_error; }
+const char* aiqmc_version(void) { return "aiqmc_b200 0.1 (sm_100a, fp64, thread-per-configuration)"; }
+
+static int psi_any(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_cfg, int mode,
+                   double* phase, double* logabs, double* grad, double* lap, void* stream) {
+  if (!sys_ok(sys) || !params || (n_cfg > 0 && (!pos || !phase || !logabs)) || n_cfg < 0) return AIQMC_E_BADARG;
+  if (mode >= 1 && n_cfg > 0 && !grad) return AIQMC_E_BADARG;
+  if (mode == 2 && n_cfg > 0 && !lap) return AIQMC_E_BADARG;
+  const aiqmc::OpsTable* ops = find_ops(sys->n_elec, sys->n_atoms);
+  if (!ops) return AIQMC_E_UNSUPPORTED;
+  return ops->psi(sys, params, pos, n_cfg, mode, phase, logabs, grad, lap, (cudaStream_t)stream);
+}
+int aiqmc_psi_fwd(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_cfg, double* phase,
+                  double* logabs, void* stream) {
+  return psi_any(sys, params, pos, n_cfg, 0, phase, logabs, nullptr, nullptr, stream);
+}
+int aiqmc_psi_grad(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_cfg, double* phase,
+                   double* logabs, double* grad, void* stream) {
+  return psi_any(sys, params, pos, n_cfg, 1, phase, logabs, grad, nullptr, stream);
+}
+int aiqmc_psi_fwdlap(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_cfg, double* phase,
+                     double* logabs, double* grad, double* lap, void* stream) {
+  return psi_any(sys, params, pos, n_cfg, 2, phase, logabs, grad, lap, stream);
+}
+
+int64_t aiqmc_vmc_workspace_bytes(const AiqmcSystem* sys, int64_t n_walkers) {
+  if (!sys_ok(sys) || n_walkers < 0) return AIQMC_E_BADARG;
+  return aiqmc::sweep_ws_bytes_rt(sys->n_elec, n_walkers);
+}
+int aiqmc_vmc_sweep(const AiqmcSystem* sys, const double* params, double* pos, const double* gauss1,
+                    const double* gauss2, const double* rnd, int64_t n_walkers, double tstep, double acyrus,
+                    int32_t signed_ratio, uint8_t* accept, double* grad_eff_old, double* aux_out, void* workspace,
+                    int64_t workspace_bytes, void* stream) {
+  if (!sys_ok(sys) || !params || n_walkers < 0 || !(tstep > 0.0) || !(acyrus > 0.0)) return AIQMC_E_BADARG;
+  if (n_walkers > 0 && (!pos || !gauss1 || !gauss2 || !rnd || !workspace)) return AIQMC_E_BADARG;
+  const aiqmc::OpsTable* ops = find_ops(sys->n_elec, sys->n_atoms);
+  if (!ops) return AIQMC_E_UNSUPPORTED;
+  return ops->sweep(sys, params, pos, gauss1, gauss2, rnd, n_walkers, tstep, acyrus, signed_ratio, accept,
+                    grad_eff_old, aux_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int64_t aiqmc_energy_workspace_bytes(const AiqmcSystem* sys, int64_t n_walkers, int32_t with_ecp) {
+  if (!sys_ok(sys) || n_walkers < 0) return AIQMC_E_BADARG;
+  return aiqmc::energy_ws_bytes_rt(sys->n_elec, sys->n_atoms, n_walkers, with_ecp);
+}
+int aiqmc_local_energy_ae(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_walkers,
+                          double* e_l, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!sys_ok(sys) || !params || n_walkers < 0 || (n_walkers > 0 && (!pos || !e_l || !workspace))) return AIQMC_E_BADARG;
+  const aiqmc::OpsTable* ops = find_ops(sys->n_elec, sys->n_atoms);
+  if (!ops) return AIQMC_E_UNSUPPORTED;
+  return ops->energy(sys, nullptr, params, pos, nullptr, n_walkers, e_l, workspace, workspace_bytes,
+                     (cudaStream_t)stream);
+}
+int aiqmc_local_energy_ecp(const AiqmcSystem* sys, const AiqmcEcp* ecp, const double* params, const double* pos,
+                           const double* rot, int64_t n_walkers, double* e_l, void* workspace,
+                           int64_t workspace_bytes, void* stream) {
+  if (!sys_ok(sys) || !ecp || !params || n_walkers < 0) return AIQMC_E_BADARG;
+  if (n_walkers > 0 && (!pos || !rot || !e_l || !workspace)) return AIQMC_E_BADARG;
+  if (ecp->k_loc < 0 || ecp->k_loc > AIQMC_ECP_MAX_K || ecp->k_nl < 0 || ecp->k_nl > AIQMC_ECP_MAX_K ||
+      ecp->n_l < 1 || ecp->n_l > AIQMC_ECP_MAX_L) return AIQMC_E_BADARG;
+  const aiqmc::OpsTable* ops = find_ops(sys->n_elec, sys->n_atoms);
+  if (!ops) return AIQMC_E_UNSUPPORTED;
+  return ops->energy(sys, ecp, params, pos, rot, n_walkers, e_l, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int aiqmc_energy_stats(const double* e_l, int32_t e_l_stride, int64_t n_walkers, double* stats, void* stream) {
+  if (!e_l || !stats || n_walkers < 0 || (e_l_stride != 1 && e_l_stride != 2)) return AIQMC_E_BADARG;
+  k_energy_stats<<<1, kBig, 0, (cudaStream_t)stream>>>(e_l, e_l_stride, n_walkers, stats);
+  AQ_CUDA_OK(cudaGetLastError());
+  return AIQMC_OK;
+}
+
+int aiqmc_dmc_ecut_min(const double* e_l, int32_t e_l_stride, int64_t n_walkers, double e_est, const double* branchcut,
+                       double* ecut_min, void* stream) {
+  if (!e_l || !branchcut || !ecut_min || n_walkers < 0 || (e_l_stride != 1 && e_l_stride != 2)) return AIQMC_E_BADARG;
+  k_ecut_min<<<1, kBig, 0, (cudaStream_t)stream>>>(e_l, e_l_stride, n_walkers, e_est, branchcut, ecut_min);
+  AQ_CUDA_OK(cudaGetLastError());
+  return AIQMC_OK;
+}
+int aiqmc_dmc_s(const double* e_l, int32_t e_l_stride, const double* drift, int64_t n_walkers, int32_t n_elec,
+                double e_trial, double e_est, const double* ecut_min, double tau, double* s_out, void* stream) {
+  if (!e_l || !drift || !ecut_min || !s_out || n_walkers < 0 || n_elec < 1 || (e_l_stride != 1 && e_l_stride != 2))
+    return AIQMC_E_BADARG;
+  if (n_walkers == 0) return AIQMC_OK;
+  k_dmc_s<<<(unsigned)((n_walkers + 255) / 256), 256, 0, (cudaStream_t)stream>>>(e_l, e_l_stride, drift, n_walkers,
+                                                                                 n_elec, e_trial, e_est, ecut_min, tau,
+                                                                                 s_out);
+  AQ_CUDA_OK(cudaGetLastError());
+  return AIQMC_OK;
+}
+int aiqmc_dmc_weights(double* weights, const double* s_old, const double* s_new, int64_t n_walkers, double tau,
+                      double tdamp, void* stream) {
+  if (!weights || !s_old || !s_new || n_walkers < 0) return AIQMC_E_BADARG;
+  if (n_walkers == 0) return AIQMC_OK;
+  k_dmc_weights<<<(unsigned)((n_walkers + 255) / 256), 256, 0, (cudaStream_t)stream>>>(weights, s_old, s_new,
+                                                                                       n_walkers, tau, tdamp);
+  AQ_CUDA_OK(cudaGetLastError());
+  return AIQMC_OK;
+}
+
+int64_t aiqmc_branch_workspace_bytes(int64_t n_walkers) { return n_walkers < 0 ? AIQMC_E_BADARG : (n_walkers + 32) * 8; }
+int aiqmc_branch_comb(const double* weights, int64_t n_walkers, double u, int32_t* newinds, double* new_weight,
+                      void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!weights || !newinds || !new_weight || !workspace || n_walkers <= 0) return AIQMC_E_BADARG;
+  if (workspace_bytes < aiqmc_branch_workspace_bytes(n_walkers)) return AIQMC_E_WORKSPACE;
+  double* cum = (double*)workspace;
+  k_cumsum<<<1, kBig, 0, (cudaStream_t)stream>>>(weights, n_walkers, cum);
+  k_comb<<<(unsigned)((n_walkers + 255) / 256), 256, 0, (cudaStream_t)stream>>>(cum, n_walkers, u, newinds, new_weight);
+  AQ_CUDA_OK(cudaGetLastError());
+  return AIQMC_OK;
+}
+int aiqmc_gather_walkers(const double* pos_in, const int32_t* newinds, int64_t n_walkers, int32_t row_doubles,
+                         double* pos_out, void* stream) {
+  if (!pos_in || !newinds || !pos_out || n_walkers < 0 || row_doubles < 1) return AIQMC_E_BADARG;
+  if (n_walkers == 0) return AIQMC_OK;
+  const int64_t nt = n_walkers * row_doubles;
+  k_gather<<<(unsigned)((nt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pos_in, newinds, n_walkers, row_doubles,
+                                                                           pos_out);
+  AQ_CUDA_OK(cudaGetLastError());
+  return AIQMC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,479 @@
+// engine_impl.cuh -- sm_100a kernels of the walker engine for one (n_elec, n_atoms) pair.
+// Included by the generated per-system translation units (build/inst_N_A.cu).
+//
+// Thread mapping (v1): one thread = one electron configuration.  A VMC sweep evaluates
+// B*(N+1) configurations, the ccECP energy B*50*N*A more, so even the smallest system fills
+// the 148 SMs many times over.  Parameters (<= ~13k doubles) are staged once per CTA in
+// shared memory and read as warp-wide broadcasts.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "fastmath.cuh"
+#include "ops_table.h"
+#include "psi_core.cuh"
+
+namespace aiqmc {
+
+constexpr int kThreads = 128;       // threads per CTA for the per-configuration kernels
+constexpr int kRedThreads = 256;
+
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Deterministic block sum; result valid in thread 0.
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v, double* red /* THREADS/32 doubles */) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < THREADS / 32; ++i) r += red[i];
+  return r;
+}
+
+template <int NE, int NA>
+__device__ __forceinline__ const double* stage_params(const double* __restrict__ params, double* sP) {
+  constexpr int total = make_layout(NE, NA).total;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) sP[i] = params[i];
+  __syncthreads();
+  return sP;
+}
+
+// ---------------------------------------------------------------------------------------
+// signed_network forward / gradient / forward-Laplacian on arbitrary configurations
+// ---------------------------------------------------------------------------------------
+template <int NE, int NA, int MODE>
+__global__ void __launch_bounds__(kThreads) k_psi(AiqmcSystem sys, const double* __restrict__ params,
+                                                  const double* __restrict__ pos, int64_t n_cfg,
+                                                  double* __restrict__ phase, double* __restrict__ logabs,
+                                                  double* __restrict__ grad, double* __restrict__ lap) {
+  extern __shared__ double sP[];
+  const double* P = stage_params<NE, NA>(params, sP);
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_cfg) return;
+  double x[3 * NE];
+  for (int q = 0; q < 3 * NE; ++q) x[q] = pos[t * 3 * NE + q];
+  double ph, la;
+  if (MODE == 0) {
+    Psi<NE, NA>::eval_value(sys, P, x, ph, la);
+  } else {
+    double g[3 * NE], lp = 0.0;
+    Psi<NE, NA>::template eval_deriv<(MODE == 2)>(sys, P, x, ph, la, g, lp);
+    for (int q = 0; q < 3 * NE; ++q) grad[t * 3 * NE + q] = g[q];
+    if (MODE == 2) lap[t] = lp;
+  }
+  phase[t] = ph;
+  logabs[t] = la;
+}
+
+// ---------------------------------------------------------------------------------------
+// VMC sweep (VMC/VMCmcstep.py:28-111), split at the two batch-global limdrift sums (quirk Q6)
+// ---------------------------------------------------------------------------------------
+struct SweepWs {           // carved out of the caller's workspace
+  double* grad;            // (B,3N)   grad log|psi| at x1
+  double* logabs1;         // (B)
+  double* logabs2;         // (B,N)
+  double* gnew;            // (B,N,3)  components 3i..3i+2 of grad log|psi| at x2[b,i]
+  double* xprop;           // (B,N,3)  proposed position of electron i
+  double* partials;        // (nblocks_max, 4)
+  double* scal;            // [0]=v2(grad x1) [1]=v2(grad x2) [2]=sum x_new [3]=sum x_prop
+};
+
+__host__ __device__ inline int64_t align256(int64_t v) { return (v + 255) & ~int64_t(255); }
+
+inline int64_t sweep_ws_bytes(int n, int64_t B) {
+  const int64_t blocks = (B * n + kThreads - 1) / kThreads + 1;
+  return align256(B * 3 * n * 8) + align256(B * 8) + align256(B * n * 8) + 2 * align256(B * n * 3 * 8) +
+         align256(blocks * 4 * 8) + 256;
+}
+
+inline SweepWs carve_sweep_ws(void* ws, int n, int64_t B) {
+  char* p = (char*)ws;
+  SweepWs w;
+  const int64_t blocks = (B * n + kThreads - 1) / kThreads + 1;
+  w.grad = (double*)p; p += align256(B * 3 * n * 8);
+  w.logabs1 = (double*)p; p += align256(B * 8);
+  w.logabs2 = (double*)p; p += align256(B * n * 8);
+  w.gnew = (double*)p; p += align256(B * n * 3 * 8);
+  w.xprop = (double*)p; p += align256(B * n * 3 * 8);
+  w.partials = (double*)p; p += align256(blocks * 4 * 8);
+  w.scal = (double*)p;
+  return w;
+}
+
+template <int NE, int NA>
+__global__ void __launch_bounds__(kThreads) k_sweep_grad(AiqmcSystem sys, const double* __restrict__ params,
+                                                         const double* __restrict__ pos, int64_t B, SweepWs w) {
+  extern __shared__ double sP[];
+  __shared__ double red[kThreads / 32];
+  const double* P = stage_params<NE, NA>(params, sP);
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double v2 = 0.0;
+  if (b < B) {
+    double x[3 * NE], g[3 * NE], ph, la, lp;
+    for (int q = 0; q < 3 * NE; ++q) x[q] = pos[b * 3 * NE + q];
+    Psi<NE, NA>::template eval_deriv<false>(sys, P, x, ph, la, g, lp);
+    for (int q = 0; q < 3 * NE; ++q) { w.grad[b * 3 * NE + q] = g[q]; v2 += g[q] * g[q]; }
+    w.logabs1[b] = la;
+  }
+  const double s = block_sum<kThreads>(v2, red);
+  if (threadIdx.x == 0) w.partials[blockIdx.x * 4 + 0] = s;
+}
+
+// sums `nparts` rows of partials[:, col] in a fixed order -> out
+static __global__ void __launch_bounds__(kRedThreads) k_reduce_partials(const double* __restrict__ partials, int nparts,
+                                                                 int col0, int ncols, double* __restrict__ out,
+                                                                 int out0) {
+  __shared__ double red[kRedThreads / 32];
+  for (int c = 0; c < ncols; ++c) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += kRedThreads) v += partials[i * 4 + col0 + c];
+    const double s = block_sum<kRedThreads>(v, red);
+    if (threadIdx.x == 0) out[out0 + c] = s;
+  }
+}
+
+__device__ __forceinline__ double taueff_of(double v2, double tau, double acyrus) {
+  return (sqrt(1.0 + 2.0 * tau * acyrus * v2) - 1.0) / (acyrus * v2);   // VMCmcstep.py:11-14
+}
+
+template <int NE, int NA>
+__global__ void __launch_bounds__(kThreads) k_sweep_moved(AiqmcSystem sys, const double* __restrict__ params,
+                                                          const double* __restrict__ pos,
+                                                          const double* __restrict__ gauss1, int64_t B, double tau,
+                                                          double acyrus, SweepWs w) {
+  extern __shared__ double sP[];
+  __shared__ double red[kThreads / 32];
+  const double* P = stage_params<NE, NA>(params, sP);
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double v2 = 0.0;
+  if (t < B * NE) {
+    const int64_t b = t / NE;
+    const int i = (int)(t - b * NE);
+    const double te = taueff_of(w.scal[0], tau, acyrus);
+    double x[3 * NE], g[3 * NE], ph, la, lp;
+    for (int q = 0; q < 3 * NE; ++q) x[q] = pos[b * 3 * NE + q];
+    for (int c = 0; c < 3; ++c) {
+      // g = grad_eff * tstep + gauss ; x2 = x1 + g on electron i only   (VMCmcstep.py:60-78)
+      const double step = (w.grad[b * 3 * NE + 3 * i + c] * te) * tau + gauss1[b * 3 * NE + 3 * i + c];
+      const double xn = step + x[3 * i + c];
+      x[3 * i + c] = xn;
+      w.xprop[t * 3 + c] = xn;
+    }
+    Psi<NE, NA>::template eval_deriv<false>(sys, P, x, ph, la, g, lp);
+    for (int q = 0; q < 3 * NE; ++q) v2 += g[q] * g[q];
+    for (int c = 0; c < 3; ++c) w.gnew[t * 3 + c] = g[3 * i + c];
+    w.logabs2[t] = la;
+  }
+  const double s = block_sum<kThreads>(v2, red);
+  if (threadIdx.x == 0) w.partials[blockIdx.x * 4 + 1] = s;
+}
+
+// accept/reject (VMCmcstep.py:80-109, walkers_accept :18-25); HBM-bound, 1 thread per (b,i)
+static __global__ void __launch_bounds__(kRedThreads) k_sweep_accept(int n, double* __restrict__ pos,
+                                                              const double* __restrict__ gauss2,
+                                                              const double* __restrict__ rnd, int64_t B, double tau,
+                                                              double acyrus, int signed_ratio,
+                                                              uint8_t* __restrict__ accept,
+                                                              double* __restrict__ grad_eff_old, SweepWs w) {
+  __shared__ double red[kRedThreads / 32];
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double s_new = 0.0, s_prop = 0.0;
+  if (t < B * n) {
+    const int64_t b = t / n;
+    const int i = (int)(t - b * n);
+    const double te_old = taueff_of(w.scal[0], tau, acyrus), te_new = taueff_of(w.scal[1], tau, acyrus);
+    double tp = 0.0;
+    for (int c = 0; c < 3; ++c) {
+      const double ge = w.grad[b * 3 * n + 3 * i + c] * te_old;
+      const double gn = w.gnew[t * 3 + c] * te_new;
+      const double g2 = gauss2[(b * n + i) * 3 * n + 3 * i + c];
+      const double fwd = g2 * g2;
+      const double bw = g2 + (ge + gn) * tau;
+      tp += exp((fwd - bw * bw) / (2.0 * tau));
+      if (grad_eff_old) grad_eff_old[b * 3 * n + 3 * i + c] = ge;
+    }
+    const double ratio = exp(w.logabs2[t] - w.logabs1[b]);
+    double acc = fabs(ratio) * fabs(ratio) * tp;
+    if (signed_ratio) acc *= (ratio > 0.0) ? 1.0 : (ratio < 0.0 ? -1.0 : 0.0);
+    const bool ok = acc > rnd[t];
+    for (int c = 0; c < 3; ++c) {
+      const double xp = w.xprop[t * 3 + c];
+      const double xo = pos[b * 3 * n + 3 * i + c];
+      const double xn = ok ? xp : xo;
+      if (ok) pos[b * 3 * n + 3 * i + c] = xp;
+      s_new += xn;
+      s_prop += xp;
+    }
+    if (accept) accept[t] = ok ? 1 : 0;
+  }
+  const double a = block_sum<kRedThreads>(s_new, red);
+  const double c2 = block_sum<kRedThreads>(s_prop, red);
+  if (threadIdx.x == 0) { w.partials[blockIdx.x * 4 + 2] = a; w.partials[blockIdx.x * 4 + 3] = c2; }
+}
+
+// ---------------------------------------------------------------------------------------
+// local energy (Energy/hamiltonian.py:236-260, Energy/pphamiltonian.py:130-190)
+// ---------------------------------------------------------------------------------------
+struct EnergyWs {
+  double* base;      // (B)    KE + Coulomb (+ local ECP channel)
+  double* logabs;    // (B)    denominator of the ECP "ratio" (quirk Q12)
+  double* phase;     // (B)
+  double* gnorm;     // (B,4)  Frobenius norm of each rotated point group (quirk Q14)
+  double* vl;        // (B,N,A,4)  v_l(r_ia)
+  double* epp;       // (B,2)  non-local energy accumulator (re, im)
+};
+
+inline int64_t energy_ws_bytes(int n, int a, int64_t B, int with_ecp) {
+  int64_t s = align256(B * 8);
+  if (with_ecp) s += 2 * align256(B * 8) + align256(B * 4 * 8) + align256(B * n * a * 4 * 8) + align256(B * 2 * 8);
+  return s;
+}
+
+inline EnergyWs carve_energy_ws(void* ws, int n, int a, int64_t B) {
+  char* p = (char*)ws;
+  EnergyWs w;
+  w.base = (double*)p; p += align256(B * 8);
+  w.logabs = (double*)p; p += align256(B * 8);
+  w.phase = (double*)p; p += align256(B * 8);
+  w.gnorm = (double*)p; p += align256(B * 4 * 8);
+  w.vl = (double*)p; p += align256(B * n * a * 4 * 8);
+  w.epp = (double*)p;
+  return w;
+}
+
+static __constant__ AiqmcEcp c_ecp;   // one ECP table per translation unit (per system instantiation)
+
+__device__ __forceinline__ int quad_group(int p) { return p < 6 ? 0 : p < 18 ? 1 : p < 26 ? 2 : 3; }
+
+template <int NE, int NA, bool ECP>
+__global__ void __launch_bounds__(kThreads) k_energy_base(AiqmcSystem sys, const double* __restrict__ params,
+                                                          const double* __restrict__ pos,
+                                                          const double* __restrict__ rot, int64_t B,
+                                                          double* __restrict__ e_out, EnergyWs w) {
+  extern __shared__ double sP[];
+  const double* P = stage_params<NE, NA>(params, sP);
+  constexpr AiqmcLayout L = make_layout(NE, NA);
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double x[3 * NE], g[3 * NE], ph, la, lp;
+  for (int q = 0; q < 3 * NE; ++q) x[q] = pos[b * 3 * NE + q];
+  Psi<NE, NA>::template eval_deriv<true>(sys, P, x, ph, la, g, lp);
+  double g2 = 0.0;
+  for (int q = 0; q < 3 * NE; ++q) g2 += g[q] * g[q];
+  double e = -0.5 * lp - 0.5 * g2;                                // pphamiltonian.py:100-102
+  for (int i = 0; i < NE; ++i)                                    // potential_electron_electron
+    for (int j = i + 1; j < NE; ++j) {
+      const double dx = x[3 * i] - x[3 * j], dy = x[3 * i + 1] - x[3 * j + 1], dz = x[3 * i + 2] - x[3 * j + 2];
+      e += 1.0 / sqrt(dx * dx + dy * dy + dz * dz);
+    }
+  for (int a = 0; a < NA; ++a)                                    // potential_nuclear_nuclear
+    for (int c = a + 1; c < NA; ++c) {
+      const double dx = P[L.atoms + 3 * a] - P[L.atoms + 3 * c], dy = P[L.atoms + 3 * a + 1] - P[L.atoms + 3 * c + 1],
+                   dz = P[L.atoms + 3 * a + 2] - P[L.atoms + 3 * c + 2];
+      e += P[L.charges + a] * P[L.charges + c] / sqrt(dx * dx + dy * dy + dz * dz);
+    }
+  for (int i = 0; i < NE; ++i)
+    for (int a = 0; a < NA; ++a) {
+      const double dx = x[3 * i] - P[L.atoms + 3 * a], dy = x[3 * i + 1] - P[L.atoms + 3 * a + 1],
+                   dz = x[3 * i + 2] - P[L.atoms + 3 * a + 2];
+      const double r = sqrt(dx * dx + dy * dy + dz * dz);
+      e += -P[L.charges + a] / r;            // potential_electron_nuclear / ECP local part1 (-Z_eff/r)
+      if (ECP) {
+        for (int k = 0; k < c_ecp.k_loc; ++k)                    // pseudopotential.py:95-101, r^(n-2)
+          e += c_ecp.local_coes[a][k] * pow(r, c_ecp.rn_local[a][k] - 2.0) * exp(-c_ecp.local_exps[a][k] * r * r);
+        for (int l = 0; l < AIQMC_ECP_MAX_L; ++l) {              // pseudopotential.py:150, r^n
+          double v = 0.0;
+          if (l < c_ecp.n_l)
+            for (int k = 0; k < c_ecp.k_nl; ++k)
+              v += c_ecp.non_local_coes[a][l][k] * pow(r, c_ecp.rn_non_local[a][l][k]) *
+                   exp(-c_ecp.non_local_exps[a][l][k] * r * r);
+          w.vl[((b * NE + i) * NA + a) * 4 + l] = v;
+        }
+      }
+    }
+  if (ECP) {
+    w.base[b] = e;
+    w.logabs[b] = la;
+    w.phase[b] = ph;
+    w.epp[2 * b] = 0.0;
+    w.epp[2 * b + 1] = 0.0;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int p = 0; p < AIQMC_NQUAD; ++p) {
+      double n2 = 0.0;
+      for (int l = 0; l < 3; ++l) {
+        double v = 0.0;
+        for (int k = 0; k < 3; ++k) v += c_ecp.quad_pts[p][k] * rot[b * 9 + 3 * k + l];
+        n2 += v * v;
+      }
+      acc[quad_group(p)] += n2;
+    }
+    for (int q = 0; q < 4; ++q) w.gnorm[4 * b + q] = sqrt(acc[q]);
+  } else {
+    e_out[b] = e;
+  }
+}
+
+// one thread = one quadrature point of one (electron, atom) pair of one walker
+template <int NE, int NA>
+__global__ void __launch_bounds__(kThreads) k_ecp_quad(AiqmcSystem sys, const double* __restrict__ params,
+                                                       const double* __restrict__ pos,
+                                                       const double* __restrict__ rot, int64_t B, EnergyWs w) {
+  extern __shared__ double sP[];
+  const double* P = stage_params<NE, NA>(params, sP);
+  constexpr AiqmcLayout L = make_layout(NE, NA);
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per_walker = (int64_t)NE * NA * AIQMC_NQUAD;
+  if (t >= B * per_walker) return;
+  const int64_t b = t / per_walker;
+  int rem = (int)(t - b * per_walker);
+  const int i = rem / (NA * AIQMC_NQUAD);
+  rem -= i * NA * AIQMC_NQUAD;
+  const int a = rem / AIQMC_NQUAD, p = rem - a * AIQMC_NQUAD;
+  const double* vl = w.vl + ((b * NE + i) * NA + a) * 4;
+  bool any = false;
+  for (int l = 0; l < AIQMC_ECP_MAX_L; ++l) any = any || (vl[l] != 0.0);
+  if (!any) return;                       // exact zero coefficient: contributes exactly 0
+  double x[3 * NE];
+  for (int q = 0; q < 3 * NE; ++q) x[q] = pos[b * 3 * NE + q];
+  double ae[3], nh[3];
+  for (int c = 0; c < 3; ++c) ae[c] = x[3 * i + c] - P[L.atoms + 3 * a + c];
+  const double r = sqrt(ae[0] * ae[0] + ae[1] * ae[1] + ae[2] * ae[2]);
+  for (int l = 0; l < 3; ++l) {           // Points = O @ rot   (pseudopotential.py:236-240)
+    double v = 0.0;
+    for (int k = 0; k < 3; ++k) v += c_ecp.quad_pts[p][k] * rot[b * 9 + 3 * k + l];
+    nh[l] = v;
+  }
+  double dot = 0.0;
+  for (int c = 0; c < 3; ++c) {
+    const double rc = r * nh[c];
+    dot += ae[c] * rc;
+    x[3 * i + c] = rc;                    // quirk Q13: absolute position r_ia * n_hat
+  }
+  const double cs = dot / (r * (r * w.gnorm[4 * b + quad_group(p)]));   // quirk Q14
+  double ph, la;
+  Psi<NE, NA>::eval_value(sys, P, x, ph, la);
+  // ratio = log psi(x') / log psi(x) * weight, complex logs (quirk Q12)
+  const double dr = w.logabs[b], di = w.phase[b];
+  const double inv = c_ecp.quad_wts[p] / (dr * dr + di * di);
+  const double rr = (la * dr + ph * di) * inv, ri = (ph * dr - la * di) * inv;
+  const double k4 = 0.07957747154594767;  // 1/(4 pi)
+  const double pl[4] = {k4, 3.0 * k4 * cs, 5.0 * k4 * 0.5 * (3.0 * cs * cs - 1.0),
+                        7.0 * k4 * 0.5 * (5.0 * cs * cs * cs - 3.0 * cs)};
+  double f = 0.0;
+  for (int l = 0; l < AIQMC_ECP_MAX_L; ++l) f += vl[l] * pl[l];
+  atomicAdd(&w.epp[2 * b], f * rr);
+  atomicAdd(&w.epp[2 * b + 1], f * ri);
+}
+
+static __global__ void k_energy_final(int64_t B, double* __restrict__ e_l, EnergyWs w) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  e_l[2 * b] = w.base[b] + w.epp[2 * b];
+  e_l[2 * b + 1] = w.epp[2 * b + 1];
+}
+
+// ---------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------
+#define AQ_CUDA_OK(call)                                   \
+  do {                                                     \
+    cudaError_t e_ = (call);                               \
+    if (e_ != cudaSuccess) { g_last_cuda_error = (int)e_; return AIQMC_E_CUDA; } \
+  } while (0)
+
+extern int g_last_cuda_error;
+
+template <int NE, int NA>
+struct Launch {
+  static constexpr int kSmem = make_layout(NE, NA).total * 8;
+
+  template <class K>
+  static cudaError_t prep(K kernel) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+  }
+
+  static int psi(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_cfg, int mode,
+                 double* phase, double* logabs, double* grad, double* lap, cudaStream_t st) {
+    if (n_cfg <= 0) return AIQMC_OK;
+    const unsigned grid = (unsigned)((n_cfg + kThreads - 1) / kThreads);
+    if (mode == 0) {
+      AQ_CUDA_OK(prep(k_psi<NE, NA, 0>));
+      k_psi<NE, NA, 0><<<grid, kThreads, kSmem, st>>>(*sys, params, pos, n_cfg, phase, logabs, grad, lap);
+    } else if (mode == 1) {
+      AQ_CUDA_OK(prep(k_psi<NE, NA, 1>));
+      k_psi<NE, NA, 1><<<grid, kThreads, kSmem, st>>>(*sys, params, pos, n_cfg, phase, logabs, grad, lap);
+    } else {
+      AQ_CUDA_OK(prep(k_psi<NE, NA, 2>));
+      k_psi<NE, NA, 2><<<grid, kThreads, kSmem, st>>>(*sys, params, pos, n_cfg, phase, logabs, grad, lap);
+    }
+    AQ_CUDA_OK(cudaGetLastError());
+    return AIQMC_OK;
+  }
+
+  static int sweep(const AiqmcSystem* sys, const double* params, double* pos, const double* gauss1,
+                   const double* gauss2, const double* rnd, int64_t B, double tau, double acyrus, int signed_ratio,
+                   uint8_t* accept, double* grad_eff_old, double* aux_out, void* ws, int64_t ws_bytes,
+                   cudaStream_t st) {
+    if (B <= 0) return AIQMC_OK;
+    if (ws_bytes < sweep_ws_bytes(NE, B)) return AIQMC_E_WORKSPACE;
+    SweepWs w = carve_sweep_ws(ws, NE, B);
+    const unsigned g1 = (unsigned)((B + kThreads - 1) / kThreads);
+    const unsigned g2 = (unsigned)((B * NE + kThreads - 1) / kThreads);
+    const unsigned g3 = (unsigned)((B * NE + kRedThreads - 1) / kRedThreads);
+    AQ_CUDA_OK(prep(k_sweep_grad<NE, NA>));
+    AQ_CUDA_OK(prep(k_sweep_moved<NE, NA>));
+    k_sweep_grad<NE, NA><<<g1, kThreads, kSmem, st>>>(*sys, params, pos, B, w);
+    k_reduce_partials<<<1, kRedThreads, 0, st>>>(w.partials, (int)g1, 0, 1, w.scal, 0);
+    k_sweep_moved<NE, NA><<<g2, kThreads, kSmem, st>>>(*sys, params, pos, gauss1, B, tau, acyrus, w);
+    k_reduce_partials<<<1, kRedThreads, 0, st>>>(w.partials, (int)g2, 1, 1, w.scal, 1);
+    k_sweep_accept<<<g3, kRedThreads, 0, st>>>(NE, pos, gauss2, rnd, B, tau, acyrus, signed_ratio, accept,
+                                               grad_eff_old, w);
+    k_reduce_partials<<<1, kRedThreads, 0, st>>>(w.partials, (int)g3, 2, 2, w.scal, 2);
+    if (aux_out) {
+      // aux_out = [sum x_new, sum x_prop, v2_old, v2_new]
+      AQ_CUDA_OK(cudaMemcpyAsync(aux_out, w.scal + 2, 2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      AQ_CUDA_OK(cudaMemcpyAsync(aux_out + 2, w.scal, 2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    AQ_CUDA_OK(cudaGetLastError());
+    return AIQMC_OK;
+  }
+
+  static int energy(const AiqmcSystem* sys, const AiqmcEcp* ecp, const double* params, const double* pos,
+                    const double* rot, int64_t B, double* e_l, void* ws, int64_t ws_bytes, cudaStream_t st) {
+    if (B <= 0) return AIQMC_OK;
+    const int with_ecp = ecp != nullptr;
+    if (ws_bytes < energy_ws_bytes(NE, NA, B, with_ecp)) return AIQMC_E_WORKSPACE;
+    EnergyWs w = carve_energy_ws(ws, NE, NA, B);
+    const unsigned g1 = (unsigned)((B + kThreads - 1) / kThreads);
+    if (!with_ecp) {
+      AQ_CUDA_OK(prep(k_energy_base<NE, NA, false>));
+      k_energy_base<NE, NA, false><<<g1, kThreads, kSmem, st>>>(*sys, params, pos, nullptr, B, e_l, w);
+    } else {
+      AQ_CUDA_OK(cudaMemcpyToSymbolAsync(c_ecp, ecp, sizeof(AiqmcEcp), 0, cudaMemcpyHostToDevice, st));
+      AQ_CUDA_OK(prep(k_energy_base<NE, NA, true>));
+      AQ_CUDA_OK(prep(k_ecp_quad<NE, NA>));
+      k_energy_base<NE, NA, true><<<g1, kThreads, kSmem, st>>>(*sys, params, pos, rot, B, e_l, w);
+      const int64_t nt = B * NE * NA * AIQMC_NQUAD;
+      const unsigned g2 = (unsigned)((nt + kThreads - 1) / kThreads);
+      k_ecp_quad<NE, NA><<<g2, kThreads, kSmem, st>>>(*sys, params, pos, rot, B, w);
+      k_energy_final<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(B, e_l, w);
+    }
+    AQ_CUDA_OK(cudaGetLastError());
+    return AIQMC_OK;
+  }
+
+  static const OpsTable* table() {
+    static const OpsTable t = {NE, NA, &Launch::psi, &Launch::sweep, &Launch::energy};
+    return &t;
+  }
+};
+
+}  // namespace aiqmc

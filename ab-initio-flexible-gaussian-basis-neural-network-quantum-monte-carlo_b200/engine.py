@@ -1,0 +1,189 @@
+"""Device-resident walker engine: thin, explicit wrapper over the C ABI.
+
+torch is used only for device memory, streams and (in throughput mode) the device RNG; every
+numerical operation of the hot path runs in the hand-written kernels of csrc/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Mapping, Optional
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from .system import AiqmcEcp, SystemSpec, pack_params
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class WalkerEngine:
+    """Owns the packed parameters + workspaces of one system on one GPU."""
+
+    def __init__(self, spec: SystemSpec, params: Optional[Mapping[str, Any]] = None, ecp: Optional[AiqmcEcp] = None,
+                 device: Optional[torch.device] = None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.AiqmcError("aiqmc_b200 needs a CUDA device; there is no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.spec = spec
+        self.sys = spec.c_struct()
+        self.n, self.a = spec.nelectrons, spec.natoms
+        if not self.lib.aiqmc_supported(self.n, self.a):
+            _lib.check(-1, f"system N={self.n}, A={self.a}")
+        self.layout = _lib.param_layout(self.n, self.a)
+        self.ecp = ecp
+        self.params_dev: Optional[torch.Tensor] = None
+        self._ws = {}
+        if params is not None:
+            self.set_params(params)
+
+    # ---- parameters -------------------------------------------------------------------
+    def set_params(self, params) -> None:
+        packed = params if isinstance(params, np.ndarray) else pack_params(self.layout, params, self.spec)
+        self.params_dev = torch.from_numpy(np.ascontiguousarray(packed)).to(self.device)
+
+    def _workspace(self, key: str, nbytes: int) -> torch.Tensor:
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws
+
+    def _pos(self, pos) -> torch.Tensor:
+        t = torch.as_tensor(pos)
+        return t.to(device=self.device, dtype=torch.float64).contiguous()
+
+    # ---- wavefunction -----------------------------------------------------------------
+    def psi(self, pos, mode: int = 0):
+        """mode 0: (phase, logabs); 1: + grad; 2: + grad, lap.  pos (..., 3N)."""
+        p = self._pos(pos)
+        lead = p.shape[:-1]
+        p2 = p.reshape(-1, 3 * self.n)
+        ncfg = p2.shape[0]
+        phase = torch.empty(ncfg, dtype=torch.float64, device=self.device)
+        logabs = torch.empty_like(phase)
+        grad = torch.empty((ncfg, 3 * self.n), dtype=torch.float64, device=self.device) if mode >= 1 else None
+        lap = torch.empty_like(phase) if mode == 2 else None
+        with torch.cuda.device(self.device):
+            if mode == 0:
+                rc = self.lib.aiqmc_psi_fwd(C.byref(self.sys), _ptr(self.params_dev), _ptr(p2), ncfg, _ptr(phase),
+                                            _ptr(logabs), _stream())
+            elif mode == 1:
+                rc = self.lib.aiqmc_psi_grad(C.byref(self.sys), _ptr(self.params_dev), _ptr(p2), ncfg, _ptr(phase),
+                                             _ptr(logabs), _ptr(grad), _stream())
+            else:
+                rc = self.lib.aiqmc_psi_fwdlap(C.byref(self.sys), _ptr(self.params_dev), _ptr(p2), ncfg, _ptr(phase),
+                                               _ptr(logabs), _ptr(grad), _ptr(lap), _stream())
+        _lib.check(rc, "aiqmc_psi")
+        out = [phase.reshape(lead), logabs.reshape(lead)]
+        if mode >= 1:
+            out.append(grad.reshape(*lead, 3 * self.n))
+        if mode == 2:
+            out.append(lap.reshape(lead))
+        return tuple(out)
+
+    # ---- VMC sweep --------------------------------------------------------------------
+    def vmc_sweep(self, pos: torch.Tensor, gauss1: torch.Tensor, gauss2: torch.Tensor, rnd: torch.Tensor,
+                  tstep: float, acyrus: float = 0.25, signed_ratio: bool = False, want_accept: bool = True,
+                  want_drift: bool = False, want_aux: bool = False):
+        """In-place sweep on pos (B,3N) float64 cuda.  Returns dict(accept, grad_eff_old, aux)."""
+        B = pos.shape[0]
+        assert pos.is_cuda and pos.dtype == torch.float64 and pos.is_contiguous()
+        nbytes = self.lib.aiqmc_vmc_workspace_bytes(C.byref(self.sys), B)
+        ws = self._workspace("vmc", nbytes)
+        accept = torch.empty((B, self.n), dtype=torch.uint8, device=self.device) if want_accept else None
+        drift = torch.empty((B, 3 * self.n), dtype=torch.float64, device=self.device) if want_drift else None
+        aux = torch.empty(4, dtype=torch.float64, device=self.device) if want_aux else None
+        with torch.cuda.device(self.device):
+            rc = self.lib.aiqmc_vmc_sweep(C.byref(self.sys), _ptr(self.params_dev), _ptr(pos), _ptr(gauss1),
+                                          _ptr(gauss2), _ptr(rnd), B, float(tstep), float(acyrus),
+                                          1 if signed_ratio else 0, _ptr(accept), _ptr(drift), _ptr(aux), _ptr(ws),
+                                          ws.numel(), _stream())
+        _lib.check(rc, "aiqmc_vmc_sweep")
+        return dict(accept=accept, grad_eff_old=drift, aux=aux)
+
+    # ---- local energy -----------------------------------------------------------------
+    def local_energy(self, pos: torch.Tensor, rot: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """All-electron (no ECP table): real (B,).  ccECP: complex128 (B,) (quirk Q25)."""
+        p = self._pos(pos).reshape(-1, 3 * self.n)
+        B = p.shape[0]
+        with_ecp = self.ecp is not None
+        nbytes = self.lib.aiqmc_energy_workspace_bytes(C.byref(self.sys), B, 1 if with_ecp else 0)
+        ws = self._workspace("energy", nbytes)
+        with torch.cuda.device(self.device):
+            if with_ecp:
+                if rot is None:
+                    raise ValueError("ccECP local energy needs the per-walker rotation matrices (B,3,3)")
+                r = torch.as_tensor(rot).to(device=self.device, dtype=torch.float64).reshape(B, 9).contiguous()
+                e = torch.empty((B, 2), dtype=torch.float64, device=self.device)
+                rc = self.lib.aiqmc_local_energy_ecp(C.byref(self.sys), C.byref(self.ecp), _ptr(self.params_dev),
+                                                     _ptr(p), _ptr(r), B, _ptr(e), _ptr(ws), ws.numel(), _stream())
+                _lib.check(rc, "aiqmc_local_energy_ecp")
+                return torch.view_as_complex(e)
+            e = torch.empty(B, dtype=torch.float64, device=self.device)
+            rc = self.lib.aiqmc_local_energy_ae(C.byref(self.sys), _ptr(self.params_dev), _ptr(p), B, _ptr(e),
+                                                _ptr(ws), ws.numel(), _stream())
+            _lib.check(rc, "aiqmc_local_energy_ae")
+            return e
+
+    def energy_stats(self, e_l: torch.Tensor) -> torch.Tensor:
+        """[sum Re E, sum Im E, sum |E|^2, count] on device (the partials of pploss.py:165-167)."""
+        if e_l.is_complex():
+            raw, stride = torch.view_as_real(e_l.contiguous()), 2
+        else:
+            raw, stride = e_l.contiguous(), 1
+        out = torch.empty(4, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.aiqmc_energy_stats(_ptr(raw), stride, e_l.shape[0], _ptr(out), _stream()),
+                       "aiqmc_energy_stats")
+        return out
+
+    # ---- DMC pieces -------------------------------------------------------------------
+    def dmc_ecut_min(self, e_l: torch.Tensor, e_est: float, branchcut: torch.Tensor) -> torch.Tensor:
+        raw, stride = (torch.view_as_real(e_l.contiguous()), 2) if e_l.is_complex() else (e_l.contiguous(), 1)
+        out = torch.empty(1, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.aiqmc_dmc_ecut_min(_ptr(raw), stride, e_l.shape[0], float(e_est), _ptr(branchcut),
+                                                   _ptr(out), _stream()), "aiqmc_dmc_ecut_min")
+        return out
+
+    def dmc_s(self, e_l: torch.Tensor, drift: torch.Tensor, e_trial: float, e_est: float, ecut_min: torch.Tensor,
+              tau: float) -> torch.Tensor:
+        raw, stride = (torch.view_as_real(e_l.contiguous()), 2) if e_l.is_complex() else (e_l.contiguous(), 1)
+        B = e_l.shape[0]
+        s = torch.empty(B, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.aiqmc_dmc_s(_ptr(raw), stride, _ptr(drift.contiguous()), B, self.n, float(e_trial),
+                                            float(e_est), _ptr(ecut_min), float(tau), _ptr(s), _stream()),
+                       "aiqmc_dmc_s")
+        return s
+
+    def dmc_weights(self, weights: torch.Tensor, s_old: torch.Tensor, s_new: torch.Tensor, tau: float,
+                    tdamp: float) -> None:
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.aiqmc_dmc_weights(_ptr(weights), _ptr(s_old), _ptr(s_new), weights.shape[0],
+                                                  float(tau), float(tdamp), _stream()), "aiqmc_dmc_weights")
+
+    def branch_comb(self, weights: torch.Tensor, u: float):
+        B = weights.shape[0]
+        ws = self._workspace("branch", self.lib.aiqmc_branch_workspace_bytes(B))
+        inds = torch.empty(B, dtype=torch.int32, device=self.device)
+        neww = torch.empty(1, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.aiqmc_branch_comb(_ptr(weights.contiguous()), B, float(u), _ptr(inds), _ptr(neww),
+                                                  _ptr(ws), ws.numel(), _stream()), "aiqmc_branch_comb")
+        return neww, inds
+
+    def gather_walkers(self, pos: torch.Tensor, inds: torch.Tensor) -> torch.Tensor:
+        out = torch.empty_like(pos)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.aiqmc_gather_walkers(_ptr(pos), _ptr(inds), pos.shape[0], pos.shape[1], _ptr(out),
+                                                     _stream()), "aiqmc_gather_walkers")
+        return out

@@ -1,0 +1,80 @@
+"""ctypes binding of libaiqmc_b200.so (the C ABI of include/aiqmc_b200.h).
+
+There is deliberately NO fallback: if the CUDA library is missing or cannot be loaded every
+product entry point raises.  The CPU oracle under oracle/ is test infrastructure only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .system import AiqmcEcp, AiqmcLayout, AiqmcSystem
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libaiqmc_b200.so")
+
+ERRORS = {-1: "AIQMC_E_UNSUPPORTED: no compiled instantiation for this (n_elec, n_atoms); add it to csrc/dispatch.h",
+          -2: "AIQMC_E_BADARG", -3: "AIQMC_E_CUDA", -4: "AIQMC_E_WORKSPACE"}
+
+EXPORTS = ["aiqmc_param_layout", "aiqmc_supported", "aiqmc_last_cuda_error", "aiqmc_version", "aiqmc_psi_fwd",
+           "aiqmc_psi_grad", "aiqmc_psi_fwdlap", "aiqmc_vmc_workspace_bytes", "aiqmc_vmc_sweep",
+           "aiqmc_energy_workspace_bytes", "aiqmc_local_energy_ae", "aiqmc_local_energy_ecp", "aiqmc_energy_stats",
+           "aiqmc_dmc_ecut_min", "aiqmc_dmc_s", "aiqmc_dmc_weights", "aiqmc_branch_workspace_bytes",
+           "aiqmc_branch_comb", "aiqmc_gather_walkers"]
+
+_lib = None
+
+
+class AiqmcError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Loads the CUDA library built by build.py; raises if it is absent (no CPU fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AiqmcError(f"{LIB_PATH} is missing: run `python __graft_entry__.py` (or aiqmc_b200.build.build()) "
+                         "to compile the sm_100a kernels; there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    sysp, ecpp = C.POINTER(AiqmcSystem), C.POINTER(AiqmcEcp)
+    sig = {
+        "aiqmc_param_layout": (C.c_int, [i32, i32, C.POINTER(AiqmcLayout)]),
+        "aiqmc_supported": (C.c_int, [i32, i32]),
+        "aiqmc_last_cuda_error": (C.c_int, []),
+        "aiqmc_version": (C.c_char_p, []),
+        "aiqmc_psi_fwd": (C.c_int, [sysp, vp, vp, i64, vp, vp, vp]),
+        "aiqmc_psi_grad": (C.c_int, [sysp, vp, vp, i64, vp, vp, vp, vp]),
+        "aiqmc_psi_fwdlap": (C.c_int, [sysp, vp, vp, i64, vp, vp, vp, vp, vp]),
+        "aiqmc_vmc_workspace_bytes": (i64, [sysp, i64]),
+        "aiqmc_vmc_sweep": (C.c_int, [sysp, vp, vp, vp, vp, vp, i64, f64, f64, i32, vp, vp, vp, vp, i64, vp]),
+        "aiqmc_energy_workspace_bytes": (i64, [sysp, i64, i32]),
+        "aiqmc_local_energy_ae": (C.c_int, [sysp, vp, vp, i64, vp, vp, i64, vp]),
+        "aiqmc_local_energy_ecp": (C.c_int, [sysp, ecpp, vp, vp, vp, i64, vp, vp, i64, vp]),
+        "aiqmc_energy_stats": (C.c_int, [vp, i32, i64, vp, vp]),
+        "aiqmc_dmc_ecut_min": (C.c_int, [vp, i32, i64, f64, vp, vp, vp]),
+        "aiqmc_dmc_s": (C.c_int, [vp, i32, vp, i64, i32, f64, f64, vp, f64, vp, vp]),
+        "aiqmc_dmc_weights": (C.c_int, [vp, vp, vp, i64, f64, f64, vp]),
+        "aiqmc_branch_workspace_bytes": (i64, [i64]),
+        "aiqmc_branch_comb": (C.c_int, [vp, i64, f64, vp, vp, vp, i64, vp]),
+        "aiqmc_gather_walkers": (C.c_int, [vp, vp, i64, i32, vp, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)          # AttributeError here == header/library mismatch
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        extra = f" (cudaError {load().aiqmc_last_cuda_error()})" if rc == -3 else ""
+        raise AiqmcError(f"{what} failed: {ERRORS.get(rc, rc)}{extra}")
+
+
+def param_layout(n_elec: int, n_atoms: int) -> AiqmcLayout:
+    lay = AiqmcLayout()
+    check(load().aiqmc_param_layout(n_elec, n_atoms, C.byref(lay)), "aiqmc_param_layout")
+    return lay

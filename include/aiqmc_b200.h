@@ -133,12 +133,16 @@ int aiqmc_energy_stats(const double* e_l, int32_t e_l_stride, int64_t n_walkers,
                        void* stream);
 
 /* ---- DMC: replaces DMC/drift_diffusion.py, S_matrix.py, dmc.py:86-92, branch.py ---------- */
-/* S = E_T - E_est + e_cut / (1 + (v2*tau/N)^2), e_cut clamped by the batch-global min of
- * |E_est - E_L| and branchcut (quirk Q20).  v2_in (B,3N) holds the limited drift (its square is
- * summed here).  global_min_io: device scalar; pass NULL to reduce over this device only, or a
- * pointer pre-filled with the cross-GPU min. */
+/* Step 1 of comput_S (S_matrix.py:22-23): min over this device's walkers of
+ * min(|E_est - Re E_L[b]|, branchcut[b]) -> ecut_min (device scalar).  The reference takes this
+ * min over ALL walkers and devices (quirk Q20): with several GPUs the host MIN-all-reduces
+ * the scalar (NCCL) before step 2. */
+int aiqmc_dmc_ecut_min(const double* e_l, int32_t e_l_stride, int64_t n_walkers, double e_est,
+                       const double* branchcut, double* ecut_min, void* stream);
+/* Step 2: S[b] = E_T - E_est + ecut_min*sign(E_est - Re E_L[b]) / (1 + (v2[b]*tau/N)^2) with
+ * v2[b] = sum_k drift[b,k]^2; drift (B,3N) is the limited drift the reference squares at dmc.py:86-89. */
 int aiqmc_dmc_s(const double* e_l, int32_t e_l_stride, const double* drift, int64_t n_walkers,
-                int32_t n_elec, double e_trial, double e_est, const double* branchcut, double tau,
+                int32_t n_elec, double e_trial, double e_est, const double* ecut_min, double tau,
                 double* s_out, void* stream);
 /* weights *= exp(tau * tdamp * 0.5 * (S_new + S_old))   (dmc.py:91-92). */
 int aiqmc_dmc_weights(double* weights, const double* s_old, const double* s_new, int64_t n_walkers,

@@ -1,0 +1,205 @@
+"""GPU parity: the CUDA path (through the C ABI / aiqmc_b200 host mirror) against the oracle on the
+same seeded inputs.  Tolerances are north_star's: log|psi| 1e-6 relative, E_L 1e-5 Ha, accept
+masks and comb indices bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from common import CASES, Case, O, ecp_tables
+
+import aiqmc_b200
+
+pytestmark = pytest.mark.gpu
+
+
+def engine(case, ecp=None):
+    return aiqmc_b200.WalkerEngine(case.spec(), case.params, ecp=ecp)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_signed_network_value_grad_laplacian(name):
+    case = Case(**CASES[name], nwalkers=64)
+    eng = engine(case)
+    ph, la, g, lp = (t.cpu().numpy() for t in eng.psi(case.pos, mode=2))
+    f = lambda x: case.net.apply(case.params, x, case.t_spins, case.t_atoms)[1]
+    pht, lat = case.net.apply(case.params, torch.tensor(case.pos), case.t_spins, case.t_atoms)
+    _, gt, dt = O.grad_and_hess_diag(f, torch.tensor(case.pos))
+    np.testing.assert_allclose(la, lat.numpy(), rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(np.angle(np.exp(1j * (ph - pht.numpy()))), 0.0, atol=1e-6)
+    np.testing.assert_allclose(g, gt.numpy(), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(lp, dt.sum(-1).numpy(), rtol=1e-6, atol=1e-6)
+    ph0, la0 = (t.cpu().numpy() for t in eng.psi(case.pos, mode=0))
+    np.testing.assert_allclose(la0, la, rtol=1e-12, atol=1e-12)
+    ph1, la1, g1 = (t.cpu().numpy() for t in eng.psi(case.pos, mode=1))
+    np.testing.assert_allclose(g1, g, rtol=1e-10, atol=1e-10)
+
+
+def test_signed_network_dropin_signature():
+    case = Case(**CASES["C_ecp"], nwalkers=16)
+    net = aiqmc_b200.make_ai_net(**case.kw)
+    phase, logabs = net.apply(case.params, torch.tensor(case.pos), case.t_spins, case.t_atoms,
+                              torch.tensor(case.charges))
+    pht, lat = case.net.apply(case.params, torch.tensor(case.pos), case.t_spins, case.t_atoms)
+    np.testing.assert_allclose(logabs.cpu().numpy(), lat.numpy(), rtol=1e-6)
+    # single configuration (no batch axis), float32 input as the reference passes
+    p1, l1 = net.apply(case.params, torch.tensor(case.pos[0], dtype=torch.float32), case.t_spins, case.t_atoms, None)
+    assert p1.shape == () and l1.shape == ()
+    np.testing.assert_allclose(float(l1), float(lat[0]), rtol=1e-5)
+
+
+def test_empty_and_ragged_batches():
+    case = Case(**CASES["C_ecp"], nwalkers=130)      # not a multiple of the CTA size
+    eng = engine(case)
+    ph, la = eng.psi(case.pos[:0], mode=0)
+    assert ph.shape == (0,) and la.shape == (0,)
+    _, la = eng.psi(case.pos, mode=0)
+    _, lat = case.net.apply(case.params, torch.tensor(case.pos), case.t_spins, case.t_atoms)
+    np.testing.assert_allclose(la.cpu().numpy(), lat.numpy(), rtol=1e-6)
+
+
+@pytest.mark.parametrize("name,signed", [("C_ecp", False), ("C_ae", False), ("N2_ecp", False), ("odd", True)])
+def test_vmc_sweep_accept_mask_bit_exact(name, signed):
+    tstep = 0.05
+    case = Case(**CASES[name], nwalkers=48)
+    eng = engine(case)
+    rand = case.sweep_rand(tstep)
+    new_data, aux = O.walkers_update(O.select_output(case.net.apply, 1), case.params, case.oracle_data(), rand, tstep,
+                                     3, case.n, case.B, signed=signed, return_aux=True)
+    pos = torch.tensor(case.pos).cuda()
+    out = eng.vmc_sweep(pos, rand['gauss1'].cuda(), rand['gauss2'].cuda().contiguous(), rand['rnd'].cuda(), tstep,
+                        signed_ratio=signed, want_drift=True, want_aux=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(out['accept'].cpu().numpy().astype(bool), aux['accept'].numpy())      # bit-exact
+    np.testing.assert_allclose(pos.cpu().numpy(), new_data.positions.numpy(), rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(out['grad_eff_old'].cpu().numpy(), aux['grad_eff'].numpy(), rtol=1e-7, atol=1e-9)
+    auxv = out['aux'].cpu().numpy()
+    np.testing.assert_allclose(auxv[2], float((aux['grad'] ** 2).sum()), rtol=1e-8)
+    assert 0 < aux['accept'].float().mean() < 1 or case.n <= 2
+
+
+def test_mc_step_dropin_three_sweeps():
+    tstep, nsteps = 0.05, 3
+    case = Case(**CASES["C_ecp"], nwalkers=32)
+    keys = [case.sweep_rand(tstep) for _ in range(nsteps)]
+    ref = O.main_monte_carlo(case.net.apply, tstep, 3, case.n, nsteps, case.B)(case.params, case.oracle_data(), keys)
+    net = aiqmc_b200.make_ai_net(**case.kw)
+    mc_step = aiqmc_b200.main_monte_carlo(net.apply, tstep, 3, case.n, nsteps, case.B)
+    data = aiqmc_b200.AINetData(positions=torch.tensor(case.pos), spins=case.t_spins, atoms=case.t_atoms,
+                                charges=torch.tensor(case.charges))
+    out = mc_step(case.params, data, keys)
+    np.testing.assert_allclose(out.positions.cpu().numpy(), ref.positions.numpy(), rtol=1e-8, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", ["C_ae", "odd", "h2like"])
+def test_local_energy_all_electron(name):
+    case = Case(**CASES[name], nwalkers=40)
+    eng = engine(case)
+    e = eng.local_energy(torch.tensor(case.pos)).cpu().numpy()
+    le = O.local_energy_ae(case.net.apply, case.charges)
+    ref, _ = le(case.params, None, case.oracle_data(batched_static=False))
+    np.testing.assert_allclose(e, ref.numpy(), atol=1e-5, rtol=0)          # north_star: 1e-5 Ha
+    np.testing.assert_allclose(e, ref.numpy(), atol=1e-8, rtol=1e-9)
+
+
+@pytest.mark.parametrize("name,rich", [("C_ecp", False), ("C_ecp", True), ("N2_ecp", True)])
+def test_local_energy_ecp(name, rich):
+    case = Case(**CASES[name], nwalkers=24, width=0.7)
+    tabs = ecp_tables(case.a, rich=rich)
+    ecp = aiqmc_b200.make_ecp(case.a, list_l=2, **tabs)
+    eng = engine(case, ecp=ecp)
+    rot = torch.tensor(O.random_rotations(case.rng, case.B))
+    e = eng.local_energy(torch.tensor(case.pos), rot).cpu().numpy()
+    le = O.local_energy_ecp(case.net.apply, O.make_log_network(case.net.apply), case.charges, None,
+                            tabs['rn_local'], tabs['local_coes'], tabs['local_exps'], tabs['rn_non_local'],
+                            tabs['non_local_coes'], tabs['non_local_exps'], case.a, case.n, 3, 2)
+    ref, _ = le(case.params, rot, case.oracle_data(batched_static=False))
+    np.testing.assert_allclose(e.real, ref.real.numpy(), atol=1e-5, rtol=0)
+    np.testing.assert_allclose(e.imag, ref.imag.numpy(), atol=1e-5, rtol=0)
+    np.testing.assert_allclose(e, ref.numpy(), atol=1e-8, rtol=1e-9)
+    stats = eng.energy_stats(torch.tensor(e).cuda()).cpu().numpy()
+    np.testing.assert_allclose(stats, [e.real.sum(), e.imag.sum(), (np.abs(e) ** 2).sum(), len(e)], rtol=1e-12)
+
+
+def test_local_energy_dropin_factory():
+    case = Case(**CASES["C_ecp"], nwalkers=8)
+    tabs = ecp_tables(1)
+    net = aiqmc_b200.make_ai_net(**case.kw)
+    le = aiqmc_b200.local_energy(net.apply, case.charges, lognetwork=None, natoms=1, nelectrons=4, ndim=3, list_l=2,
+                                 **tabs)
+    rot = torch.tensor(O.random_rotations(case.rng, case.B))
+    data = aiqmc_b200.AINetData(positions=torch.tensor(case.pos), spins=case.t_spins, atoms=case.t_atoms,
+                                charges=torch.tensor(case.charges))
+    e, aux = le(case.params, rot, data)
+    assert aux is None and e.is_complex() and e.shape == (case.B,)
+    ref, _ = O.local_energy_ecp(case.net.apply, O.make_log_network(case.net.apply), case.charges, None,
+                                tabs['rn_local'], tabs['local_coes'], tabs['local_exps'], tabs['rn_non_local'],
+                                tabs['non_local_coes'], tabs['non_local_exps'], 1, 4, 3, 2)(
+        case.params, rot, case.oracle_data(batched_static=False))
+    np.testing.assert_allclose(e.cpu().numpy(), ref.numpy(), atol=1e-5)
+
+
+def test_dmc_drift_S_weights_branch():
+    tstep = 0.05
+    case = Case(**CASES["C_ecp"], nwalkers=64)
+    eng = engine(case)
+    net = aiqmc_b200.make_ai_net(**case.kw)
+    packed = net.pack(case.params, case.atoms)
+    rand = case.sweep_rand(tstep)
+    # oracle
+    dd = O.propose_drift_diffusion(O.select_output(case.net.apply, 1), tstep, 3, case.n, case.B)
+    new_data, tdamp, g_old, g_new, aux = dd(case.params, rand, case.oracle_data())
+    # engine
+    data = aiqmc_b200.AINetData(positions=torch.tensor(case.pos), spins=case.t_spins, atoms=case.t_atoms,
+                                charges=torch.tensor(case.charges))
+    nd, tdamp_g, go_g, gn_g, acc = aiqmc_b200.propose_drift_diffusion(net.apply, tstep, 3, case.n, case.B)(packed, rand, data)
+    assert np.array_equal(acc.cpu().numpy().astype(bool), aux['accept'].numpy())
+    np.testing.assert_allclose(float(tdamp_g), float(tdamp), rtol=1e-10)
+    np.testing.assert_allclose(go_g.cpu().numpy(), g_old.numpy(), rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(gn_g.cpu().numpy(), g_new.numpy(), rtol=1e-7, atol=1e-9)
+    # S and weights on synthetic energies
+    rng = case.rng
+    eloc = torch.tensor(rng.normal(-5.4, 0.5, size=case.B) + 1j * rng.normal(0, 0.01, size=case.B))
+    branchcut = torch.full((case.B,), 10 * 0.5)
+    s_ref = O.comput_S(-5.41, -5.40, branchcut, g_old ** 2, tstep, eloc, case.n)
+    s_gpu = aiqmc_b200.comput_S(eng, -5.41, -5.40, branchcut.cuda(), go_g, tstep, eloc.cuda())
+    np.testing.assert_allclose(s_gpu.cpu().numpy(), s_ref.numpy(), rtol=1e-10, atol=1e-12)
+    s2_ref = O.comput_S(-5.41, -5.40, branchcut, g_new ** 2, tstep, eloc * 1.01, case.n)
+    s2_gpu = aiqmc_b200.comput_S(eng, -5.41, -5.40, branchcut.cuda(), gn_g, tstep, (eloc * 1.01).cuda())
+    w = torch.ones(case.B).cuda()
+    eng.dmc_weights(w, s_gpu, s2_gpu, tstep, float(tdamp))
+    w_ref = torch.exp(tstep * tdamp * (0.5 * s2_ref + 0.5 * s_ref))
+    np.testing.assert_allclose(w.cpu().numpy(), w_ref.numpy(), rtol=1e-12)
+
+
+@pytest.mark.parametrize("B", [8, 1000, 65536])
+def test_branch_comb_bit_exact_on_dyadic_weights_and_gather(B):
+    rng = np.random.default_rng(B)
+    w = torch.tensor(rng.integers(0, 9, size=B) / 4.0)          # dyadic rationals: cumsum exact in any order
+    w[0] = 1.0
+    case = Case(**CASES["C_ecp"], nwalkers=2)
+    eng = engine(case)
+    u = 0.3125
+    neww_ref, inds_ref = O.branch(w, u)
+    neww, inds = eng.branch_comb(w.cuda(), u)
+    assert np.array_equal(inds.cpu().numpy(), inds_ref.numpy().astype(np.int32))                   # bit-exact
+    assert float(neww) == float(neww_ref)
+    counts = np.bincount(inds.cpu().numpy(), minlength=B)
+    assert counts.sum() == B and np.all(np.abs(counts - w.numpy() / float(neww_ref)) < 1 + 1e-9)
+    pos = torch.tensor(rng.normal(size=(B, 12))).cuda()
+    np.testing.assert_array_equal(eng.gather_walkers(pos, inds).cpu().numpy(), pos.cpu().numpy()[inds.cpu().numpy()])
+    # random weights: statistical agreement (indices may differ only where cumsum rounding differs)
+    wr = torch.tensor(rng.uniform(0.2, 1.8, size=B))
+    _, ir = O.branch(wr, 0.77)
+    _, ig = eng.branch_comb(wr.cuda(), 0.77)
+    assert np.mean(ig.cpu().numpy() != ir.numpy()) < 1e-3
+
+
+def test_unsupported_system_and_bad_args_fail_loudly():
+    case = Case(n=7, natoms=3, spins=[1.] * 4 + [-1.] * 3, seed=3)
+    with pytest.raises(aiqmc_b200.lib.AiqmcError):
+        engine(case)
+    case = Case(**CASES["C_ecp"], nwalkers=4)
+    eng = engine(case)
+    with pytest.raises(ValueError):
+        eng.ecp = aiqmc_b200.make_ecp(1, list_l=2, **ecp_tables(1))
+        eng.local_energy(torch.tensor(case.pos))           # rotation missing
