@@ -12,14 +12,16 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-BUILD = os.path.join(CSRC, "build")
-LIB = os.path.join(HERE, "libaiqmc_b200.so")
+BUILD = os.path.join(CSRC, os.environ.get("AIQMC_BUILD_DIR", "build"))
+LIB = os.path.join(HERE, os.environ.get("AIQMC_LIB_NAME", "libaiqmc_b200.so"))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
 
 def systems():
+    if os.environ.get("AIQMC_SYSTEMS"):          # debugging aid: "10,2;4,1" builds only those instantiations
+        return [tuple(int(v) for v in s.split(",")) for s in os.environ["AIQMC_SYSTEMS"].split(";")]
     txt = open(os.path.join(CSRC, "dispatch.h")).read()
     body = txt[txt.index("#define AIQMC_FOR_EACH_SYSTEM"):]
     return [(int(a), int(b)) for a, b in re.findall(r"X\((\d+),\s*(\d+)\)", body)]
@@ -33,12 +35,23 @@ def _sources_digest():
             if os.path.isfile(p) and name.endswith((".cu", ".cuh", ".h")):
                 h.update(name.encode())
                 h.update(open(p, "rb").read())
-    h.update(" ".join(FLAGS + ARCH).encode())
+    h.update(" ".join(FLAGS + ARCH + _extra_flags()).encode())
     return h.hexdigest()
 
 
+def _extra_flags():
+    extra = os.environ.get("AIQMC_EXTRA_FLAGS", "").split()
+    if os.environ.get("AIQMC_SYSTEMS"):
+        os.makedirs(BUILD, exist_ok=True)            # nvcc splits -D values at commas: use a pre-include
+        hdr = os.path.join(BUILD, "systems_override.h")
+        with open(hdr, "w") as f:
+            f.write("#define AIQMC_SYSTEM_LIST " + " ".join(f"X({n},{a})" for n, a in systems()) + "\n")
+        extra += ["-include", hdr]
+    return extra
+
+
 def _compile(src, obj, log):
-    cmd = [NVCC] + ARCH + FLAGS + ["-c", src, "-o", obj]
+    cmd = [NVCC] + ARCH + FLAGS + _extra_flags() + ["-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     with open(log, "w") as f:
         f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
@@ -57,7 +70,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for n, a in systems():
         src = os.path.join(BUILD, f"inst_{n}_{a}.cu")
         with open(src, "w") as f:
-            f.write('#include "../engine_impl.cuh"\n'
+            f.write('#include "' + os.path.join(CSRC, 'engine_impl.cuh') + '"\n'
                     f'extern "C" const aiqmc::OpsTable* aiqmc_ops_{n}_{a}() {{ return aiqmc::Launch<{n}, {a}>::table(); }}\n')
         jobs.append((src, os.path.join(BUILD, f"inst_{n}_{a}.o"), os.path.join(BUILD, f"inst_{n}_{a}.log")))
     for name in ("abi", "wsizes"):

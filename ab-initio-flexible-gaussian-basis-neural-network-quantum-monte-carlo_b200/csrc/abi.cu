@@ -153,6 +153,18 @@ __global__ void k_gather(const double* __restrict__ in, const int32_t* __restric
   const int c = (int)(t - b * row);
   out[t] = in[(int64_t)idx[b] * row + c];
 }
+__global__ void __launch_bounds__(256) k_bench_dfma(int64_t iters, double* __restrict__ sink) {
+  double a[8];
+  const double x = 1.0 + 1e-9 * threadIdx.x, y = 1e-12 * blockIdx.x;
+  for (int c = 0; c < 8; ++c) a[c] = c + threadIdx.x;
+  for (int64_t i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a[c] = fma(a[c], x, y);
+  }
+  double s = 0.0;
+  for (int c = 0; c < 8; ++c) s += a[c];
+  if (s == 123.456) sink[0] = s;          // never true; keeps the loop alive
+}
 }  // namespace
 
 // ------------------------------------------------------------------ C ABI
@@ -214,19 +226,26 @@ int aiqmc_local_energy_ae(const AiqmcSystem* sys, const double* params, const do
   if (!sys_ok(sys) || !params || n_walkers < 0 || (n_walkers > 0 && (!pos || !e_l || !workspace))) return AIQMC_E_BADARG;
   const aiqmc::OpsTable* ops = find_ops(sys->n_elec, sys->n_atoms);
   if (!ops) return AIQMC_E_UNSUPPORTED;
-  return ops->energy(sys, nullptr, params, pos, nullptr, n_walkers, e_l, workspace, workspace_bytes,
+  return ops->energy(sys, nullptr, params, pos, nullptr, n_walkers, e_l, workspace, workspace_bytes, 7,
                      (cudaStream_t)stream);
 }
-int aiqmc_local_energy_ecp(const AiqmcSystem* sys, const AiqmcEcp* ecp, const double* params, const double* pos,
-                           const double* rot, int64_t n_walkers, double* e_l, void* workspace,
-                           int64_t workspace_bytes, void* stream) {
-  if (!sys_ok(sys) || !ecp || !params || n_walkers < 0) return AIQMC_E_BADARG;
+int aiqmc_local_energy_ecp_stages(const AiqmcSystem* sys, const AiqmcEcp* ecp, const double* params,
+                                  const double* pos, const double* rot, int64_t n_walkers, double* e_l,
+                                  void* workspace, int64_t workspace_bytes, int32_t stage_mask, void* stream) {
+  if (!sys_ok(sys) || !ecp || !params || n_walkers < 0 || (stage_mask & ~7) || stage_mask == 0) return AIQMC_E_BADARG;
   if (n_walkers > 0 && (!pos || !rot || !e_l || !workspace)) return AIQMC_E_BADARG;
   if (ecp->k_loc < 0 || ecp->k_loc > AIQMC_ECP_MAX_K || ecp->k_nl < 0 || ecp->k_nl > AIQMC_ECP_MAX_K ||
       ecp->n_l < 1 || ecp->n_l > AIQMC_ECP_MAX_L) return AIQMC_E_BADARG;
   const aiqmc::OpsTable* ops = find_ops(sys->n_elec, sys->n_atoms);
   if (!ops) return AIQMC_E_UNSUPPORTED;
-  return ops->energy(sys, ecp, params, pos, rot, n_walkers, e_l, workspace, workspace_bytes, (cudaStream_t)stream);
+  return ops->energy(sys, ecp, params, pos, rot, n_walkers, e_l, workspace, workspace_bytes, stage_mask,
+                     (cudaStream_t)stream);
+}
+int aiqmc_local_energy_ecp(const AiqmcSystem* sys, const AiqmcEcp* ecp, const double* params, const double* pos,
+                           const double* rot, int64_t n_walkers, double* e_l, void* workspace,
+                           int64_t workspace_bytes, void* stream) {
+  return aiqmc_local_energy_ecp_stages(sys, ecp, params, pos, rot, n_walkers, e_l, workspace, workspace_bytes, 7,
+                                       stream);
 }
 
 int aiqmc_energy_stats(const double* e_l, int32_t e_l_stride, int64_t n_walkers, double* stats, void* stream) {
@@ -273,6 +292,14 @@ int aiqmc_branch_comb(const double* weights, int64_t n_walkers, double u, int32_
   k_cumsum<<<1, kBig, 0, (cudaStream_t)stream>>>(weights, n_walkers, cum);
   k_comb<<<(unsigned)((n_walkers + 255) / 256), 256, 0, (cudaStream_t)stream>>>(cum, n_walkers, u, newinds, new_weight);
   AQ_CUDA_OK(cudaGetLastError());
+  return AIQMC_OK;
+}
+int aiqmc_bench_dfma(int64_t iters, double* sink, double* flops_out, void* stream) {
+  if (iters <= 0 || !sink || !flops_out) return AIQMC_E_BADARG;
+  const int grid = 148 * 8;
+  k_bench_dfma<<<grid, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+  AQ_CUDA_OK(cudaGetLastError());
+  *flops_out = (double)grid * 256.0 * 8.0 * 2.0 * (double)iters;
   return AIQMC_OK;
 }
 int aiqmc_gather_walkers(const double* pos_in, const int32_t* newinds, int64_t n_walkers, int32_t row_doubles,

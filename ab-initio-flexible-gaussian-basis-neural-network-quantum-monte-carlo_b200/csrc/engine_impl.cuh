@@ -7,6 +7,7 @@
 // shared memory and read as warp-wide broadcasts.
 #pragma once
 #include <cuda_runtime.h>
+#include <string.h>
 
 #include "fastmath.cuh"
 #include "ops_table.h"
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(kThreads) k_energy_base(AiqmcSystem sys, const
                                                           double* __restrict__ e_out, EnergyWs w) {
   extern __shared__ double sP[];
   const double* P = stage_params<NE, NA>(params, sP);
-  constexpr AiqmcLayout L = make_layout(NE, NA);
+  constexpr LayoutC<NE, NA> L{};
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   double x[3 * NE], g[3 * NE], ph, la, lp;
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(kThreads) k_ecp_quad(AiqmcSystem sys, const do
                                                        const double* __restrict__ rot, int64_t B, EnergyWs w) {
   extern __shared__ double sP[];
   const double* P = stage_params<NE, NA>(params, sP);
-  constexpr AiqmcLayout L = make_layout(NE, NA);
+  constexpr LayoutC<NE, NA> L{};
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t per_walker = (int64_t)NE * NA * AIQMC_NQUAD;
   if (t >= B * per_walker) return;
@@ -447,7 +448,7 @@ struct Launch {
   }
 
   static int energy(const AiqmcSystem* sys, const AiqmcEcp* ecp, const double* params, const double* pos,
-                    const double* rot, int64_t B, double* e_l, void* ws, int64_t ws_bytes, cudaStream_t st) {
+                    const double* rot, int64_t B, double* e_l, void* ws, int64_t ws_bytes, int stages, cudaStream_t st) {
     if (B <= 0) return AIQMC_OK;
     const int with_ecp = ecp != nullptr;
     if (ws_bytes < energy_ws_bytes(NE, NA, B, with_ecp)) return AIQMC_E_WORKSPACE;
@@ -457,14 +458,24 @@ struct Launch {
       AQ_CUDA_OK(prep(k_energy_base<NE, NA, false>));
       k_energy_base<NE, NA, false><<<g1, kThreads, kSmem, st>>>(*sys, params, pos, nullptr, B, e_l, w);
     } else {
-      AQ_CUDA_OK(cudaMemcpyToSymbolAsync(c_ecp, ecp, sizeof(AiqmcEcp), 0, cudaMemcpyHostToDevice, st));
-      AQ_CUDA_OK(prep(k_energy_base<NE, NA, true>));
-      AQ_CUDA_OK(prep(k_ecp_quad<NE, NA>));
-      k_energy_base<NE, NA, true><<<g1, kThreads, kSmem, st>>>(*sys, params, pos, rot, B, e_l, w);
-      const int64_t nt = B * NE * NA * AIQMC_NQUAD;
-      const unsigned g2 = (unsigned)((nt + kThreads - 1) / kThreads);
-      k_ecp_quad<NE, NA><<<g2, kThreads, kSmem, st>>>(*sys, params, pos, rot, B, w);
-      k_energy_final<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(B, e_l, w);
+      static AiqmcEcp h_ecp;                 // last table uploaded to this TU's __constant__ copy
+      static bool h_valid = false;
+      if (!h_valid || memcmp(&h_ecp, ecp, sizeof(AiqmcEcp)) != 0) {
+        AQ_CUDA_OK(cudaMemcpyToSymbolAsync(c_ecp, ecp, sizeof(AiqmcEcp), 0, cudaMemcpyHostToDevice, st));
+        h_ecp = *ecp;
+        h_valid = true;
+      }
+      if (stages & 1) {
+        AQ_CUDA_OK(prep(k_energy_base<NE, NA, true>));
+        k_energy_base<NE, NA, true><<<g1, kThreads, kSmem, st>>>(*sys, params, pos, rot, B, e_l, w);
+      }
+      if (stages & 2) {
+        AQ_CUDA_OK(prep(k_ecp_quad<NE, NA>));
+        const int64_t nt = B * NE * NA * AIQMC_NQUAD;
+        const unsigned g2 = (unsigned)((nt + kThreads - 1) / kThreads);
+        k_ecp_quad<NE, NA><<<g2, kThreads, kSmem, st>>>(*sys, params, pos, rot, B, w);
+      }
+      if (stages & 4) k_energy_final<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(B, e_l, w);
     }
     AQ_CUDA_OK(cudaGetLastError());
     return AIQMC_OK;

@@ -13,6 +13,6 @@ struct OpsTable {
   int (*sweep)(const AiqmcSystem*, const double*, double*, const double*, const double*, const double*, int64_t,
                double, double, int, uint8_t*, double*, double*, void*, int64_t, cudaStream_t);
   int (*energy)(const AiqmcSystem*, const AiqmcEcp*, const double*, const double*, const double*, int64_t, double*,
-                void*, int64_t, cudaStream_t);
+                void*, int64_t, int, cudaStream_t);
 };
 }  // namespace aiqmc

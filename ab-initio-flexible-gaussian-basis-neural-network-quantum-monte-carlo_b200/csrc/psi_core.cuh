@@ -73,6 +73,36 @@ AQ_HD constexpr AiqmcLayout make_layout(int N, int A) {
   return L;
 }
 
+
+// Compile-time view of the layout.  NOTE: a function-local `constexpr AiqmcLayout` that is indexed
+// with a runtime layer number gets materialised in local memory, and nvcc 12.9's stack colouring
+// then overlapped it with the caller's gradient buffer (observed on sm_100a: the first 19 doubles
+// of grad came back as layout offsets).  The selectors below keep every offset an immediate.
+template <int V0, int V1, int V2> struct Sel3 {
+  AQ_HD constexpr int operator[](int l) const { return l == 0 ? V0 : (l == 1 ? V1 : V2); }
+};
+template <int V0, int V1> struct Sel2 {
+  AQ_HD constexpr int operator[](int l) const { return l == 0 ? V0 : V1; }
+};
+template <int NE, int NA>
+struct LayoutC {
+  static constexpr AiqmcLayout K = make_layout(NE, NA);
+  Sel3<K.conv_w[0], K.conv_w[1], K.conv_w[2]> conv_w;
+  Sel3<K.conv_b[0], K.conv_b[1], K.conv_b[2]> conv_b;
+  Sel3<K.sing_w[0], K.sing_w[1], K.sing_w[2]> sing_w;
+  Sel3<K.sing_b[0], K.sing_b[1], K.sing_b[2]> sing_b;
+  Sel2<K.dbl_w[0], K.dbl_w[1]> dbl_w;
+  Sel2<K.dbl_b[0], K.dbl_b[1]> dbl_b;
+  Sel3<K.yn_w[0], K.yn_w[1], K.yn_w[2]> yn_w;
+  Sel3<K.yn_b[0], K.yn_b[1], K.yn_b[2]> yn_b;
+  Sel2<K.orb_w[0], K.orb_w[1]> orb_w;
+  Sel2<K.orb_b[0], K.orb_b[1]> orb_b;
+  static constexpr int y_w = K.y_w, jas_alpha = K.jas_alpha, jas_cusp = K.jas_cusp, jas_beta = K.jas_beta,
+                       jas_c34 = K.jas_c34, jas_c14 = K.jas_c14, env_pi = K.env_pi, env_sx = K.env_sx,
+                       env_alpha = K.env_alpha, env_beta = K.env_beta, atoms = K.atoms, charges = K.charges,
+                       total = K.total;
+};
+
 // ---------------------------------------------------------------------------------------
 // scalars: double, or a jet carrying d/dx_c and d2/dx_c^2 for the 3 coordinates of ONE electron
 // ---------------------------------------------------------------------------------------
@@ -167,7 +197,7 @@ struct Psi {
   static AQ_HD void electron_local(const double* __restrict__ P, int e, const S xe[3], S* __restrict__ h0,
                                    S y[6], S& env, S& jae) {
     using Op = ScalarOps<S>;
-    constexpr AiqmcLayout L = make_layout(NE, NA);
+    constexpr LayoutC<NE, NA> L{};
     const double c0 = 0.28209479177387814;        // 1/2 sqrt(1/pi)
     const double c1 = 0.48860251190291992;        // sqrt(3/(4 pi))
     const double k15h = 1.0925484305920792;       // 1/2 sqrt(15/pi)
@@ -238,7 +268,7 @@ struct Psi {
   template <class S>
   static AQ_HD void pair_chain(const double* __restrict__ P, const S d[3], bool diag, S h0[4], S h1[4], S h2[4]) {
     using Op = ScalarOps<S>;
-    constexpr AiqmcLayout L = make_layout(NE, NA);
+    constexpr LayoutC<NE, NA> L{};
     if (diag) {
       h0[0] = Op::cst(0.0);
     } else {
@@ -266,7 +296,7 @@ struct Psi {
                               const S* __restrict__ gup, const S* __restrict__ gdn, const S Gu[4], const S Gd[4],
                               S hout[4]) {
     using Op = ScalarOps<S>;
-    constexpr AiqmcLayout L = make_layout(NE, NA);
+    constexpr LayoutC<NE, NA> L{};
     constexpr int DTOT = 3 * DIN + 8, Q = DTOT / 4;
     const double* cw = P + L.conv_w[l] + k * DTOT;
     const double* cb = P + L.conv_b[l] + k * Q;
@@ -372,7 +402,7 @@ struct Psi {
   // ---- forward pass up to the orbital matrix; fills `pr`, returns M (row-major N x N)
   static AQ_HD void forward(const AiqmcSystem& sys, const double* __restrict__ P, const double* __restrict__ x,
                             Primal& pr, cplx* __restrict__ M) {
-    constexpr AiqmcLayout L = make_layout(NE, NA);
+    constexpr LayoutC<NE, NA> L{};
     const double inv_nup = 1.0 / sys.n_up, inv_ndn = 1.0 / sys.n_dn;
     double jas = 0.0;
     for (int e = 0; e < N; ++e) {
@@ -454,7 +484,7 @@ struct Psi {
   static AQ_HD void eval_deriv(const AiqmcSystem& sys, const double* __restrict__ P, const double* __restrict__ x,
                                double& phase, double& logabs, double* __restrict__ grad, double& lap) {
     using J = Jet<LAP>;
-    constexpr AiqmcLayout L = make_layout(NE, NA);
+    constexpr LayoutC<NE, NA> L{};
     using Op = ScalarOps<J>;
     Primal pr;
     cplx Mi[N * N];

@@ -110,7 +110,8 @@ class WalkerEngine:
         return dict(accept=accept, grad_eff_old=drift, aux=aux)
 
     # ---- local energy -----------------------------------------------------------------
-    def local_energy(self, pos: torch.Tensor, rot: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def local_energy(self, pos: torch.Tensor, rot: Optional[torch.Tensor] = None, stages: int = 7,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """All-electron (no ECP table): real (B,).  ccECP: complex128 (B,) (quirk Q25)."""
         p = self._pos(pos).reshape(-1, 3 * self.n)
         B = p.shape[0]
@@ -122,9 +123,10 @@ class WalkerEngine:
                 if rot is None:
                     raise ValueError("ccECP local energy needs the per-walker rotation matrices (B,3,3)")
                 r = torch.as_tensor(rot).to(device=self.device, dtype=torch.float64).reshape(B, 9).contiguous()
-                e = torch.empty((B, 2), dtype=torch.float64, device=self.device)
-                rc = self.lib.aiqmc_local_energy_ecp(C.byref(self.sys), C.byref(self.ecp), _ptr(self.params_dev),
-                                                     _ptr(p), _ptr(r), B, _ptr(e), _ptr(ws), ws.numel(), _stream())
+                e = out if out is not None else torch.empty((B, 2), dtype=torch.float64, device=self.device)
+                rc = self.lib.aiqmc_local_energy_ecp_stages(C.byref(self.sys), C.byref(self.ecp),
+                                                            _ptr(self.params_dev), _ptr(p), _ptr(r), B, _ptr(e),
+                                                            _ptr(ws), ws.numel(), int(stages), _stream())
                 _lib.check(rc, "aiqmc_local_energy_ecp")
                 return torch.view_as_complex(e)
             e = torch.empty(B, dtype=torch.float64, device=self.device)

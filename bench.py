@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- VMC walker-steps/s incl. local energy (BASELINE.json metric).
+
+One "step" = one walkers_update sweep (AIQMCrelease3/VMC/VMCmcstep.py:28-111) + one ccECP
+local_energy (Energy/pphamiltonian.py:130-190) + the energy mean/variance partials, over one batch
+of synthetic walkers.  Workload (BASELINE.json configs[1]): carbon atom, ccECP, N=4 electrons,
+A=1, 65,536 walkers per GPU (weak scaling: walkers are the independent units, sharded across
+ranks; the only collective is the 4-double energy all-reduce).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference ...                     # CPU port of the reference (oracle), timed on host cores
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SEED = 20260101
+TSTEP = 0.05
+WALKERS_PER_GPU = 65536
+METRIC = "VMC walker-steps/s incl. local energy"
+UNIT = "walker-steps/s"
+
+
+def flops_psi(n, a):
+    """F(N,A) = (8/3)N^3 + 130N^2 + 40NA flop per psi value."""
+    return (8.0 / 3.0) * n ** 3 + 130.0 * n ** 2 + 40.0 * n * a
+
+
+def flops_walker_step_ecp(n, a):
+    """A_ECP = (6N + 5 + 50NA) F   (fixed algorithmic count, independent of implementation tricks)."""
+    return (6 * n + 5 + 50 * n * a) * flops_psi(n, a)
+
+
+def build_case(nwalkers, seed=SEED):
+    from common import Case, ecp_tables
+    case = Case(n=4, natoms=1, spins=[1., -1., 1., -1.], seed=seed, atoms=[[0., 0., 0.]], charges=[4.0],
+                nwalkers=nwalkers, width=1.0)
+    # "random-init params": the reference's init scales (weights N(0,1)/sqrt(fan_in), biases N(0,1),
+    # Jastrow/envelope = 1), SURVEY 8(d)
+    case.params = case.net.init(np.random.default_rng(seed), randomize_all=False)
+    return case, ecp_tables(1)
+
+
+def make_rand(rng, B, n, tstep):
+    return dict(gauss1=(rng.standard_normal((B, 3 * n)) * math.sqrt(tstep)),
+                gauss2=(rng.standard_normal((B, n, 3 * n)) * math.sqrt(tstep)),
+                rnd=rng.uniform(size=(B, n)))
+
+
+def random_rot(rng, B):
+    q, r = np.linalg.qr(rng.standard_normal((B, 3, 3)))
+    return q * np.sign(np.diagonal(r, axis1=-2, axis2=-1))[:, None, :]
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for k, name in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (a port of the reference), all host threads
+# ------------------------------------------------------------------------------------------
+def cpu_step_fn(nwalkers, dtype=torch.float32):
+    """Returns (fn, description): fn() runs ONE walker-step batch (sweep + ccECP energy) on the CPU oracle
+    in the reference's own dtype (float32/complex64, quirk Q1)."""
+    from oracle import aiqmc_oracle as O
+    case, tabs = build_case(nwalkers)
+    net = O.make_ai_net(**case.kw, dtype=dtype)
+    params = O.tree_map(lambda t: t.to(dtype), case.params)
+    rng = np.random.default_rng(SEED + 7)
+    logabs = O.select_output(net.apply, 1)
+    le = O.local_energy_ecp(net.apply, O.make_log_network(net.apply), case.charges, None, tabs['rn_local'],
+                            tabs['local_coes'], tabs['local_exps'], tabs['rn_non_local'], tabs['non_local_coes'],
+                            tabs['non_local_exps'], 1, case.n, 3, 2)
+    B, n = nwalkers, case.n
+    state = {"pos": torch.tensor(case.pos, dtype=dtype)}
+    atoms, spins = torch.tensor(case.atoms, dtype=dtype), torch.tensor(case.spins, dtype=dtype)
+    charges = torch.tensor(case.charges, dtype=dtype)
+
+    def fn():
+        rand = {k: torch.tensor(v, dtype=dtype) for k, v in make_rand(rng, B, n, TSTEP).items()}
+        rot = torch.tensor(random_rot(rng, B), dtype=dtype)
+        data = O.AINetData(positions=state["pos"], spins=spins.expand(B, n), atoms=atoms.expand(B, 1, 3),
+                           charges=charges.expand(B, 1))
+        new = O.walkers_update(logabs, params, data, rand, TSTEP, 3, n, B)
+        state["pos"] = new.positions
+        e, _ = le(params, rot, O.AINetData(positions=new.positions, spins=spins, atoms=atoms, charges=charges))
+        return float(e.real.mean())
+    return fn
+
+
+def time_cpu(nwalkers, steps, warmup):
+    fn = cpu_step_fn(nwalkers)
+    for _ in range(warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    dt = time.perf_counter() - t0
+    return nwalkers * steps / dt, dt / steps
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  JAX is not installable in this
+    image, so this is the oracle port (kind "port") in float32 on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    nwalk = args.cpu_walkers
+    value, sec_per_step = time_cpu(nwalk, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C atom ccECP (N=4, A=1) VMC sweep + local energy", "walkers_per_step": nwalk,
+                       "tstep": TSTEP, "note": "oracle port of AIQMCrelease3 (torch CPU, float32/complex64); "
+                       "JAX is not installable here so the genuine reference cannot run"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{nwalk} walkers x {args.steps} steps of the same workload"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch.distributed as dist
+    import aiqmc_b200
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.walkers
+    case, tabs = build_case(B, seed=SEED + rank)          # different walkers per rank, same parameters
+    case.params = build_case(8, seed=SEED)[0].params
+    n, a = case.n, case.a
+    ecp = aiqmc_b200.make_ecp(1, list_l=2, **tabs)
+    eng = aiqmc_b200.WalkerEngine(case.spec(), case.params, ecp=ecp, device=dev)
+    lib = eng.lib
+    rng = np.random.default_rng(SEED + 1000 + rank)
+    nsets = args.steps + args.warmup
+    # pinned host copies of every step's inputs (e2e leg) + device-resident copies (kernel leg)
+    host_sets = []
+    for _ in range(nsets):
+        r = make_rand(rng, B, n, TSTEP)
+        r["rot"] = random_rot(rng, B)
+        host_sets.append({k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in r.items()})
+    dev_sets = [{k: v.to(dev) for k, v in s.items()} for s in host_sets]
+    pos0 = torch.from_numpy(case.pos.copy()).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)      # 256 MiB > 126 MB L2
+
+    e_l = torch.empty((B, 2), dtype=torch.float64, device=dev)
+
+    def step(pos, s, timed_quad=None):
+        eng.vmc_sweep(pos, s["gauss1"], s["gauss2"], s["rnd"], TSTEP, want_accept=False)
+        if timed_quad is None:
+            eng.local_energy(pos, s["rot"], out=e_l)
+        else:
+            eng.local_energy(pos, s["rot"], stages=1, out=e_l)
+            timed_quad[0].record()
+            eng.local_energy(pos, s["rot"], stages=2, out=e_l)
+            timed_quad[1].record()
+            eng.local_energy(pos, s["rot"], stages=4, out=e_l)
+        stats = eng.energy_stats(torch.view_as_complex(e_l))
+        if world > 1:
+            dist.all_reduce(stats)                          # the path's only collective (pploss.py:165-167)
+        return stats
+
+    launches_per_step = 6 + 3 + 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- kernel leg: inputs resident in HBM ------------------------------------------------
+    pos = pos0.to(dev)
+    for w in range(args.warmup):
+        step(pos, dev_sets[w])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    evq = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall0 = time.perf_counter()
+    last = None
+    for k in range(args.steps):
+        flush.zero_()                                       # L2 flush between timed iterations (untimed)
+        ev[k][0].record()
+        last = step(pos, dev_sets[args.warmup + k], timed_quad=evq[k])
+        ev[k][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    ms_steps = [a_.elapsed_time(b_) for a_, b_ in ev]
+    ms_quad = [a_.elapsed_time(b_) for a_, b_ in evq]
+    t_dev = torch.tensor([sum(ms_steps) / 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    total_time = float(t_dev)
+    value = world * B * args.steps / total_time
+    stats = last.cpu().numpy()
+    e_mean = stats[0] / stats[3]
+
+    # ---- e2e leg: host buffers in, host result out, every step -------------------------------
+    pos_host = pos0.clone().pin_memory()
+    stats_host = torch.empty(4, dtype=torch.float64).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in host_sets[0].values()) + pos_host.numel() * 8
+    d2h = pos_host.numel() * 8 + 32
+
+    def e2e_step(s):
+        p = pos_host.to(dev, non_blocking=True)
+        sd = {k: v.to(dev, non_blocking=True) for k, v in s.items()}
+        st = step(p, sd)
+        pos_host.copy_(p, non_blocking=True)
+        stats_host.copy_(st, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for w in range(min(args.warmup, 3)):
+        e2e_step(host_sets[w])
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for k in range(args.steps):
+        e2e_step(host_sets[args.warmup + k])
+    ev1.record()
+    barrier()
+    t_e2e = torch.tensor([ev0.elapsed_time(ev1) / 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(t_e2e)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_ecp_quad): FP64 FMA peak measured live --------------
+    sink = torch.zeros(8, dtype=torch.float64, device=dev)
+    fl = C.c_double(0.0)
+    st_ptr = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    best = 0.0
+    for it in range(6):
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        lib.aiqmc_bench_dfma(200000, C.c_void_p(sink.data_ptr()), C.byref(fl), st_ptr)
+        a1.record()
+        torch.cuda.synchronize()
+        if it >= 1:
+            best = max(best, fl.value / (a0.elapsed_time(a1) * 1e-3) / 1e12)
+    quad_s = float(np.mean(ms_quad)) * 1e-3
+    quad_flops = 50.0 * n * a * flops_psi(n, a) * B            # algorithmic flops of one k_ecp_quad launch
+    achieved = quad_flops / quad_s / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("k_ecp_quad_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "fp64", "kernel": "k_ecp_quad<4,1>", "achieved": achieved, "peak": best, "unit": "TFLOP/s",
+                "frac": achieved / best if best > 0 else None, "traffic": traffic,
+                "share_of_step": float(np.mean(ms_quad) / np.mean(ms_steps)),
+                "whole_step_frac": (value / world) * flops_walker_step_ecp(n, a) / 1e12 / best if best > 0 else None,
+                "note": "compute-bound on the FP64 pipe (SURVEY 8d), not HBM/tensor; achieved = SURVEY's fixed "
+                        "algorithmic flops 50*N*A*F(N,A) per walker / CUDA-event time of the kernel; peak = DFMA "
+                        "microbenchmark measured in this run (nominal B200 FP64 ~37 TFLOP/s; MEASURED_PEAKS.json "
+                        "has no FP64 entry)"}
+
+    # ---- CPU baseline (bounded sample, rank 0, N=1 only) ------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        v, sps = time_cpu(args.cpu_walkers, 2, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{args.cpu_walkers} walkers x 2 steps (oracle port, torch CPU float32, {sps:.2f} s/step)"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_time / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C atom ccECP (N=4, A=1): VMC sweep + ccECP local energy, BASELINE configs[1]",
+                       "walkers_per_gpu": B, "global_walkers": B * world, "tstep": TSTEP, "nsteps_per_step": 1,
+                       "params": "random-init (reference init scales)", "parallelism": f"walker-sharded x{world}",
+                       "l2": "256 MiB flush write between timed iterations (untimed)",
+                       "rng": "per-step gauss/uniform/rotation arrays pre-generated (parity-mode inputs)"},
+            "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": t_wall, "energy_mean_last_step": e_mean}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--walkers", type=int, default=WALKERS_PER_GPU, help="walkers per GPU")
+    ap.add_argument("--cpu-walkers", type=int, default=256, help="walkers in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

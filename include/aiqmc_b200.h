@@ -126,6 +126,13 @@ int aiqmc_local_energy_ae(const AiqmcSystem* sys, const double* params, const do
 int aiqmc_local_energy_ecp(const AiqmcSystem* sys, const AiqmcEcp* ecp, const double* params,
                            const double* pos, const double* rot, int64_t n_walkers, double* e_l,
                            void* workspace, int64_t workspace_bytes, void* stream);
+/* Same, running only the stages in stage_mask: 1 = KE + Coulomb + local channel + v_l tables
+ * (k_energy_base), 2 = non-local quadrature (k_ecp_quad), 4 = assembly.  Stages must be issued in
+ * order over the same workspace; used by bench.py to time the dominant kernel on its own stream. */
+int aiqmc_local_energy_ecp_stages(const AiqmcSystem* sys, const AiqmcEcp* ecp, const double* params,
+                                  const double* pos, const double* rot, int64_t n_walkers, double* e_l,
+                                  void* workspace, int64_t workspace_bytes, int32_t stage_mask,
+                                  void* stream);
 /* Block-reduced [sum Re E, sum Im E, sum |E|^2, count] -> stats[4] (device), the partials of
  * pmean(mean(e_l)) and the variance at Loss/pploss.py:165-167; all-reduced over GPUs by the host
  * (NCCL sum of 4 doubles).  e_l_stride = 1 (real) or 2 (complex interleaved). */
@@ -155,6 +162,12 @@ int aiqmc_branch_comb(const double* weights, int64_t n_walkers, double u, int32_
 /* Gather walkers by index: pos_out[b] = pos_in[newinds[b]]  (HBM-bound, 24N+4 B/walker). */
 int aiqmc_gather_walkers(const double* pos_in, const int32_t* newinds, int64_t n_walkers,
                          int32_t row_doubles, double* pos_out, void* stream);
+
+/* ---- measurement aid ------------------------------------------------------------------ */
+/* Dependent-free FP64 FMA loop over the whole chip (148*8 CTAs x 256 threads x 8 chains):
+ * performs *flops_out = grid*256*8*2*iters flops; time it with CUDA events to get the DFMA peak
+ * that bench.py uses as the roofline denominator (MEASURED_PEAKS.json has no FP64 figure). */
+int aiqmc_bench_dfma(int64_t iters, double* sink, double* flops_out, void* stream);
 
 #ifdef __cplusplus
 }
