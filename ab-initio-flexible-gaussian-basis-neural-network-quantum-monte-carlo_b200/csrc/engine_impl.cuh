@@ -159,18 +159,21 @@ __global__ void __launch_bounds__(kThreads) k_sweep_moved(AiqmcSystem sys, const
     const int64_t b = t / NE;
     const int i = (int)(t - b * NE);
     const double te = taueff_of(w.scal[0], tau, acyrus);
-    double x[3 * NE], g[3 * NE], ph, la, lp;
-    for (int q = 0; q < 3 * NE; ++q) x[q] = pos[b * 3 * NE + q];
+    double x[3 * NE], g[3 * NE], ph, la, lp, xn[3];
     for (int c = 0; c < 3; ++c) {
       // g = grad_eff * tstep + gauss ; x2 = x1 + g on electron i only   (VMCmcstep.py:60-78)
       const double step = (w.grad[b * 3 * NE + 3 * i + c] * te) * tau + gauss1[b * 3 * NE + 3 * i + c];
-      const double xn = step + x[3 * i + c];
-      x[3 * i + c] = xn;
-      w.xprop[t * 3 + c] = xn;
+      xn[c] = step + pos[b * 3 * NE + 3 * i + c];
+      w.xprop[t * 3 + c] = xn[c];
     }
+    // no dynamically indexed stores into x (nvcc 12.9 miscompiled that pattern in k_ecp_quad)
+    for (int e = 0; e < NE; ++e)
+      for (int c = 0; c < 3; ++c) x[3 * e + c] = (e == i) ? xn[c] : pos[b * 3 * NE + 3 * e + c];
     Psi<NE, NA>::template eval_deriv<false>(sys, P, x, ph, la, g, lp);
     for (int q = 0; q < 3 * NE; ++q) v2 += g[q] * g[q];
-    for (int c = 0; c < 3; ++c) w.gnew[t * 3 + c] = g[3 * i + c];
+    for (int e = 0; e < NE; ++e)
+      if (e == i)
+        for (int c = 0; c < 3; ++c) w.gnew[t * 3 + c] = g[3 * e + c];
     w.logabs2[t] = la;
   }
   const double s = block_sum<kThreads>(v2, red);
@@ -234,7 +237,7 @@ struct EnergyWs {
 
 inline int64_t energy_ws_bytes(int n, int a, int64_t B, int with_ecp) {
   int64_t s = align256(B * 8);
-  if (with_ecp) s += 2 * align256(B * 8) + align256(B * 4 * 8) + align256(B * n * a * 4 * 8) + align256(B * 2 * 8);
+  if (with_ecp) s += 2 * align256(B * 8) + align256(B * 4 * 8) + align256(B * n * a * 4 * 8 + 64 * 8 * 8) + align256(B * 2 * 8);
   return s;
 }
 
@@ -245,7 +248,7 @@ inline EnergyWs carve_energy_ws(void* ws, int n, int a, int64_t B) {
   w.logabs = (double*)p; p += align256(B * 8);
   w.phase = (double*)p; p += align256(B * 8);
   w.gnorm = (double*)p; p += align256(B * 4 * 8);
-  w.vl = (double*)p; p += align256(B * n * a * 4 * 8);
+  w.vl = (double*)p; p += align256(B * n * a * 4 * 8 + 64 * 8 * 8);
   w.epp = (double*)p;
   return w;
 }
@@ -342,10 +345,8 @@ __global__ void __launch_bounds__(kThreads) k_ecp_quad(AiqmcSystem sys, const do
   bool any = false;
   for (int l = 0; l < AIQMC_ECP_MAX_L; ++l) any = any || (vl[l] != 0.0);
   if (!any) return;                       // exact zero coefficient: contributes exactly 0
-  double x[3 * NE];
-  for (int q = 0; q < 3 * NE; ++q) x[q] = pos[b * 3 * NE + q];
   double ae[3], nh[3];
-  for (int c = 0; c < 3; ++c) ae[c] = x[3 * i + c] - P[L.atoms + 3 * a + c];
+  for (int c = 0; c < 3; ++c) ae[c] = pos[b * 3 * NE + 3 * i + c] - P[L.atoms + 3 * a + c];
   const double r = sqrt(ae[0] * ae[0] + ae[1] * ae[1] + ae[2] * ae[2]);
   for (int l = 0; l < 3; ++l) {           // Points = O @ rot   (pseudopotential.py:236-240)
     double v = 0.0;
@@ -353,11 +354,12 @@ __global__ void __launch_bounds__(kThreads) k_ecp_quad(AiqmcSystem sys, const do
     nh[l] = v;
   }
   double dot = 0.0;
-  for (int c = 0; c < 3; ++c) {
-    const double rc = r * nh[c];
-    dot += ae[c] * rc;
-    x[3 * i + c] = rc;                    // quirk Q13: absolute position r_ia * n_hat
-  }
+  for (int c = 0; c < 3; ++c) dot += ae[c] * (r * nh[c]);
+  // moved configuration, built without dynamically indexed stores (keeps x in registers);
+  // quirk Q13: electron i is placed at the absolute position r_ia * n_hat
+  double x[3 * NE];
+  for (int e = 0; e < NE; ++e)
+    for (int c = 0; c < 3; ++c) x[3 * e + c] = (e == i) ? r * nh[c] : pos[b * 3 * NE + 3 * e + c];
   const double cs = dot / (r * (r * w.gnorm[4 * b + quad_group(p)]));   // quirk Q14
   double ph, la;
   Psi<NE, NA>::eval_value(sys, P, x, ph, la);
@@ -370,6 +372,9 @@ __global__ void __launch_bounds__(kThreads) k_ecp_quad(AiqmcSystem sys, const do
                         7.0 * k4 * 0.5 * (5.0 * cs * cs * cs - 3.0 * cs)};
   double f = 0.0;
   for (int l = 0; l < AIQMC_ECP_MAX_L; ++l) f += vl[l] * pl[l];
+#ifdef AIQMC_DEBUG_QUAD
+  if (t < 64) { double* d = w.vl + B * NE * NA * 4 + t * 8; d[0] = la; d[1] = ph; d[2] = cs; d[3] = f; d[4] = rr; d[5] = ri; d[6] = r; d[7] = dr; }
+#endif
   atomicAdd(&w.epp[2 * b], f * rr);
   atomicAdd(&w.epp[2 * b + 1], f * ri);
 }
