@@ -17,6 +17,9 @@ namespace aiqmc {
 
 constexpr int kThreads = 128;       // threads per CTA for the per-configuration kernels
 constexpr int kRedThreads = 256;
+#ifndef AIQMC_QUAD_MINB
+#define AIQMC_QUAD_MINB 1            // min resident CTAs/SM requested for the value-only kernels
+#endif
 
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -327,7 +330,7 @@ __global__ void __launch_bounds__(kThreads) k_energy_base(AiqmcSystem sys, const
 
 // one thread = one quadrature point of one (electron, atom) pair of one walker
 template <int NE, int NA>
-__global__ void __launch_bounds__(kThreads) k_ecp_quad(AiqmcSystem sys, const double* __restrict__ params,
+__global__ void __launch_bounds__(kThreads, AIQMC_QUAD_MINB) k_ecp_quad(AiqmcSystem sys, const double* __restrict__ params,
                                                        const double* __restrict__ pos,
                                                        const double* __restrict__ rot, int64_t B, EnergyWs w) {
   extern __shared__ double sP[];
