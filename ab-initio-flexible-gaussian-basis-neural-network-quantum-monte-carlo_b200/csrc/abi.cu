@@ -232,7 +232,7 @@ int aiqmc_local_energy_ae(const AiqmcSystem* sys, const double* params, const do
 int aiqmc_local_energy_ecp_stages(const AiqmcSystem* sys, const AiqmcEcp* ecp, const double* params,
                                   const double* pos, const double* rot, int64_t n_walkers, double* e_l,
                                   void* workspace, int64_t workspace_bytes, int32_t stage_mask, void* stream) {
-  if (!sys_ok(sys) || !ecp || !params || n_walkers < 0 || (stage_mask & ~7) || stage_mask == 0) return AIQMC_E_BADARG;
+  if (!sys_ok(sys) || !ecp || !params || n_walkers < 0 || (stage_mask & ~15) || (stage_mask & 7) == 0) return AIQMC_E_BADARG;
   if (n_walkers > 0 && (!pos || !rot || !e_l || !workspace)) return AIQMC_E_BADARG;
   if (ecp->k_loc < 0 || ecp->k_loc > AIQMC_ECP_MAX_K || ecp->k_nl < 0 || ecp->k_nl > AIQMC_ECP_MAX_K ||
       ecp->n_l < 1 || ecp->n_l > AIQMC_ECP_MAX_L) return AIQMC_E_BADARG;

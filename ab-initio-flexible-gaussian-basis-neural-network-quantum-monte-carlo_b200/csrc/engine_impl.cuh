@@ -46,6 +46,7 @@ template <int NE, int NA>
 __device__ __forceinline__ const double* stage_params(const double* __restrict__ params, double* sP) {
   constexpr int total = make_layout(NE, NA).total;
   for (int i = threadIdx.x; i < total; i += blockDim.x) sP[i] = params[i];
+  if (threadIdx.x < kExpTab) g_exp_tab[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / kExpTab));
   __syncthreads();
   return sP;
 }
@@ -236,10 +237,14 @@ struct EnergyWs {
   double* gnorm;     // (B,4)  Frobenius norm of each rotated point group (quirk Q14)
   double* vl;        // (B,N,A,4)  v_l(r_ia)
   double* epp;       // (B,2)  non-local energy accumulator (re, im)
+  double* cache;     // (B, MoveCache::SIZE) per-walker single-electron-move cache
 };
+
+inline int64_t move_cache_doubles(int n, int a) { return 12 * n * n + 24 * n + 4 * a * n + 8 * a + 8 * n + 4; }
 
 inline int64_t energy_ws_bytes(int n, int a, int64_t B, int with_ecp) {
   int64_t s = align256(B * 8);
+  if (with_ecp) s += align256(B * move_cache_doubles(n, a) * 8);
   if (with_ecp) s += 2 * align256(B * 8) + align256(B * 4 * 8) + align256(B * n * a * 4 * 8 + 64 * 8 * 8) + align256(B * 2 * 8);
   return s;
 }
@@ -252,7 +257,8 @@ inline EnergyWs carve_energy_ws(void* ws, int n, int a, int64_t B) {
   w.phase = (double*)p; p += align256(B * 8);
   w.gnorm = (double*)p; p += align256(B * 4 * 8);
   w.vl = (double*)p; p += align256(B * n * a * 4 * 8 + 64 * 8 * 8);
-  w.epp = (double*)p;
+  w.epp = (double*)p; p += align256(B * 2 * 8);
+  w.cache = (double*)p;
   return w;
 }
 
@@ -272,7 +278,8 @@ __global__ void __launch_bounds__(kThreads) k_energy_base(AiqmcSystem sys, const
   if (b >= B) return;
   double x[3 * NE], g[3 * NE], ph, la, lp;
   for (int q = 0; q < 3 * NE; ++q) x[q] = pos[b * 3 * NE + q];
-  Psi<NE, NA>::template eval_deriv<true>(sys, P, x, ph, la, g, lp);
+  static_assert(MoveCache<NE, NA>::SIZE == 12 * NE * NE + 24 * NE + 4 * NA * NE + 8 * NA + 8 * NE + 4, "cache size");
+  Psi<NE, NA>::template eval_deriv<true>(sys, P, x, ph, la, g, lp, ECP ? w.cache + b * MoveCache<NE, NA>::SIZE : nullptr);
   double g2 = 0.0;
   for (int q = 0; q < 3 * NE; ++q) g2 += g[q] * g[q];
   double e = -0.5 * lp - 0.5 * g2;                                // pphamiltonian.py:100-102
@@ -389,6 +396,10 @@ static __global__ void k_energy_final(int64_t B, double* __restrict__ e_l, Energ
   e_l[2 * b + 1] = w.epp[2 * b + 1];
 }
 
+}  // namespace aiqmc
+#include "ecp_coop.cuh"
+namespace aiqmc {
+
 // ---------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------
@@ -403,6 +414,7 @@ extern int g_last_cuda_error;
 template <int NE, int NA>
 struct Launch {
   static constexpr int kSmem = make_layout(NE, NA).total * 8;
+  static constexpr bool kCoop = (NE <= 16 && NA <= 4);   // lane-per-electron quadrature kernel available
 
   template <class K>
   static cudaError_t prep(K kernel) {
@@ -478,10 +490,22 @@ struct Launch {
         k_energy_base<NE, NA, true><<<g1, kThreads, kSmem, st>>>(*sys, params, pos, rot, B, e_l, w);
       }
       if (stages & 2) {
-        AQ_CUDA_OK(prep(k_ecp_quad<NE, NA>));
-        const int64_t nt = B * NE * NA * AIQMC_NQUAD;
-        const unsigned g2 = (unsigned)((nt + kThreads - 1) / kThreads);
-        k_ecp_quad<NE, NA><<<g2, kThreads, kSmem, st>>>(*sys, params, pos, rot, B, w);
+        if constexpr (kCoop) {
+          if (!(stages & 8)) {
+            const int T = coop_threads<NE, NA>();
+            const int smem = CoopSmem<NE, NA>::doubles(T / GroupSize<NE>::G) * 8;
+            AQ_CUDA_OK(cudaFuncSetAttribute(k_ecp_coop<NE, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            AQ_CUDA_OK(cudaFuncSetAttribute(k_ecp_coop<NE, NA>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                            cudaSharedmemCarveoutMaxShared));
+            k_ecp_coop<NE, NA><<<(unsigned)B, T, smem, st>>>(*sys, params, pos, rot, B, w.cache, w);
+          }
+        }
+        if (!kCoop || (stages & 8)) {   // thread-per-point reference kernel (N > 16, or forced for cross-checks)
+          AQ_CUDA_OK(prep(k_ecp_quad<NE, NA>));
+          const int64_t nt = B * NE * NA * AIQMC_NQUAD;
+          const unsigned g2 = (unsigned)((nt + kThreads - 1) / kThreads);
+          k_ecp_quad<NE, NA><<<g2, kThreads, kSmem, st>>>(*sys, params, pos, rot, B, w);
+        }
       }
       if (stages & 4) k_energy_final<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(B, e_l, w);
     }

@@ -25,6 +25,7 @@
 #include <stdint.h>
 
 #include "../../include/aiqmc_b200.h"
+#include "fastmath.cuh"
 
 #ifdef __CUDACC__
 #define AQ_HD __host__ __device__ __forceinline__
@@ -157,13 +158,24 @@ template <bool L> AQ_HD Jet<L> chain(const Jet<L>& u, double f, double f1, doubl
   return r;
 }
 
-// fast double-precision exp / tanh live in fastmath.cuh (included by the kernels); the default
-// here is libm so the host build and the first device build agree with the oracle to ~1 ulp.
-#ifndef AQ_TANH
-#define AQ_TANH(x) tanh(x)
+// exp / tanh: in-house fexp/ftanh (fastmath.cuh) unless AIQMC_LIBM is defined.  On the device the
+// 64-entry 2^(j/64) table lives in shared memory (filled by stage_params in every kernel).
+#ifdef __CUDACC__
+__shared__ double g_exp_tab[kExpTab];
 #endif
-#ifndef AQ_EXP
+AQ_HD const double* exp_tab() {
+#ifdef __CUDA_ARCH__
+  return g_exp_tab;
+#else
+  return host_exp_table();
+#endif
+}
+#ifdef AIQMC_LIBM
+#define AQ_TANH(x) tanh(x)
 #define AQ_EXP(x) exp(x)
+#else
+#define AQ_TANH(x) ftanh(x, exp_tab())
+#define AQ_EXP(x) fexp(x, exp_tab())
 #endif
 
 AQ_HD double s_tanh(double x) { return AQ_TANH(x); }
@@ -183,6 +195,21 @@ AQ_HD cplx cscale(cplx a, double s) { return {a.re * s, a.im * s}; }
 AQ_HD cplx cinv(cplx a) { double n = 1.0 / (a.re * a.re + a.im * a.im); return {a.re * n, -a.im * n}; }
 AQ_HD void cfma(cplx& acc, cplx a, cplx b) { acc.re += a.re * b.re - a.im * b.im; acc.im += a.re * b.im + a.im * b.re; }
 AQ_HD void cfms(cplx& acc, cplx a, cplx b) { acc.re -= a.re * b.re - a.im * b.im; acc.im -= a.re * b.im + a.im * b.re; }
+
+// Per-walker cache consumed by the single-electron-move kernels (ecp_coop.cuh): everything of the
+// base configuration that survives when ONE electron is displaced.
+template <int NE, int NA>
+struct MoveCache {
+  static constexpr int HP = 0;                            // [3][N][N][4]  pair chains h_two^l[i,j,:]
+  static constexpr int GS = HP + 3 * NE * NE * 4;         // [3][2][N][4]  block sums over i of h_two^l[i,j,:]
+  static constexpr int H0 = GS + 3 * 2 * NE * 4;          // [N][4A]       layer-0 one-electron features
+  static constexpr int G0M = H0 + NE * 4 * NA;            // [2][4A]       block MEANS of H0
+  static constexpr int Y = G0M + 2 * 4 * NA;              // [N][6]        Ynlm stream output
+  static constexpr int ENV = Y + NE * 6;                  // [N]
+  static constexpr int JAE = ENV + NE;                    // [N]
+  static constexpr int MISC = JAE + NE;                   // [4] total Jastrow, log|psi|, phase, 0
+  static constexpr int SIZE = MISC + 4;
+};
 
 // ---------------------------------------------------------------------------------------
 template <int NE, int NA>
@@ -396,12 +423,13 @@ struct Psi {
     double g[3][2][4];        // block means of h[1], h[2] (index l = 1,2)
     double y[N][6];
     double env[N];
+    double jae[N];            // per-electron electron-nucleus Jastrow term
     double jastrow;
   };
 
   // ---- forward pass up to the orbital matrix; fills `pr`, returns M (row-major N x N)
   static AQ_HD void forward(const AiqmcSystem& sys, const double* __restrict__ P, const double* __restrict__ x,
-                            Primal& pr, cplx* __restrict__ M) {
+                            Primal& pr, cplx* __restrict__ M, double* __restrict__ hp = nullptr) {
     constexpr LayoutC<NE, NA> L{};
     const double inv_nup = 1.0 / sys.n_up, inv_ndn = 1.0 / sys.n_dn;
     double jas = 0.0;
@@ -409,6 +437,7 @@ struct Psi {
       double xe[3] = {x[3 * e], x[3 * e + 1], x[3 * e + 2]};
       double jae;
       electron_local<double>(P, e, xe, pr.h0[e], pr.y[e], pr.env[e], jae);
+      pr.jae[e] = jae;
       jas += jae;
     }
     for (int s = 0; s < 2; ++s)
@@ -429,6 +458,13 @@ struct Psi {
         double a0[4], a1[4], a2[4];
         pair_chain<double>(P, d, i == j, a0, a1, a2);
         for (int c = 0; c < 4; ++c) { pr.G[0][s][j][c] += a0[c]; pr.G[1][s][j][c] += a1[c]; pr.G[2][s][j][c] += a2[c]; }
+        if (hp) {   // pair-chain cache for the single-electron-move kernels: hp[l][i][j][c]
+          for (int c = 0; c < 4; ++c) {
+            hp[((0 * N + i) * N + j) * 4 + c] = a0[c];
+            hp[((1 * N + i) * N + j) * 4 + c] = a1[c];
+            hp[((2 * N + i) * N + j) * 4 + c] = a2[c];
+          }
+        }
         if (i < j) {   // electron-electron Pade term (Jastrow.py:23-41)
           double r = a0[0];
           jas += P[L.jas_cusp + i * N + j] * r / (1.0 + P[L.jas_alpha + i * N + j] * r);
@@ -468,6 +504,26 @@ struct Psi {
     }
   }
 
+  static AQ_HD void write_cache(const Primal& pr, double logabs, double phase, double* __restrict__ cache) {
+    using MC = MoveCache<NE, NA>;
+    for (int l = 0; l < 3; ++l)
+      for (int s = 0; s < 2; ++s)
+        for (int j = 0; j < N; ++j)
+          for (int c = 0; c < 4; ++c) cache[MC::GS + ((l * 2 + s) * N + j) * 4 + c] = pr.G[l][s][j][c];
+    for (int s = 0; s < 2; ++s)
+      for (int q = 0; q < 4 * A; ++q) cache[MC::G0M + s * 4 * A + q] = pr.g0[s][q];
+    for (int e = 0; e < N; ++e) {
+      for (int q = 0; q < 4 * A; ++q) cache[MC::H0 + e * 4 * A + q] = pr.h0[e][q];
+      for (int m = 0; m < 6; ++m) cache[MC::Y + e * 6 + m] = pr.y[e][m];
+      cache[MC::ENV + e] = pr.env[e];
+      cache[MC::JAE + e] = pr.jae[e];
+    }
+    cache[MC::MISC + 0] = pr.jastrow;
+    cache[MC::MISC + 1] = logabs;
+    cache[MC::MISC + 2] = phase;
+    cache[MC::MISC + 3] = 0.0;
+  }
+
   // ---- value only
   static AQ_HD void eval_value(const AiqmcSystem& sys, const double* __restrict__ P, const double* __restrict__ x,
                                double& phase, double& logabs) {
@@ -482,16 +538,18 @@ struct Psi {
   // ---- value + gradient (+ Laplacian of log|psi| if LAP)
   template <bool LAP>
   static AQ_HD void eval_deriv(const AiqmcSystem& sys, const double* __restrict__ P, const double* __restrict__ x,
-                               double& phase, double& logabs, double* __restrict__ grad, double& lap) {
+                               double& phase, double& logabs, double* __restrict__ grad, double& lap,
+                               double* __restrict__ cache = nullptr) {
     using J = Jet<LAP>;
     constexpr LayoutC<NE, NA> L{};
     using Op = ScalarOps<J>;
     Primal pr;
     cplx Mi[N * N];
-    forward(sys, P, x, pr, Mi);
+    forward(sys, P, x, pr, Mi, cache ? cache + MoveCache<NE, NA>::HP : nullptr);
     double ld;
     gj_inverse(Mi, ld, phase);
     logabs = ld + pr.jastrow;
+    if (cache) write_cache(pr, logabs, phase, cache);
     const double inv_n[2] = {1.0 / sys.n_up, 1.0 / sys.n_dn};
 
     // G[k,c] = sum_j Wc[c,j] E[k,j] Minv[j,k];  T[k,c,l] likewise for every column l (LAP only)

@@ -127,7 +127,8 @@ int aiqmc_local_energy_ecp(const AiqmcSystem* sys, const AiqmcEcp* ecp, const do
                            const double* pos, const double* rot, int64_t n_walkers, double* e_l,
                            void* workspace, int64_t workspace_bytes, void* stream);
 /* Same, running only the stages in stage_mask: 1 = KE + Coulomb + local channel + v_l tables
- * (k_energy_base), 2 = non-local quadrature (k_ecp_quad), 4 = assembly.  Stages must be issued in
+ * (k_energy_base), 2 = non-local quadrature (k_ecp_quad), 4 = assembly, +8 = force the
+ * thread-per-point reference quadrature kernel instead of the lane-per-electron one.  Stages must be issued in
  * order over the same workspace; used by bench.py to time the dominant kernel on its own stream. */
 int aiqmc_local_energy_ecp_stages(const AiqmcSystem* sys, const AiqmcEcp* ecp, const double* params,
                                   const double* pos, const double* rot, int64_t n_walkers, double* e_l,

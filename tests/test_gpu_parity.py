@@ -203,3 +203,18 @@ def test_unsupported_system_and_bad_args_fail_loudly():
     with pytest.raises(ValueError):
         eng.ecp = aiqmc_b200.make_ecp(1, list_l=2, **ecp_tables(1))
         eng.local_energy(torch.tensor(case.pos))           # rotation missing
+
+
+@pytest.mark.parametrize("name,rich", [("C_ecp", True), ("N2_ecp", True), ("odd", True), ("h2like", False)])
+def test_coop_quadrature_matches_thread_per_point_kernel(name, rich):
+    """The lane-per-electron cached kernel (ecp_coop.cuh) against the plain one-thread-per-point kernel."""
+    case = Case(**CASES[name], nwalkers=33, width=0.8)
+    tabs = ecp_tables(case.a, rich=rich)
+    eng = engine(case, ecp=aiqmc_b200.make_ecp(case.a, list_l=2, **tabs))
+    rot = torch.tensor(O.random_rotations(case.rng, case.B))
+    e_coop = eng.local_energy(torch.tensor(case.pos), rot, stages=7).cpu().numpy()
+    e_ref = eng.local_energy(torch.tensor(case.pos), rot, stages=15).cpu().numpy()
+    np.testing.assert_allclose(e_coop, e_ref, rtol=1e-11, atol=1e-11)
+    # run-to-run bit reproducibility of the deterministic reduction
+    e_again = eng.local_energy(torch.tensor(case.pos), rot, stages=7).cpu().numpy()
+    assert np.array_equal(e_coop, e_again)
