@@ -173,6 +173,27 @@ AQ_HD const double* exp_tab() {
 #ifdef AIQMC_LIBM
 #define AQ_TANH(x) tanh(x)
 #define AQ_EXP(x) exp(x)
+#elif defined(AIQMC_TANH_NOINLINE) && defined(__CUDACC__)
+// out-of-line transcendental bodies: the fully unrolled kernels are 170-400 kB of SASS and stall on
+// instruction fetch ("no_instructions"); one shared body per function shrinks them ~3x.
+static __device__ __noinline__ double ftanh_ool(double x) { return ftanh(x, g_exp_tab); }
+static __device__ __noinline__ double fexp_ool(double x) { return fexp(x, g_exp_tab); }
+AQ_HD double tanh_dispatch(double x) {
+#ifdef __CUDA_ARCH__
+  return ftanh_ool(x);
+#else
+  return ftanh(x, host_exp_table());
+#endif
+}
+AQ_HD double exp_dispatch(double x) {
+#ifdef __CUDA_ARCH__
+  return fexp_ool(x);
+#else
+  return fexp(x, host_exp_table());
+#endif
+}
+#define AQ_TANH(x) tanh_dispatch(x)
+#define AQ_EXP(x) exp_dispatch(x)
 #else
 #define AQ_TANH(x) ftanh(x, exp_tab())
 #define AQ_EXP(x) fexp(x, exp_tab())

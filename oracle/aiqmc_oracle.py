@@ -697,3 +697,85 @@ def reconfigure(positions: torch.Tensor, newinds: torch.Tensor, noise: torch.Ten
     if nmiss > 0:
         temp = torch.cat([temp, temp[-1][None, :] + noise[:nmiss]], dim=0)
     return temp, uniq.shape[0]
+
+
+# --------------------------------------------------------------------------
+# T-moves  (DMC/Tmoves.py:32-225)
+# --------------------------------------------------------------------------
+def _lex_gt(a: torch.Tensor, b: torch.Tensor):
+    """jnp `>` on complex numbers is lexicographic: (real, then imag)   (quirk Q25)."""
+    return (a.real > b.real) | ((a.real == b.real) & (a.imag > b.imag))
+
+
+def _lex_le(a: torch.Tensor, b: torch.Tensor):
+    return (a.real < b.real) | ((a.real == b.real) & (a.imag <= b.imag))
+
+
+def searchsorted_scan(arr: torch.Tensor, query: complex):
+    """jnp.searchsorted(arr, query) with side='left', method='scan' (jax/_src/numpy/lax_numpy.py
+    `_searchsorted_via_scan`): a fixed-trip-count bisection that is well defined on UNSORTED input,
+    which is what Tmoves.py:141-149 feeds it (complex cdf, lexicographic compare)."""
+    n = arr.shape[0]
+    low, high = 0, n
+    q = torch.as_tensor(query, dtype=arr.dtype)
+    for _ in range(int(np.ceil(np.log2(n + 1)))):
+        mid = (low + high) // 2
+        if bool(_lex_le(q, arr[mid])):
+            high = mid
+        else:
+            low = mid
+    return high
+
+
+def compute_tmoves(list_l, tstep, nelectrons, natoms, ndim, lognetwork, Rn_non_local, Non_local_coes,
+                   Non_local_exps):
+    """Tmoves.py:32-225 for ONE walker: calculate_ratio_weight_tmoves(data, params, key) with
+    key = dict(rot (3,3), u scalar in [0,1), rnd (N,1)) -- the three draws the reference makes from its key
+    (:69, :146, :216-217).  Returns (final_configuration (3N,), acceptance (N,1))."""
+    get_P = get_P_l(nelectrons, natoms, ndim, lognetwork)
+    get_v = get_non_v_l(ndim, nelectrons, natoms, Rn_non_local, Non_local_coes, Non_local_exps)
+    N = nelectrons
+
+    def calculate_ratio_weight_tmoves(data: AINetData, params, key):
+        *points, weights = get_rot(key['rot'])
+        v_l = get_v(data)                                            # (N,A,L)
+        fwd, ratios_g, coords_g = [], [], []
+        for g, pts in enumerate(points):
+            cos_theta, ratios, _, _, roted = get_P(data, params, pts, weights[g])
+            pl = torch.stack(P_l(cos_theta, list_l), dim=0)          # (L,N,A,P)
+            wts = ((torch.exp(-tstep * v_l.movedim(-1, 0)) - 1)[..., None] * pl).sum(dim=0)     # (N,A,P)
+            t_amp = ratios * wts
+            fwd.append(torch.where(_lex_gt(t_amp, torch.zeros_like(t_amp)), t_amp, torch.zeros_like(t_amp)))
+            ratios_g.append(ratios)
+            coords_g.append(roted)
+        norm = 1 + sum((weights[g] * fwd[g]).sum() for g in range(4))
+        total = torch.cat(fwd, dim=-1).reshape(N, -1)                # (N, A*50): atom-major, points OA..OD
+        total = torch.cat([torch.ones(N, 1, dtype=total.dtype), total], dim=-1)
+        cdf = torch.cumsum(total / norm, dim=-1)
+        r = complex(float(key['u']) + 1.0, 0.0)
+        nmov = total.shape[1]
+        sel = [searchsorted_scan(cdf[i], r) for i in range(N)]
+        sel = [s if s < nmov else 0 for s in sel]
+        coords = torch.cat(coords_g, dim=2).reshape(N, -1, ndim)
+        x1 = data.positions.reshape(N, ndim)
+        coords = torch.cat([x1[:, None, :], coords], dim=1)          # (N, 1+50A, 3)
+        ratio_total = torch.cat(ratios_g, dim=-1).reshape(N, -1)
+        ratio_total = torch.cat([torch.ones(N, 1, dtype=ratio_total.dtype), ratio_total], dim=1)
+        new_conf, back = [], []
+        for i in range(N):
+            mv = sel[i]
+            new_conf.append(coords[i, mv])
+            # quirk Q18: t_amp[move] indexes the ELECTRON axis with a move index (clamped read)
+            back.append(total[min(mv, N - 1)] * (1 / ratio_total[i, mv]))
+        new_conf, back = torch.stack(new_conf), torch.stack(back)    # (N,3), (N,1+50A)
+        wf = torch.cat([torch.zeros(1, 1, dtype=weights.dtype), weights])           # (5,1)
+        sl = [(1, 19), (19, 55), (55, 79), (79, 151)]                # hard-coded for A=3 (quirk Q18)
+        back_norm = 1.0 + wf[0] * back[:, 0]
+        for g, (lo, hi) in enumerate(sl):
+            back_norm = back_norm + (wf[g + 1] * back[:, lo:hi]).sum(dim=-1)
+        acceptance = (norm / back_norm).real.reshape(-1, 1)
+        cond = acceptance > key['rnd'].reshape(-1, 1)
+        final = torch.where(cond, new_conf, x1).reshape(-1)
+        aux = dict(selected=torch.tensor(sel), norm=norm, back_norm=back_norm, cdf=cdf, total=total, accept=cond)
+        return final, acceptance, aux
+    return calculate_ratio_weight_tmoves
