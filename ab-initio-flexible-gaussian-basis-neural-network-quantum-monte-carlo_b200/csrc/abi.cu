@@ -13,8 +13,9 @@
 namespace aiqmc {
 int g_last_cuda_error = 0;
 
-int64_t sweep_ws_bytes_rt(int n, int64_t B);
+int64_t sweep_ws_bytes_rt(int n, int a, int64_t B);
 int64_t energy_ws_bytes_rt(int n, int a, int64_t B, int with_ecp);
+int64_t psi_ws_bytes_rt(int n, int a, int64_t n_cfg, int with_lap);
 }  // namespace aiqmc
 
 #define X(NE, NA) extern "C" const aiqmc::OpsTable* aiqmc_ops_##NE##_##NA();
@@ -177,33 +178,37 @@ int aiqmc_param_layout(int32_t n_elec, int32_t n_atoms, AiqmcLayout* out) {
 }
 int aiqmc_supported(int32_t n_elec, int32_t n_atoms) { return find_ops(n_elec, n_atoms) != nullptr; }
 int aiqmc_last_cuda_error(void) { return g_last_cuda_error; }
-const char* aiqmc_version(void) { return "aiqmc_b200 0.1 (sm_100a, fp64, thread-per-configuration)"; }
+const char* aiqmc_version(void) { return "aiqmc_b200 0.2 (sm_100a, fp64, two-pass derivatives, cached single-electron-move quadrature)"; }
 
 static int psi_any(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_cfg, int mode,
-                   double* phase, double* logabs, double* grad, double* lap, void* stream) {
+                   double* phase, double* logabs, double* grad, double* lap, void* ws, int64_t ws_bytes, void* stream) {
   if (!sys_ok(sys) || !params || (n_cfg > 0 && (!pos || !phase || !logabs)) || n_cfg < 0) return AIQMC_E_BADARG;
   if (mode >= 1 && n_cfg > 0 && !grad) return AIQMC_E_BADARG;
   if (mode == 2 && n_cfg > 0 && !lap) return AIQMC_E_BADARG;
   const aiqmc::OpsTable* ops = find_ops(sys->n_elec, sys->n_atoms);
   if (!ops) return AIQMC_E_UNSUPPORTED;
-  return ops->psi(sys, params, pos, n_cfg, mode, phase, logabs, grad, lap, (cudaStream_t)stream);
+  return ops->psi(sys, params, pos, n_cfg, mode, phase, logabs, grad, lap, ws, ws_bytes, (cudaStream_t)stream);
 }
 int aiqmc_psi_fwd(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_cfg, double* phase,
                   double* logabs, void* stream) {
-  return psi_any(sys, params, pos, n_cfg, 0, phase, logabs, nullptr, nullptr, stream);
+  return psi_any(sys, params, pos, n_cfg, 0, phase, logabs, nullptr, nullptr, nullptr, 0, stream);
+}
+int64_t aiqmc_psi_workspace_bytes(const AiqmcSystem* sys, int64_t n_cfg, int32_t with_lap) {
+  if (!sys_ok(sys) || n_cfg < 0) return AIQMC_E_BADARG;
+  return aiqmc::psi_ws_bytes_rt(sys->n_elec, sys->n_atoms, n_cfg, with_lap);
 }
 int aiqmc_psi_grad(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_cfg, double* phase,
-                   double* logabs, double* grad, void* stream) {
-  return psi_any(sys, params, pos, n_cfg, 1, phase, logabs, grad, nullptr, stream);
+                   double* logabs, double* grad, void* workspace, int64_t workspace_bytes, void* stream) {
+  return psi_any(sys, params, pos, n_cfg, 1, phase, logabs, grad, nullptr, workspace, workspace_bytes, stream);
 }
 int aiqmc_psi_fwdlap(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_cfg, double* phase,
-                     double* logabs, double* grad, double* lap, void* stream) {
-  return psi_any(sys, params, pos, n_cfg, 2, phase, logabs, grad, lap, stream);
+                     double* logabs, double* grad, double* lap, void* workspace, int64_t workspace_bytes, void* stream) {
+  return psi_any(sys, params, pos, n_cfg, 2, phase, logabs, grad, lap, workspace, workspace_bytes, stream);
 }
 
 int64_t aiqmc_vmc_workspace_bytes(const AiqmcSystem* sys, int64_t n_walkers) {
   if (!sys_ok(sys) || n_walkers < 0) return AIQMC_E_BADARG;
-  return aiqmc::sweep_ws_bytes_rt(sys->n_elec, n_walkers);
+  return aiqmc::sweep_ws_bytes_rt(sys->n_elec, sys->n_atoms, n_walkers);
 }
 int aiqmc_vmc_sweep(const AiqmcSystem* sys, const double* params, double* pos, const double* gauss1,
                     const double* gauss2, const double* rnd, int64_t n_walkers, double tstep, double acyrus,
@@ -232,7 +237,7 @@ int aiqmc_local_energy_ae(const AiqmcSystem* sys, const double* params, const do
 int aiqmc_local_energy_ecp_stages(const AiqmcSystem* sys, const AiqmcEcp* ecp, const double* params,
                                   const double* pos, const double* rot, int64_t n_walkers, double* e_l,
                                   void* workspace, int64_t workspace_bytes, int32_t stage_mask, void* stream) {
-  if (!sys_ok(sys) || !ecp || !params || n_walkers < 0 || (stage_mask & ~15) || (stage_mask & 7) == 0) return AIQMC_E_BADARG;
+  if (!sys_ok(sys) || !ecp || !params || n_walkers < 0 || (stage_mask & ~31) || (stage_mask & 7) == 0) return AIQMC_E_BADARG;
   if (n_walkers > 0 && (!pos || !rot || !e_l || !workspace)) return AIQMC_E_BADARG;
   if (ecp->k_loc < 0 || ecp->k_loc > AIQMC_ECP_MAX_K || ecp->k_nl < 0 || ecp->k_nl > AIQMC_ECP_MAX_K ||
       ecp->n_l < 1 || ecp->n_l > AIQMC_ECP_MAX_L) return AIQMC_E_BADARG;

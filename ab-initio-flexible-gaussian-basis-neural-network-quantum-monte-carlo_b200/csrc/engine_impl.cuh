@@ -12,6 +12,7 @@
 #include "fastmath.cuh"
 #include "ops_table.h"
 #include "psi_core.cuh"
+#include "deriv_split.cuh"
 
 namespace aiqmc {
 
@@ -54,11 +55,10 @@ __device__ __forceinline__ const double* stage_params(const double* __restrict__
 // ---------------------------------------------------------------------------------------
 // signed_network forward / gradient / forward-Laplacian on arbitrary configurations
 // ---------------------------------------------------------------------------------------
-template <int NE, int NA, int MODE>
+template <int NE, int NA>
 __global__ void __launch_bounds__(kThreads) k_psi(AiqmcSystem sys, const double* __restrict__ params,
                                                   const double* __restrict__ pos, int64_t n_cfg,
-                                                  double* __restrict__ phase, double* __restrict__ logabs,
-                                                  double* __restrict__ grad, double* __restrict__ lap) {
+                                                  double* __restrict__ phase, double* __restrict__ logabs) {
   extern __shared__ double sP[];
   const double* P = stage_params<NE, NA>(params, sP);
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -66,14 +66,7 @@ __global__ void __launch_bounds__(kThreads) k_psi(AiqmcSystem sys, const double*
   double x[3 * NE];
   for (int q = 0; q < 3 * NE; ++q) x[q] = pos[t * 3 * NE + q];
   double ph, la;
-  if (MODE == 0) {
-    Psi<NE, NA>::eval_value(sys, P, x, ph, la);
-  } else {
-    double g[3 * NE], lp = 0.0;
-    Psi<NE, NA>::template eval_deriv<(MODE == 2)>(sys, P, x, ph, la, g, lp);
-    for (int q = 0; q < 3 * NE; ++q) grad[t * 3 * NE + q] = g[q];
-    if (MODE == 2) lap[t] = lp;
-  }
+  Psi<NE, NA>::eval_value(sys, P, x, ph, la);
   phase[t] = ph;
   logabs[t] = la;
 }
@@ -89,47 +82,155 @@ struct SweepWs {           // carved out of the caller's workspace
   double* xprop;           // (B,N,3)  proposed position of electron i
   double* partials;        // (nblocks_max, 4)
   double* scal;            // [0]=v2(grad x1) [1]=v2(grad x2) [2]=sum x_new [3]=sum x_prop
+  double* dcache;          // (DerivCache::SIZE_GRAD, B*N) structure-of-arrays derivative cache
 };
 
 __host__ __device__ inline int64_t align256(int64_t v) { return (v + 255) & ~int64_t(255); }
 
-inline int64_t sweep_ws_bytes(int n, int64_t B) {
-  const int64_t blocks = (B * n + kThreads - 1) / kThreads + 1;
-  return align256(B * 3 * n * 8) + align256(B * 8) + align256(B * n * 8) + 2 * align256(B * n * 3 * 8) +
-         align256(blocks * 4 * 8) + 256;
+inline int64_t deriv_cache_doubles(int n, int a, bool lap) {
+  const int qm = (3 * a + 2) > 5 ? (3 * a + 2) : 5;
+  return 3 * n + 12 * n * n + 24 * n + 4 * a * n + 8 * a + 12 * n + 16 + 3 * n * qm + 2 * n * n + 8 * n +
+         (lap ? 8 * n * n : 0);
+}
+// The derivative cache is filled and consumed in chunks of configurations so that it never exceeds
+// kDerivCacheBudget bytes, whatever the batch (C6H6: 152 kB per configuration).
+constexpr int64_t kDerivCacheBudget = int64_t(1) << 30;
+inline int64_t deriv_chunk(int n, int a, bool lap) {
+  int64_t c = kDerivCacheBudget / (deriv_cache_doubles(n, a, lap) * 8);
+  c &= ~int64_t(127);
+  return c < 128 ? 128 : c;
+}
+inline int64_t deriv_cache_bytes(int n, int a, bool lap, int64_t n_cfg) {
+  const int64_t c = deriv_chunk(n, a, lap);
+  return align256(deriv_cache_doubles(n, a, lap) * (n_cfg < c ? n_cfg : c) * 8);
+}
+// rows of block partials one tangent sweep over n_cfg configurations produces (chunked launches)
+inline int64_t tangent_rows(int n, int a, bool lap, int64_t n_cfg) {
+  const int64_t c = deriv_chunk(n, a, lap);
+  const int64_t full = n_cfg / c, rest = n_cfg - full * c;
+  return full * ((c * 3 * n + kThreads - 1) / kThreads) + (rest * 3 * n + kThreads - 1) / kThreads;
+}
+inline int64_t sweep_partial_rows(int n, int a, int64_t B) {
+  const int64_t r = tangent_rows(n, a, false, B * n), r3 = (B * n + kRedThreads - 1) / kRedThreads;
+  return (r > r3 ? r : r3) + 1;
+}
+inline int64_t psi_ws_bytes(int n, int a, int64_t n_cfg, int with_lap) {
+  return deriv_cache_bytes(n, a, with_lap != 0, n_cfg) +
+         (with_lap ? align256((n_cfg < deriv_chunk(n, a, true) ? n_cfg : deriv_chunk(n, a, true)) * 3 * n * 8) : 0);
 }
 
-inline SweepWs carve_sweep_ws(void* ws, int n, int64_t B) {
+inline int64_t sweep_ws_bytes(int n, int a, int64_t B) {
+  return align256(B * 3 * n * 8) + align256(B * 8) + align256(B * n * 8) + 2 * align256(B * n * 3 * 8) +
+         align256(sweep_partial_rows(n, a, B) * 4 * 8) + 256 + deriv_cache_bytes(n, a, false, B * n);
+}
+
+inline SweepWs carve_sweep_ws(void* ws, int n, int a, int64_t B) {
   char* p = (char*)ws;
   SweepWs w;
-  const int64_t blocks = (B * n + kThreads - 1) / kThreads + 1;
   w.grad = (double*)p; p += align256(B * 3 * n * 8);
   w.logabs1 = (double*)p; p += align256(B * 8);
   w.logabs2 = (double*)p; p += align256(B * n * 8);
   w.gnew = (double*)p; p += align256(B * n * 3 * 8);
   w.xprop = (double*)p; p += align256(B * n * 3 * 8);
-  w.partials = (double*)p; p += align256(blocks * 4 * 8);
-  w.scal = (double*)p;
+  w.partials = (double*)p; p += align256(sweep_partial_rows(n, a, B) * 4 * 8);
+  w.scal = (double*)p; p += 256;
+  w.dcache = (double*)p;
   return w;
 }
 
-template <int NE, int NA>
-__global__ void __launch_bounds__(kThreads) k_sweep_grad(AiqmcSystem sys, const double* __restrict__ params,
-                                                         const double* __restrict__ pos, int64_t B, SweepWs w) {
+__device__ __forceinline__ double taueff_of(double v2, double tau, double acyrus) {
+  return (sqrt(1.0 + 2.0 * tau * acyrus * v2) - 1.0) / (acyrus * v2);   // VMCmcstep.py:11-14
+}
+
+// ---------------------------------------------------------------------------------------
+// two-pass derivatives (deriv_split.cuh)
+// ---------------------------------------------------------------------------------------
+struct MovedSrc {          // SRC == 1: configuration (b,i) = walker b with electron i at its proposed position
+  const double* grad;      // (B,3N) grad log|psi| at x1
+  const double* gauss1;    // (B,3N)
+  const double* scal;      // [0] = v2 of grad(x1)
+  double* xprop;           // (B,N,3) out
+  double tau, acyrus;
+};
+
+// primal pass: one thread per configuration -> structure-of-arrays derivative cache dc[slot * n_cfg + cfg]
+template <int NE, int NA, bool LAP, int SRC>
+__global__ void __launch_bounds__(kThreads) k_primal(AiqmcSystem sys, const double* __restrict__ params,
+                                                     const double* __restrict__ pos, int64_t cfg0, int64_t n_cfg,
+                                                     MovedSrc ms, double* __restrict__ dc, double* __restrict__ mc,
+                                                     double* __restrict__ phase, double* __restrict__ logabs) {
+  extern __shared__ double sP[];
+  const double* P = stage_params<NE, NA>(params, sP);
+  const int64_t tl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // index inside this chunk
+  if (tl >= n_cfg) return;
+  const int64_t t = cfg0 + tl;                                           // global configuration index
+  double x[3 * NE];
+  if (SRC == 0) {
+    for (int q = 0; q < 3 * NE; ++q) x[q] = pos[t * 3 * NE + q];
+  } else {
+    const int64_t b = t / NE;
+    const int i = (int)(t - b * NE);
+    const double te = taueff_of(ms.scal[0], ms.tau, ms.acyrus);
+    double xn[3];
+    for (int c = 0; c < 3; ++c) {
+      // g = grad_eff * tstep + gauss ; x2 = x1 + g on electron i only   (VMCmcstep.py:60-78)
+      const double step = (ms.grad[b * 3 * NE + 3 * i + c] * te) * ms.tau + ms.gauss1[b * 3 * NE + 3 * i + c];
+      xn[c] = step + pos[b * 3 * NE + 3 * i + c];
+      ms.xprop[t * 3 + c] = xn[c];
+    }
+    // no dynamically indexed stores into x (nvcc 12.9 miscompiled that pattern in k_ecp_quad)
+    for (int e = 0; e < NE; ++e)
+      for (int c = 0; c < 3; ++c) x[3 * e + c] = (e == i) ? xn[c] : pos[b * 3 * NE + 3 * e + c];
+  }
+  double ph, la;
+  DerivSplit<NE, NA>::template primal<LAP>(sys, P, x, dc + tl, n_cfg, mc ? mc + t * MoveCache<NE, NA>::SIZE : nullptr, ph, la);
+  if (phase) phase[t] = ph;
+  logabs[t] = la;
+}
+
+// tangent pass: one thread per (configuration, electron, direction); a warp = 32 configurations of one
+// (electron, direction).  OUT == 0: grad (n_cfg,3N) [+ lap_parts (3N,n_cfg)];  OUT == 1: configurations are
+// (walker, moved electron i): only electron i's components are kept, gnew (n_cfg,3).
+// Always: block partial of sum g^2 -> partials[blockIdx*4 + pcol]   (limdrift's batch-global v2, quirk Q6).
+template <int NE, int NA, bool LAP, int OUT>
+__global__ void __launch_bounds__(kThreads) k_tangent(AiqmcSystem sys, const double* __restrict__ params,
+                                                      const double* __restrict__ dc, int64_t cfg0, int64_t n_cfg,
+                                                      double* __restrict__ gout, double* __restrict__ lap_parts,
+                                                      int64_t lap_stride, double* __restrict__ partials, int pcol) {
   extern __shared__ double sP[];
   __shared__ double red[kThreads / 32];
   const double* P = stage_params<NE, NA>(params, sP);
-  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  double v2 = 0.0;
-  if (b < B) {
-    double x[3 * NE], g[3 * NE], ph, la, lp;
-    for (int q = 0; q < 3 * NE; ++q) x[q] = pos[b * 3 * NE + q];
-    Psi<NE, NA>::template eval_deriv<false>(sys, P, x, ph, la, g, lp);
-    for (int q = 0; q < 3 * NE; ++q) { w.grad[b * 3 * NE + q] = g[q]; v2 += g[q] * g[q]; }
-    w.logabs1[b] = la;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double g2 = 0.0;
+  if (t < n_cfg * 3 * NE) {
+    const int ed = (int)(t / n_cfg);
+    const int64_t cfg = t - (int64_t)ed * n_cfg;
+    const int e = ed / 3, dir = ed - 3 * e;
+    double g, l2 = 0.0;
+    DerivSplit<NE, NA>::template tangent<LAP>(sys, P, dc + cfg, n_cfg, e, dir, g, l2);
+    g2 = g * g;
+    const int64_t gc = cfg0 + cfg;                                       // global configuration index
+    if (OUT == 0) {
+      gout[gc * 3 * NE + ed] = g;
+      if (LAP) lap_parts[(int64_t)ed * lap_stride + gc] = l2;
+    } else {
+      if (e == (int)(gc % NE)) gout[gc * 3 + dir] = g;
+    }
   }
-  const double s = block_sum<kThreads>(v2, red);
-  if (threadIdx.x == 0) w.partials[blockIdx.x * 4 + 0] = s;
+  if (partials) {
+    const double s = block_sum<kThreads>(g2, red);
+    if (threadIdx.x == 0) partials[blockIdx.x * 4 + pcol] = s;
+  }
+}
+
+// lap[cfg0 + c] = sum_q parts[q * stride + c]  (fixed order)
+static __global__ void k_sum_lap_parts(int nq, const double* __restrict__ parts, int64_t stride, int64_t n,
+                                       double* __restrict__ lap) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  double s = 0.0;
+  for (int q = 0; q < nq; ++q) s += parts[(int64_t)q * stride + c];
+  lap[c] = s;
 }
 
 // sums `nparts` rows of partials[:, col] in a fixed order -> out
@@ -143,45 +244,6 @@ static __global__ void __launch_bounds__(kRedThreads) k_reduce_partials(const do
     const double s = block_sum<kRedThreads>(v, red);
     if (threadIdx.x == 0) out[out0 + c] = s;
   }
-}
-
-__device__ __forceinline__ double taueff_of(double v2, double tau, double acyrus) {
-  return (sqrt(1.0 + 2.0 * tau * acyrus * v2) - 1.0) / (acyrus * v2);   // VMCmcstep.py:11-14
-}
-
-template <int NE, int NA>
-__global__ void __launch_bounds__(kThreads) k_sweep_moved(AiqmcSystem sys, const double* __restrict__ params,
-                                                          const double* __restrict__ pos,
-                                                          const double* __restrict__ gauss1, int64_t B, double tau,
-                                                          double acyrus, SweepWs w) {
-  extern __shared__ double sP[];
-  __shared__ double red[kThreads / 32];
-  const double* P = stage_params<NE, NA>(params, sP);
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  double v2 = 0.0;
-  if (t < B * NE) {
-    const int64_t b = t / NE;
-    const int i = (int)(t - b * NE);
-    const double te = taueff_of(w.scal[0], tau, acyrus);
-    double x[3 * NE], g[3 * NE], ph, la, lp, xn[3];
-    for (int c = 0; c < 3; ++c) {
-      // g = grad_eff * tstep + gauss ; x2 = x1 + g on electron i only   (VMCmcstep.py:60-78)
-      const double step = (w.grad[b * 3 * NE + 3 * i + c] * te) * tau + gauss1[b * 3 * NE + 3 * i + c];
-      xn[c] = step + pos[b * 3 * NE + 3 * i + c];
-      w.xprop[t * 3 + c] = xn[c];
-    }
-    // no dynamically indexed stores into x (nvcc 12.9 miscompiled that pattern in k_ecp_quad)
-    for (int e = 0; e < NE; ++e)
-      for (int c = 0; c < 3; ++c) x[3 * e + c] = (e == i) ? xn[c] : pos[b * 3 * NE + 3 * e + c];
-    Psi<NE, NA>::template eval_deriv<false>(sys, P, x, ph, la, g, lp);
-    for (int q = 0; q < 3 * NE; ++q) v2 += g[q] * g[q];
-    for (int e = 0; e < NE; ++e)
-      if (e == i)
-        for (int c = 0; c < 3; ++c) w.gnew[t * 3 + c] = g[3 * e + c];
-    w.logabs2[t] = la;
-  }
-  const double s = block_sum<kThreads>(v2, red);
-  if (threadIdx.x == 0) w.partials[blockIdx.x * 4 + 1] = s;
 }
 
 // accept/reject (VMCmcstep.py:80-109, walkers_accept :18-25); HBM-bound, 1 thread per (b,i)
@@ -237,28 +299,37 @@ struct EnergyWs {
   double* gnorm;     // (B,4)  Frobenius norm of each rotated point group (quirk Q14)
   double* vl;        // (B,N,A,4)  v_l(r_ia)
   double* epp;       // (B,2)  non-local energy accumulator (re, im)
-  double* cache;     // (B, MoveCache::SIZE) per-walker single-electron-move cache
+  double* cache;     // (B, MoveCache::SIZE) per-walker single-electron-move cache (quadrature kernels)
+  double* grad;      // (B,3N) grad log|psi|
+  double* lap_parts; // (3N,B) d2 log|psi| / dx_q^2
+  double* dcache;    // (DerivCache::SIZE_LAP, B) structure-of-arrays derivative cache
 };
 
-inline int64_t move_cache_doubles(int n, int a) { return 12 * n * n + 24 * n + 4 * a * n + 8 * a + 8 * n + 4; }
+inline int64_t move_cache_doubles(int n, int a) { return 12 * n * n + 24 * n + 4 * a * n + 8 * a + 9 * n + 4; }
 
 inline int64_t energy_ws_bytes(int n, int a, int64_t B, int with_ecp) {
-  int64_t s = align256(B * 8);
+  int64_t s = align256(B * 8) + 2 * align256(B * 8) + 2 * align256(B * 3 * n * 8) + deriv_cache_bytes(n, a, true, B);
   if (with_ecp) s += align256(B * move_cache_doubles(n, a) * 8);
-  if (with_ecp) s += 2 * align256(B * 8) + align256(B * 4 * 8) + align256(B * n * a * 4 * 8 + 64 * 8 * 8) + align256(B * 2 * 8);
+  if (with_ecp) s += align256(B * 4 * 8) + align256(B * n * a * 4 * 8 + 64 * 8 * 8) + align256(B * 2 * 8);
   return s;
 }
 
-inline EnergyWs carve_energy_ws(void* ws, int n, int a, int64_t B) {
+inline EnergyWs carve_energy_ws(void* ws, int n, int a, int64_t B, int with_ecp) {
   char* p = (char*)ws;
   EnergyWs w;
   w.base = (double*)p; p += align256(B * 8);
   w.logabs = (double*)p; p += align256(B * 8);
   w.phase = (double*)p; p += align256(B * 8);
-  w.gnorm = (double*)p; p += align256(B * 4 * 8);
-  w.vl = (double*)p; p += align256(B * n * a * 4 * 8 + 64 * 8 * 8);
-  w.epp = (double*)p; p += align256(B * 2 * 8);
-  w.cache = (double*)p;
+  w.grad = (double*)p; p += align256(B * 3 * n * 8);
+  w.lap_parts = (double*)p; p += align256(B * 3 * n * 8);
+  w.dcache = (double*)p; p += deriv_cache_bytes(n, a, true, B);
+  w.gnorm = w.vl = w.epp = w.cache = nullptr;
+  if (with_ecp) {
+    w.gnorm = (double*)p; p += align256(B * 4 * 8);
+    w.vl = (double*)p; p += align256(B * n * a * 4 * 8 + 64 * 8 * 8);
+    w.epp = (double*)p; p += align256(B * 2 * 8);
+    w.cache = (double*)p;
+  }
   return w;
 }
 
@@ -266,8 +337,10 @@ static __constant__ AiqmcEcp c_ecp;   // one ECP table per translation unit (per
 
 __device__ __forceinline__ int quad_group(int p) { return p < 6 ? 0 : p < 18 ? 1 : p < 26 ? 2 : 3; }
 
+// everything of E_L except the non-local quadrature, from the two derivative passes' outputs:
+// one thread per walker
 template <int NE, int NA, bool ECP>
-__global__ void __launch_bounds__(kThreads) k_energy_base(AiqmcSystem sys, const double* __restrict__ params,
+__global__ void __launch_bounds__(kThreads) k_energy_rest(AiqmcSystem sys, const double* __restrict__ params,
                                                           const double* __restrict__ pos,
                                                           const double* __restrict__ rot, int64_t B,
                                                           double* __restrict__ e_out, EnergyWs w) {
@@ -276,12 +349,14 @@ __global__ void __launch_bounds__(kThreads) k_energy_base(AiqmcSystem sys, const
   constexpr LayoutC<NE, NA> L{};
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  double x[3 * NE], g[3 * NE], ph, la, lp;
+  double x[3 * NE];
   for (int q = 0; q < 3 * NE; ++q) x[q] = pos[b * 3 * NE + q];
-  static_assert(MoveCache<NE, NA>::SIZE == 12 * NE * NE + 24 * NE + 4 * NA * NE + 8 * NA + 8 * NE + 4, "cache size");
-  Psi<NE, NA>::template eval_deriv<true>(sys, P, x, ph, la, g, lp, ECP ? w.cache + b * MoveCache<NE, NA>::SIZE : nullptr);
-  double g2 = 0.0;
-  for (int q = 0; q < 3 * NE; ++q) g2 += g[q] * g[q];
+  double g2 = 0.0, lp = 0.0;
+  for (int q = 0; q < 3 * NE; ++q) {                                // fixed order: deterministic
+    const double g = w.grad[b * 3 * NE + q];
+    g2 += g * g;
+    lp += w.lap_parts[(int64_t)q * B + b];
+  }
   double e = -0.5 * lp - 0.5 * g2;                                // pphamiltonian.py:100-102
   for (int i = 0; i < NE; ++i)                                    // potential_electron_electron
     for (int j = i + 1; j < NE; ++j) {
@@ -315,8 +390,6 @@ __global__ void __launch_bounds__(kThreads) k_energy_base(AiqmcSystem sys, const
     }
   if (ECP) {
     w.base[b] = e;
-    w.logabs[b] = la;
-    w.phase[b] = ph;
     w.epp[2 * b] = 0.0;
     w.epp[2 * b + 1] = 0.0;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
@@ -398,6 +471,7 @@ static __global__ void k_energy_final(int64_t B, double* __restrict__ e_l, Energ
 
 }  // namespace aiqmc
 #include "ecp_coop.cuh"
+#include "ecp_pt.cuh"
 namespace aiqmc {
 
 // ---------------------------------------------------------------------------------------
@@ -415,25 +489,62 @@ template <int NE, int NA>
 struct Launch {
   static constexpr int kSmem = make_layout(NE, NA).total * 8;
   static constexpr bool kCoop = (NE <= 16 && NA <= 4);   // lane-per-electron quadrature kernel available
+  static constexpr bool kPt = (NE <= 4 && make_layout(NE, NA).total <= kConstParMax);   // thread-per-point kernel
 
   template <class K>
   static cudaError_t prep(K kernel) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
   }
 
+  // One chunked sweep of the two derivative passes over n_cfg configurations (deriv_split.cuh).
+  //   SRC/OUT as in k_primal / k_tangent.  partials (may be null): block partials of sum g^2 go to rows
+  //   [*rows, ...) column pcol; *rows is advanced.
+  template <bool LAP, int SRC, int OUT>
+  static int deriv(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_cfg, MovedSrc ms,
+                   double* dcache, double* mc, double* phase, double* logabs, double* gout, double* lap_parts,
+                   int64_t lap_stride, double* partials, int pcol, int64_t* rows, cudaStream_t st) {
+    AQ_CUDA_OK(prep(k_primal<NE, NA, LAP, SRC>));
+    AQ_CUDA_OK(prep(k_tangent<NE, NA, LAP, OUT>));
+    const int64_t chunk = deriv_chunk(NE, NA, LAP);
+    for (int64_t c0 = 0; c0 < n_cfg; c0 += chunk) {
+      const int64_t nc = (n_cfg - c0 < chunk) ? n_cfg - c0 : chunk;
+      const unsigned gp = (unsigned)((nc + kThreads - 1) / kThreads);
+      const unsigned gt = (unsigned)((nc * 3 * NE + kThreads - 1) / kThreads);
+      k_primal<NE, NA, LAP, SRC><<<gp, kThreads, kSmem, st>>>(*sys, params, pos, c0, nc, ms, dcache, mc, phase, logabs);
+      k_tangent<NE, NA, LAP, OUT><<<gt, kThreads, kSmem, st>>>(*sys, params, dcache, c0, nc, gout, lap_parts, lap_stride,
+                                                              partials ? partials + *rows * 4 : nullptr, pcol);
+      if (rows) *rows += gt;
+    }
+    AQ_CUDA_OK(cudaGetLastError());
+    return AIQMC_OK;
+  }
+
   static int psi(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_cfg, int mode,
-                 double* phase, double* logabs, double* grad, double* lap, cudaStream_t st) {
+                 double* phase, double* logabs, double* grad, double* lap, void* ws, int64_t ws_bytes,
+                 cudaStream_t st) {
     if (n_cfg <= 0) return AIQMC_OK;
-    const unsigned grid = (unsigned)((n_cfg + kThreads - 1) / kThreads);
     if (mode == 0) {
-      AQ_CUDA_OK(prep(k_psi<NE, NA, 0>));
-      k_psi<NE, NA, 0><<<grid, kThreads, kSmem, st>>>(*sys, params, pos, n_cfg, phase, logabs, grad, lap);
-    } else if (mode == 1) {
-      AQ_CUDA_OK(prep(k_psi<NE, NA, 1>));
-      k_psi<NE, NA, 1><<<grid, kThreads, kSmem, st>>>(*sys, params, pos, n_cfg, phase, logabs, grad, lap);
-    } else {
-      AQ_CUDA_OK(prep(k_psi<NE, NA, 2>));
-      k_psi<NE, NA, 2><<<grid, kThreads, kSmem, st>>>(*sys, params, pos, n_cfg, phase, logabs, grad, lap);
+      const unsigned grid = (unsigned)((n_cfg + kThreads - 1) / kThreads);
+      AQ_CUDA_OK(prep(k_psi<NE, NA>));
+      k_psi<NE, NA><<<grid, kThreads, kSmem, st>>>(*sys, params, pos, n_cfg, phase, logabs);
+      AQ_CUDA_OK(cudaGetLastError());
+      return AIQMC_OK;
+    }
+    if (!ws || ws_bytes < psi_ws_bytes(NE, NA, n_cfg, mode == 2)) return AIQMC_E_WORKSPACE;
+    MovedSrc ms{};
+    double* dcache = (double*)ws;
+    if (mode == 1)
+      return deriv<false, 0, 0>(sys, params, pos, n_cfg, ms, dcache, nullptr, phase, logabs, grad, nullptr, 0, nullptr, 0,
+                                nullptr, st);
+    // Laplacian: the per-coordinate second derivatives of one chunk are summed right after its tangent pass
+    double* parts = (double*)((char*)ws + deriv_cache_bytes(NE, NA, true, n_cfg));
+    const int64_t chunk = deriv_chunk(NE, NA, true);
+    for (int64_t c0 = 0; c0 < n_cfg; c0 += chunk) {
+      const int64_t nc = (n_cfg - c0 < chunk) ? n_cfg - c0 : chunk;
+      const int rc = deriv<true, 0, 0>(sys, params, pos + c0 * 3 * NE, nc, ms, dcache, nullptr, phase + c0, logabs + c0,
+                                       grad + c0 * 3 * NE, parts, nc, nullptr, 0, nullptr, st);
+      if (rc != AIQMC_OK) return rc;
+      k_sum_lap_parts<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(3 * NE, parts, nc, nc, lap + c0);
     }
     AQ_CUDA_OK(cudaGetLastError());
     return AIQMC_OK;
@@ -444,17 +555,23 @@ struct Launch {
                    uint8_t* accept, double* grad_eff_old, double* aux_out, void* ws, int64_t ws_bytes,
                    cudaStream_t st) {
     if (B <= 0) return AIQMC_OK;
-    if (ws_bytes < sweep_ws_bytes(NE, B)) return AIQMC_E_WORKSPACE;
-    SweepWs w = carve_sweep_ws(ws, NE, B);
-    const unsigned g1 = (unsigned)((B + kThreads - 1) / kThreads);
-    const unsigned g2 = (unsigned)((B * NE + kThreads - 1) / kThreads);
+    if (ws_bytes < sweep_ws_bytes(NE, NA, B)) return AIQMC_E_WORKSPACE;
+    SweepWs w = carve_sweep_ws(ws, NE, NA, B);
+    const int64_t n2 = B * NE;                                              // single-electron-moved configurations
     const unsigned g3 = (unsigned)((B * NE + kRedThreads - 1) / kRedThreads);
-    AQ_CUDA_OK(prep(k_sweep_grad<NE, NA>));
-    AQ_CUDA_OK(prep(k_sweep_moved<NE, NA>));
-    k_sweep_grad<NE, NA><<<g1, kThreads, kSmem, st>>>(*sys, params, pos, B, w);
-    k_reduce_partials<<<1, kRedThreads, 0, st>>>(w.partials, (int)g1, 0, 1, w.scal, 0);
-    k_sweep_moved<NE, NA><<<g2, kThreads, kSmem, st>>>(*sys, params, pos, gauss1, B, tau, acyrus, w);
-    k_reduce_partials<<<1, kRedThreads, 0, st>>>(w.partials, (int)g2, 1, 1, w.scal, 1);
+    MovedSrc ms{w.grad, gauss1, w.scal, w.xprop, tau, acyrus};
+    // grad log|psi| at x1 and its batch-global square sum (limdrift, quirk Q6)
+    int64_t rows = 0;
+    int rc = deriv<false, 0, 0>(sys, params, pos, B, ms, w.dcache, nullptr, nullptr, w.logabs1, w.grad, nullptr, 0,
+                                w.partials, 0, &rows, st);
+    if (rc != AIQMC_OK) return rc;
+    k_reduce_partials<<<1, kRedThreads, 0, st>>>(w.partials, (int)rows, 0, 1, w.scal, 0);
+    // the N single-electron-moved configurations of every walker
+    rows = 0;
+    rc = deriv<false, 1, 1>(sys, params, pos, n2, ms, w.dcache, nullptr, nullptr, w.logabs2, w.gnew, nullptr, 0,
+                            w.partials, 1, &rows, st);
+    if (rc != AIQMC_OK) return rc;
+    k_reduce_partials<<<1, kRedThreads, 0, st>>>(w.partials, (int)rows, 1, 1, w.scal, 1);
     k_sweep_accept<<<g3, kRedThreads, 0, st>>>(NE, pos, gauss2, rnd, B, tau, acyrus, signed_ratio, accept,
                                                grad_eff_old, w);
     k_reduce_partials<<<1, kRedThreads, 0, st>>>(w.partials, (int)g3, 2, 2, w.scal, 2);
@@ -472,11 +589,15 @@ struct Launch {
     if (B <= 0) return AIQMC_OK;
     const int with_ecp = ecp != nullptr;
     if (ws_bytes < energy_ws_bytes(NE, NA, B, with_ecp)) return AIQMC_E_WORKSPACE;
-    EnergyWs w = carve_energy_ws(ws, NE, NA, B);
+    EnergyWs w = carve_energy_ws(ws, NE, NA, B, with_ecp);
     const unsigned g1 = (unsigned)((B + kThreads - 1) / kThreads);
+    MovedSrc ms{};
     if (!with_ecp) {
-      AQ_CUDA_OK(prep(k_energy_base<NE, NA, false>));
-      k_energy_base<NE, NA, false><<<g1, kThreads, kSmem, st>>>(*sys, params, pos, nullptr, B, e_l, w);
+      AQ_CUDA_OK(prep(k_energy_rest<NE, NA, false>));
+      const int rc = deriv<true, 0, 0>(sys, params, pos, B, ms, w.dcache, nullptr, w.phase, w.logabs, w.grad, w.lap_parts,
+                                       B, nullptr, 0, nullptr, st);
+      if (rc != AIQMC_OK) return rc;
+      k_energy_rest<NE, NA, false><<<g1, kThreads, kSmem, st>>>(*sys, params, pos, nullptr, B, e_l, w);
     } else {
       static AiqmcEcp h_ecp;                 // last table uploaded to this TU's __constant__ copy
       static bool h_valid = false;
@@ -486,21 +607,39 @@ struct Launch {
         h_valid = true;
       }
       if (stages & 1) {
-        AQ_CUDA_OK(prep(k_energy_base<NE, NA, true>));
-        k_energy_base<NE, NA, true><<<g1, kThreads, kSmem, st>>>(*sys, params, pos, rot, B, e_l, w);
+        AQ_CUDA_OK(prep(k_energy_rest<NE, NA, true>));
+        const int rc = deriv<true, 0, 0>(sys, params, pos, B, ms, w.dcache, w.cache, w.phase, w.logabs, w.grad,
+                                         w.lap_parts, B, nullptr, 0, nullptr, st);
+        if (rc != AIQMC_OK) return rc;
+        k_energy_rest<NE, NA, true><<<g1, kThreads, kSmem, st>>>(*sys, params, pos, rot, B, e_l, w);
       }
       if (stages & 2) {
+        // stage bits 8 / 16 force the thread-per-point full-evaluation kernel / the lane-per-electron
+        // kernel (cross-checks and systems the faster ones do not cover)
+        bool done = false;
+        if constexpr (kPt) {
+          if (!(stages & (8 | 16))) {
+            constexpr int WPC = AIQMC_PT_WPC;
+            AQ_CUDA_OK(cudaMemcpyToSymbolAsync(c_par, params, make_layout(NE, NA).total * sizeof(double), 0,
+                                               cudaMemcpyDeviceToDevice, st));
+            AQ_CUDA_OK(cudaFuncSetAttribute(k_ecp_pt<NE, NA, WPC>, cudaFuncAttributePreferredSharedMemoryCarveout, 25));
+            k_ecp_pt<NE, NA, WPC><<<(unsigned)((B + WPC - 1) / WPC), pt_threads<NE, NA, WPC>(), 0, st>>>(
+                *sys, pos, rot, B, w.cache, w);
+            done = true;
+          }
+        }
         if constexpr (kCoop) {
-          if (!(stages & 8)) {
+          if (!done && !(stages & 8)) {
             const int T = coop_threads<NE, NA>();
             const int smem = CoopSmem<NE, NA>::doubles(T / GroupSize<NE>::G) * 8;
             AQ_CUDA_OK(cudaFuncSetAttribute(k_ecp_coop<NE, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             AQ_CUDA_OK(cudaFuncSetAttribute(k_ecp_coop<NE, NA>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                             cudaSharedmemCarveoutMaxShared));
             k_ecp_coop<NE, NA><<<(unsigned)B, T, smem, st>>>(*sys, params, pos, rot, B, w.cache, w);
+            done = true;
           }
         }
-        if (!kCoop || (stages & 8)) {   // thread-per-point reference kernel (N > 16, or forced for cross-checks)
+        if (!done) {   // thread-per-point full evaluation (N > 16, or forced)
           AQ_CUDA_OK(prep(k_ecp_quad<NE, NA>));
           const int64_t nt = B * NE * NA * AIQMC_NQUAD;
           const unsigned g2 = (unsigned)((nt + kThreads - 1) / kThreads);

@@ -9,7 +9,7 @@ namespace aiqmc {
 struct OpsTable {
   int n_elec, n_atoms;
   int (*psi)(const AiqmcSystem*, const double*, const double*, int64_t, int, double*, double*, double*, double*,
-             cudaStream_t);
+             void*, int64_t, cudaStream_t);
   int (*sweep)(const AiqmcSystem*, const double*, double*, const double*, const double*, const double*, int64_t,
                double, double, int, uint8_t*, double*, double*, void*, int64_t, cudaStream_t);
   int (*energy)(const AiqmcSystem*, const AiqmcEcp*, const double*, const double*, const double*, int64_t, double*,

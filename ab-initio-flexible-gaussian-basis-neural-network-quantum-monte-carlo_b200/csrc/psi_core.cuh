@@ -107,11 +107,11 @@ struct LayoutC {
 // ---------------------------------------------------------------------------------------
 // scalars: double, or a jet carrying d/dx_c and d2/dx_c^2 for the 3 coordinates of ONE electron
 // ---------------------------------------------------------------------------------------
-template <bool LAP>
+template <bool LAP, int ND = 3>
 struct Jet {
   double v;
-  double d[3];
-  double s[3];
+  double d[ND];
+  double s[ND];
 };
 
 template <class S> struct ScalarOps;
@@ -120,41 +120,41 @@ template <> struct ScalarOps<double> {
   static AQ_HD double cst(double x) { return x; }
   static AQ_HD double val(double x) { return x; }
 };
-template <bool LAP> struct ScalarOps<Jet<LAP>> {
-  static AQ_HD Jet<LAP> cst(double x) { Jet<LAP> r; r.v = x; for (int c = 0; c < 3; ++c) { r.d[c] = 0; r.s[c] = 0; } return r; }
-  static AQ_HD double val(const Jet<LAP>& x) { return x.v; }
+template <bool LAP, int ND> struct ScalarOps<Jet<LAP, ND>> {
+  static AQ_HD Jet<LAP, ND> cst(double x) { Jet<LAP, ND> r; r.v = x; for (int c = 0; c < ND; ++c) { r.d[c] = 0; r.s[c] = 0; } return r; }
+  static AQ_HD double val(const Jet<LAP, ND>& x) { return x.v; }
 };
 
-template <bool L> AQ_HD Jet<L> operator+(const Jet<L>& a, const Jet<L>& b) {
-  Jet<L> r; r.v = a.v + b.v;
-  for (int c = 0; c < 3; ++c) { r.d[c] = a.d[c] + b.d[c]; if (L) r.s[c] = a.s[c] + b.s[c]; else r.s[c] = 0; }
+template <bool L, int ND> AQ_HD Jet<L, ND> operator+(const Jet<L, ND>& a, const Jet<L, ND>& b) {
+  Jet<L, ND> r; r.v = a.v + b.v;
+  for (int c = 0; c < ND; ++c) { r.d[c] = a.d[c] + b.d[c]; if (L) r.s[c] = a.s[c] + b.s[c]; else r.s[c] = 0; }
   return r;
 }
-template <bool L> AQ_HD Jet<L> operator-(const Jet<L>& a, const Jet<L>& b) {
-  Jet<L> r; r.v = a.v - b.v;
-  for (int c = 0; c < 3; ++c) { r.d[c] = a.d[c] - b.d[c]; if (L) r.s[c] = a.s[c] - b.s[c]; else r.s[c] = 0; }
+template <bool L, int ND> AQ_HD Jet<L, ND> operator-(const Jet<L, ND>& a, const Jet<L, ND>& b) {
+  Jet<L, ND> r; r.v = a.v - b.v;
+  for (int c = 0; c < ND; ++c) { r.d[c] = a.d[c] - b.d[c]; if (L) r.s[c] = a.s[c] - b.s[c]; else r.s[c] = 0; }
   return r;
 }
-template <bool L> AQ_HD Jet<L> operator+(const Jet<L>& a, double b) { Jet<L> r = a; r.v += b; return r; }
-template <bool L> AQ_HD Jet<L> operator-(const Jet<L>& a, double b) { Jet<L> r = a; r.v -= b; return r; }
-template <bool L> AQ_HD Jet<L> operator*(const Jet<L>& a, double b) {
-  Jet<L> r; r.v = a.v * b;
-  for (int c = 0; c < 3; ++c) { r.d[c] = a.d[c] * b; r.s[c] = L ? a.s[c] * b : 0.0; }
+template <bool L, int ND> AQ_HD Jet<L, ND> operator+(const Jet<L, ND>& a, double b) { Jet<L, ND> r = a; r.v += b; return r; }
+template <bool L, int ND> AQ_HD Jet<L, ND> operator-(const Jet<L, ND>& a, double b) { Jet<L, ND> r = a; r.v -= b; return r; }
+template <bool L, int ND> AQ_HD Jet<L, ND> operator*(const Jet<L, ND>& a, double b) {
+  Jet<L, ND> r; r.v = a.v * b;
+  for (int c = 0; c < ND; ++c) { r.d[c] = a.d[c] * b; r.s[c] = L ? a.s[c] * b : 0.0; }
   return r;
 }
-template <bool L> AQ_HD Jet<L> operator*(double b, const Jet<L>& a) { return a * b; }
-template <bool L> AQ_HD Jet<L> operator*(const Jet<L>& a, const Jet<L>& b) {
-  Jet<L> r; r.v = a.v * b.v;
-  for (int c = 0; c < 3; ++c) {
+template <bool L, int ND> AQ_HD Jet<L, ND> operator*(double b, const Jet<L, ND>& a) { return a * b; }
+template <bool L, int ND> AQ_HD Jet<L, ND> operator*(const Jet<L, ND>& a, const Jet<L, ND>& b) {
+  Jet<L, ND> r; r.v = a.v * b.v;
+  for (int c = 0; c < ND; ++c) {
     r.d[c] = a.d[c] * b.v + a.v * b.d[c];
     r.s[c] = L ? (a.s[c] * b.v + 2.0 * a.d[c] * b.d[c] + a.v * b.s[c]) : 0.0;
   }
   return r;
 }
 // r = f(u) given f, f', f'' at u.v
-template <bool L> AQ_HD Jet<L> chain(const Jet<L>& u, double f, double f1, double f2) {
-  Jet<L> r; r.v = f;
-  for (int c = 0; c < 3; ++c) { r.d[c] = f1 * u.d[c]; r.s[c] = L ? (f2 * u.d[c] * u.d[c] + f1 * u.s[c]) : 0.0; }
+template <bool L, int ND> AQ_HD Jet<L, ND> chain(const Jet<L, ND>& u, double f, double f1, double f2) {
+  Jet<L, ND> r; r.v = f;
+  for (int c = 0; c < ND; ++c) { r.d[c] = f1 * u.d[c]; r.s[c] = L ? (f2 * u.d[c] * u.d[c] + f1 * u.s[c]) : 0.0; }
   return r;
 }
 
@@ -201,12 +201,45 @@ AQ_HD double exp_dispatch(double x) {
 
 AQ_HD double s_tanh(double x) { return AQ_TANH(x); }
 AQ_HD double s_exp(double x) { return AQ_EXP(x); }
-AQ_HD double s_sqrt(double x) { return sqrt(x); }
+#ifdef AIQMC_LIBM
+AQ_HD double s_rsqrt(double x) { return 1.0 / sqrt(x); }
 AQ_HD double s_inv(double x) { return 1.0 / x; }
-template <bool L> AQ_HD Jet<L> s_tanh(const Jet<L>& u) { double t = AQ_TANH(u.v); double g = 1.0 - t * t; return chain(u, t, g, -2.0 * t * g); }
-template <bool L> AQ_HD Jet<L> s_exp(const Jet<L>& u) { double e = AQ_EXP(u.v); return chain(u, e, e, e); }
-template <bool L> AQ_HD Jet<L> s_sqrt(const Jet<L>& u) { double f = sqrt(u.v); double i = 1.0 / f; return chain(u, f, 0.5 * i, -0.25 * i / u.v); }
-template <bool L> AQ_HD Jet<L> s_inv(const Jet<L>& u) { double f = 1.0 / u.v; return chain(u, f, -f * f, 2.0 * f * f * f); }
+#else
+AQ_HD double s_rsqrt(double x) { return frsqrt(x); }
+AQ_HD double s_inv(double x) { return frcp(x); }
+#endif
+AQ_HD double s_sqrt(double x) { return x * s_rsqrt(x); }                      // x > 0
+template <bool L, int ND> AQ_HD Jet<L, ND> s_tanh(const Jet<L, ND>& u) { double t = AQ_TANH(u.v); double g = 1.0 - t * t; return chain(u, t, g, -2.0 * t * g); }
+template <bool L, int ND> AQ_HD Jet<L, ND> s_exp(const Jet<L, ND>& u) { double e = AQ_EXP(u.v); return chain(u, e, e, e); }
+template <bool L, int ND> AQ_HD Jet<L, ND> s_sqrt(const Jet<L, ND>& u) { double i = s_rsqrt(u.v); return chain(u, u.v * i, 0.5 * i, -0.25 * i * i * i); }
+template <bool L, int ND> AQ_HD Jet<L, ND> s_inv(const Jet<L, ND>& u) { double f = s_inv(u.v); return chain(u, f, -f * f, 2.0 * f * f * f); }
+// r = sqrt(r2) and 1/r from one reciprocal square root
+AQ_HD void s_sqrt_inv(double r2, double& r, double& ri) { ri = s_rsqrt(r2); r = r2 * ri; }
+template <bool L, int ND> AQ_HD void s_sqrt_inv(const Jet<L, ND>& r2, Jet<L, ND>& r, Jet<L, ND>& ri) {
+  const double i = s_rsqrt(r2.v), i2 = i * i;
+  r = chain(r2, r2.v * i, 0.5 * i, -0.25 * i * i2);
+  ri = chain(r2, i, -0.5 * i * i2, 0.75 * i * i2 * i2);
+}
+
+// NV tanh at once: doubles go through the interleaved ftanh_n (ILP), jets one by one.
+template <int NV, int ACC>
+AQ_HD void tanhv(const double* __restrict__ z, double* __restrict__ out) {
+#ifdef AIQMC_LIBM
+  for (int i = 0; i < NV; ++i) out[i] = tanh(z[i]);
+#else
+  constexpr int CH = 8;
+  if constexpr (NV <= CH) {
+    ftanh_n<NV, ACC>(z, out, exp_tab());
+  } else {
+    ftanh_n<CH, ACC>(z, out, exp_tab());
+    tanhv<NV - CH, ACC>(z + CH, out + CH);
+  }
+#endif
+}
+template <int NV, int ACC, bool L, int ND>
+AQ_HD void tanhv(const Jet<L, ND>* __restrict__ z, Jet<L, ND>* __restrict__ out) {
+  for (int i = 0; i < NV; ++i) out[i] = s_tanh(z[i]);
+}
 
 struct cplx { double re, im; };
 AQ_HD cplx cmul(cplx a, cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
@@ -228,7 +261,8 @@ struct MoveCache {
   static constexpr int Y = G0M + 2 * 4 * NA;              // [N][6]        Ynlm stream output
   static constexpr int ENV = Y + NE * 6;                  // [N]
   static constexpr int JAE = ENV + NE;                    // [N]
-  static constexpr int MISC = JAE + NE;                   // [4] total Jastrow, log|psi|, phase, 0
+  static constexpr int JEE = JAE + NE;                    // [N]           sum_{k != i} u_ee(r_ik)
+  static constexpr int MISC = JEE + NE;                   // [4] total Jastrow, log|psi|, phase, 0
   static constexpr int SIZE = MISC + 4;
 };
 
@@ -241,7 +275,7 @@ struct Psi {
 
   // ---- electron-local quantities: h0 = [r_ea, ae] (4A), Ynlm stream output y[6], envelope,
   //      electron-nucleus Jastrow term.  S = double or Jet.
-  template <class S>
+  template <class S, int ACC = 0>
   static AQ_HD void electron_local(const double* __restrict__ P, int e, const S xe[3], S* __restrict__ h0,
                                    S y[6], S& env, S& jae) {
     using Op = ScalarOps<S>;
@@ -267,8 +301,8 @@ struct Psi {
       S ae[3];
       for (int c = 0; c < 3; ++c) ae[c] = xe[c] - P[L.atoms + 3 * a + c];
       S r2 = ae[0] * ae[0] + ae[1] * ae[1] + ae[2] * ae[2];
-      S r = s_sqrt(r2);
-      S ri = s_inv(r);
+      S r, ri;
+      s_sqrt_inv(r2, r, ri);
       h0[4 * a] = r;
       for (int c = 0; c < 3; ++c) h0[4 * a + 1 + c] = ae[c];
       S t0 = ae[0] * ri, t1 = ae[1] * ri, t2 = ae[2] * ri;
@@ -298,9 +332,10 @@ struct Psi {
     S mdf = sum_df * (1.0 / (12.0 * A)), msp = sum_sp * (1.0 / (4.0 * A));
     for (int m = 0; m < 6; ++m) z[m] = z[m] + mdf * W0[(4 * A) * 6 + m] + msp * W0[(4 * A + 1) * 6 + m];
     if (A == 1) { y0keep[4] = mdf; y0keep[5] = msp; }
-    for (int m = 0; m < 6; ++m) {
-      S t = s_tanh(z[m]);
-      y[m] = (A == 1) ? (y0keep[m] + t) * kInvSqrt2 : t;   // residual only if 4A+2 == 6 (quirk Q5)
+    {
+      S t[6];
+      tanhv<6, ACC>(z, t);
+      for (int m = 0; m < 6; ++m) y[m] = (A == 1) ? (y0keep[m] + t[m]) * kInvSqrt2 : t[m];   // residual only if 4A+2 == 6 (quirk Q5)
     }
     for (int l = 1; l < 3; ++l) {
       const double* W = P + L.yn_w[l];
@@ -308,12 +343,14 @@ struct Psi {
       for (int m = 0; m < 6; ++m) zz[m] = Op::cst(P[L.yn_b[l] + m]);
       for (int q = 0; q < 6; ++q)
         for (int m = 0; m < 6; ++m) zz[m] = zz[m] + y[q] * W[q * 6 + m];
-      for (int m = 0; m < 6; ++m) y[m] = (y[m] + s_tanh(zz[m])) * kInvSqrt2;
+      S t[6];
+      tanhv<6, ACC>(zz, t);
+      for (int m = 0; m < 6; ++m) y[m] = (y[m] + t[m]) * kInvSqrt2;
     }
   }
 
   // ---- two-electron chain for one ordered pair: h0=[r,d], h1, h2 (nn.py:305-309)
-  template <class S>
+  template <class S, int ACC = 0>
   static AQ_HD void pair_chain(const double* __restrict__ P, const S d[3], bool diag, S h0[4], S h1[4], S h2[4]) {
     using Op = ScalarOps<S>;
     constexpr LayoutC<NE, NA> L{};
@@ -331,7 +368,9 @@ struct Psi {
       for (int m = 0; m < 4; ++m) z[m] = Op::cst(P[L.dbl_b[l] + m]);
       for (int q = 0; q < 4; ++q)
         for (int m = 0; m < 4; ++m) z[m] = z[m] + in[q] * W[q * 4 + m];
-      for (int m = 0; m < 4; ++m) out[m] = (in[m] + s_tanh(z[m])) * kInvSqrt2;
+      S t[4];
+      tanhv<4, ACC>(z, t);
+      for (int m = 0; m < 4; ++m) out[m] = (in[m] + t[m]) * kInvSqrt2;
       in = h1;
       out = h2;
     }
@@ -339,17 +378,17 @@ struct Psi {
 
   // ---- one-electron layer for electron k: conv (grouped mean of 4) -> tanh -> linear -> tanh
   //      xin = [h_k (DIN), g_up (DIN), g_dn (DIN), G_up[k]/n_up (4), G_dn[k]/n_dn (4)]
-  template <int DIN, class S>
+  template <int DIN, class S, int ACC = 0>
   static AQ_HD void one_layer(const double* __restrict__ P, int l, int k, const S* __restrict__ hk,
                               const S* __restrict__ gup, const S* __restrict__ gdn, const S Gu[4], const S Gd[4],
-                              S hout[4]) {
+                              S hout[4], double* __restrict__ rec = nullptr, int64_t rec_stride = 0) {
     using Op = ScalarOps<S>;
     constexpr LayoutC<NE, NA> L{};
     constexpr int DTOT = 3 * DIN + 8, Q = DTOT / 4;
     const double* cw = P + L.conv_w[l] + k * DTOT;
     const double* cb = P + L.conv_b[l] + k * Q;
     const double* sw = P + L.sing_w[l];
-    S z[4];
+    S z[4], pre[Q], t[Q];
     for (int m = 0; m < 4; ++m) z[m] = Op::cst(P[L.sing_b[l] + m]);
     for (int q = 0; q < Q; ++q) {
       S acc = Op::cst(0.0);
@@ -359,13 +398,16 @@ struct Psi {
                      : idx < 3 * DIN + 4 ? Gu[idx - 3 * DIN] : Gd[idx - 3 * DIN - 4];
         acc = acc + x * cw[idx];
       }
-      S t = s_tanh(acc * 0.25 + cb[q]);
-      for (int m = 0; m < 4; ++m) z[m] = z[m] + t * sw[q * 4 + m];
+      pre[q] = acc * 0.25 + cb[q];
     }
-    for (int m = 0; m < 4; ++m) {
-      S t = s_tanh(z[m]);
-      hout[m] = (DIN == 4) ? (hk[m] + t) * kInvSqrt2 : t;   // residual only if shapes match (Q5)
-    }
+    tanhv<Q, ACC>(pre, t);
+    if (rec)
+      for (int q = 0; q < Q; ++q) rec[q * rec_stride] = Op::val(t[q]);   // first-stage tanh outputs (deriv_split.cuh)
+    for (int q = 0; q < Q; ++q)
+      for (int m = 0; m < 4; ++m) z[m] = z[m] + t[q] * sw[q * 4 + m];
+    S tz[4];
+    tanhv<4, ACC>(z, tz);
+    for (int m = 0; m < 4; ++m) hout[m] = (DIN == 4) ? (hk[m] + tz[m]) * kInvSqrt2 : tz[m];   // residual only if shapes match (Q5)
   }
 
   // ---- complex LU (value only): log|det| and phase; destroys m
@@ -445,12 +487,17 @@ struct Psi {
     double y[N][6];
     double env[N];
     double jae[N];            // per-electron electron-nucleus Jastrow term
+    double jee[N];            // per-electron sum of the electron-electron Jastrow terms it takes part in
     double jastrow;
   };
 
   // ---- forward pass up to the orbital matrix; fills `pr`, returns M (row-major N x N)
+  static constexpr int QM = (3 * NA + 2) > 5 ? (3 * NA + 2) : 5;     // first-stage width of a one-electron layer
+  // hp: optional pair-chain cache [3][N][N][4] with element stride hp_stride;
+  // t1: optional record of the first-stage tanh outputs [3][N][QM] with element stride t1_stride.
   static AQ_HD void forward(const AiqmcSystem& sys, const double* __restrict__ P, const double* __restrict__ x,
-                            Primal& pr, cplx* __restrict__ M, double* __restrict__ hp = nullptr) {
+                            Primal& pr, cplx* __restrict__ M, double* __restrict__ hp = nullptr, int64_t hp_stride = 1,
+                            double* __restrict__ t1 = nullptr, int64_t t1_stride = 1) {
     constexpr LayoutC<NE, NA> L{};
     const double inv_nup = 1.0 / sys.n_up, inv_ndn = 1.0 / sys.n_dn;
     double jas = 0.0;
@@ -459,6 +506,7 @@ struct Psi {
       double jae;
       electron_local<double>(P, e, xe, pr.h0[e], pr.y[e], pr.env[e], jae);
       pr.jae[e] = jae;
+      pr.jee[e] = 0.0;
       jas += jae;
     }
     for (int s = 0; s < 2; ++s)
@@ -481,14 +529,17 @@ struct Psi {
         for (int c = 0; c < 4; ++c) { pr.G[0][s][j][c] += a0[c]; pr.G[1][s][j][c] += a1[c]; pr.G[2][s][j][c] += a2[c]; }
         if (hp) {   // pair-chain cache for the single-electron-move kernels: hp[l][i][j][c]
           for (int c = 0; c < 4; ++c) {
-            hp[((0 * N + i) * N + j) * 4 + c] = a0[c];
-            hp[((1 * N + i) * N + j) * 4 + c] = a1[c];
-            hp[((2 * N + i) * N + j) * 4 + c] = a2[c];
+            hp[(((0 * N + i) * N + j) * 4 + c) * hp_stride] = a0[c];
+            hp[(((1 * N + i) * N + j) * 4 + c) * hp_stride] = a1[c];
+            hp[(((2 * N + i) * N + j) * 4 + c) * hp_stride] = a2[c];
           }
         }
         if (i < j) {   // electron-electron Pade term (Jastrow.py:23-41)
-          double r = a0[0];
-          jas += P[L.jas_cusp + i * N + j] * r / (1.0 + P[L.jas_alpha + i * N + j] * r);
+          const double r = a0[0];
+          const double u = P[L.jas_cusp + i * N + j] * r * s_inv(1.0 + P[L.jas_alpha + i * N + j] * r);
+          jas += u;
+          pr.jee[i] += u;
+          pr.jee[j] += u;
         }
       }
     }
@@ -497,7 +548,8 @@ struct Psi {
     for (int k = 0; k < N; ++k) {
       double Gu[4], Gd[4];
       for (int c = 0; c < 4; ++c) { Gu[c] = pr.G[0][0][k][c] * inv_nup; Gd[c] = pr.G[0][1][k][c] * inv_ndn; }
-      one_layer<4 * A, double>(P, 0, k, pr.h0[k], pr.g0[0], pr.g0[1], Gu, Gd, pr.h[1][k]);
+      one_layer<4 * A, double>(P, 0, k, pr.h0[k], pr.g0[0], pr.g0[1], Gu, Gd, pr.h[1][k],
+                               t1 ? t1 + (int64_t)(k * QM) * t1_stride : nullptr, t1_stride);
     }
     for (int l = 1; l < 3; ++l) {
       for (int s = 0; s < 2; ++s) for (int c = 0; c < 4; ++c) pr.g[l][s][c] = 0.0;
@@ -506,7 +558,8 @@ struct Psi {
       for (int k = 0; k < N; ++k) {
         double Gu[4], Gd[4];
         for (int c = 0; c < 4; ++c) { Gu[c] = pr.G[l][0][k][c] * inv_nup; Gd[c] = pr.G[l][1][k][c] * inv_ndn; }
-        one_layer<4, double>(P, l, k, pr.h[l][k], pr.g[l][0], pr.g[l][1], Gu, Gd, pr.h[l + 1][k]);
+        one_layer<4, double>(P, l, k, pr.h[l][k], pr.g[l][0], pr.g[l][1], Gu, Gd, pr.h[l + 1][k],
+                             t1 ? t1 + (int64_t)((l * N + k) * QM) * t1_stride : nullptr, t1_stride);
       }
     }
     // orbital matrix M[k,j] = P[k,j] * env[k] * Yo[k,j]
@@ -538,6 +591,7 @@ struct Psi {
       for (int m = 0; m < 6; ++m) cache[MC::Y + e * 6 + m] = pr.y[e][m];
       cache[MC::ENV + e] = pr.env[e];
       cache[MC::JAE + e] = pr.jae[e];
+      cache[MC::JEE + e] = pr.jee[e];
     }
     cache[MC::MISC + 0] = pr.jastrow;
     cache[MC::MISC + 1] = logabs;
@@ -566,7 +620,7 @@ struct Psi {
     using Op = ScalarOps<J>;
     Primal pr;
     cplx Mi[N * N];
-    forward(sys, P, x, pr, Mi, cache ? cache + MoveCache<NE, NA>::HP : nullptr);
+    forward(sys, P, x, pr, Mi, cache ? cache + MoveCache<NE, NA>::HP : nullptr, 1);
     double ld;
     gj_inverse(Mi, ld, phase);
     logabs = ld + pr.jastrow;

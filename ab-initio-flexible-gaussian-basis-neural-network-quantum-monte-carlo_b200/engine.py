@@ -71,16 +71,19 @@ class WalkerEngine:
         logabs = torch.empty_like(phase)
         grad = torch.empty((ncfg, 3 * self.n), dtype=torch.float64, device=self.device) if mode >= 1 else None
         lap = torch.empty_like(phase) if mode == 2 else None
+        ws = None
+        if mode >= 1:
+            ws = self._workspace("psi", self.lib.aiqmc_psi_workspace_bytes(C.byref(self.sys), ncfg, 1 if mode == 2 else 0))
         with torch.cuda.device(self.device):
             if mode == 0:
                 rc = self.lib.aiqmc_psi_fwd(C.byref(self.sys), _ptr(self.params_dev), _ptr(p2), ncfg, _ptr(phase),
                                             _ptr(logabs), _stream())
             elif mode == 1:
                 rc = self.lib.aiqmc_psi_grad(C.byref(self.sys), _ptr(self.params_dev), _ptr(p2), ncfg, _ptr(phase),
-                                             _ptr(logabs), _ptr(grad), _stream())
+                                             _ptr(logabs), _ptr(grad), _ptr(ws), ws.numel(), _stream())
             else:
                 rc = self.lib.aiqmc_psi_fwdlap(C.byref(self.sys), _ptr(self.params_dev), _ptr(p2), ncfg, _ptr(phase),
-                                               _ptr(logabs), _ptr(grad), _ptr(lap), _stream())
+                                               _ptr(logabs), _ptr(grad), _ptr(lap), _ptr(ws), ws.numel(), _stream())
         _lib.check(rc, "aiqmc_psi")
         out = [phase.reshape(lead), logabs.reshape(lead)]
         if mode >= 1:

@@ -17,7 +17,7 @@ ERRORS = {-1: "AIQMC_E_UNSUPPORTED: no compiled instantiation for this (n_elec, 
           -2: "AIQMC_E_BADARG", -3: "AIQMC_E_CUDA", -4: "AIQMC_E_WORKSPACE"}
 
 EXPORTS = ["aiqmc_param_layout", "aiqmc_supported", "aiqmc_last_cuda_error", "aiqmc_version", "aiqmc_psi_fwd",
-           "aiqmc_psi_grad", "aiqmc_psi_fwdlap", "aiqmc_vmc_workspace_bytes", "aiqmc_vmc_sweep",
+           "aiqmc_psi_workspace_bytes", "aiqmc_psi_grad", "aiqmc_psi_fwdlap", "aiqmc_vmc_workspace_bytes", "aiqmc_vmc_sweep",
            "aiqmc_energy_workspace_bytes", "aiqmc_local_energy_ae", "aiqmc_local_energy_ecp", "aiqmc_local_energy_ecp_stages", "aiqmc_energy_stats",
            "aiqmc_dmc_ecut_min", "aiqmc_dmc_s", "aiqmc_dmc_weights", "aiqmc_branch_workspace_bytes",
            "aiqmc_branch_comb", "aiqmc_gather_walkers", "aiqmc_bench_dfma"]
@@ -46,8 +46,9 @@ def load() -> C.CDLL:
         "aiqmc_last_cuda_error": (C.c_int, []),
         "aiqmc_version": (C.c_char_p, []),
         "aiqmc_psi_fwd": (C.c_int, [sysp, vp, vp, i64, vp, vp, vp]),
-        "aiqmc_psi_grad": (C.c_int, [sysp, vp, vp, i64, vp, vp, vp, vp]),
-        "aiqmc_psi_fwdlap": (C.c_int, [sysp, vp, vp, i64, vp, vp, vp, vp, vp]),
+        "aiqmc_psi_workspace_bytes": (i64, [sysp, i64, i32]),
+        "aiqmc_psi_grad": (C.c_int, [sysp, vp, vp, i64, vp, vp, vp, vp, i64, vp]),
+        "aiqmc_psi_fwdlap": (C.c_int, [sysp, vp, vp, i64, vp, vp, vp, vp, vp, i64, vp]),
         "aiqmc_vmc_workspace_bytes": (i64, [sysp, i64]),
         "aiqmc_vmc_sweep": (C.c_int, [sysp, vp, vp, vp, vp, vp, i64, f64, f64, i32, vp, vp, vp, vp, i64, vp]),
         "aiqmc_energy_workspace_bytes": (i64, [sysp, i64, i32]),

@@ -92,12 +92,17 @@ int aiqmc_psi_fwd(const AiqmcSystem* sys, const double* params, const double* po
                   double* phase, double* logabs, void* stream);
 /* + grad (n_cfg,3N) = d log|psi| / d pos: replaces jax.grad(logabs_f, argnums=1)
  * (VMC/VMCmcstep.py:41, Energy/hamiltonian.py:104). */
+/* Scratch for the two derivative entry points below (structure-of-arrays derivative cache of one chunk of
+ * configurations; bounded by 1 GiB whatever n_cfg).  with_lap = 0 for aiqmc_psi_grad, 1 for aiqmc_psi_fwdlap. */
+int64_t aiqmc_psi_workspace_bytes(const AiqmcSystem* sys, int64_t n_cfg, int32_t with_lap);
 int aiqmc_psi_grad(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_cfg,
-                   double* phase, double* logabs, double* grad, void* stream);
+                   double* phase, double* logabs, double* grad, void* workspace, int64_t workspace_bytes,
+                   void* stream);
 /* + lap (n_cfg) = sum_i d^2 log|psi| / d pos_i^2 by forward Laplacian: replaces
  * jax.linearize(grad) + the fori_loop of 3N jvps (Energy/pphamiltonian.py:74-106). */
 int aiqmc_psi_fwdlap(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_cfg,
-                     double* phase, double* logabs, double* grad, double* lap, void* stream);
+                     double* phase, double* logabs, double* grad, double* lap, void* workspace,
+                     int64_t workspace_bytes, void* stream);
 
 /* ---- VMC: replaces walkers_update (VMC/VMCmcstep.py:28-111) ---------------------------- */
 int64_t aiqmc_vmc_workspace_bytes(const AiqmcSystem* sys, int64_t n_walkers);
@@ -127,8 +132,10 @@ int aiqmc_local_energy_ecp(const AiqmcSystem* sys, const AiqmcEcp* ecp, const do
                            const double* pos, const double* rot, int64_t n_walkers, double* e_l,
                            void* workspace, int64_t workspace_bytes, void* stream);
 /* Same, running only the stages in stage_mask: 1 = KE + Coulomb + local channel + v_l tables
- * (k_energy_base), 2 = non-local quadrature (k_ecp_quad), 4 = assembly, +8 = force the
- * thread-per-point reference quadrature kernel instead of the lane-per-electron one.  Stages must be issued in
+ * (k_energy_base), 2 = non-local quadrature, 4 = assembly.  The quadrature kernel is picked by system
+ * size (thread-per-point on the single-electron-move cache for N <= 4, lane-per-electron up to N = 16,
+ * full evaluation per point beyond); +8 forces the full-evaluation kernel, +16 the lane-per-electron
+ * one (cross-checks).  Stages must be issued in
  * order over the same workspace; used by bench.py to time the dominant kernel on its own stream. */
 int aiqmc_local_energy_ecp_stages(const AiqmcSystem* sys, const AiqmcEcp* ecp, const double* params,
                                   const double* pos, const double* rot, int64_t n_walkers, double* e_l,

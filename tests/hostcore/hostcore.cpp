@@ -2,7 +2,9 @@
 // arithmetic can be checked against the oracle on a CPU-only box.  Never loaded by the
 // product package; the product path is the CUDA library and fails loudly without it.
 #include "../../ab-initio-flexible-gaussian-basis-neural-network-quantum-monte-carlo_b200/csrc/psi_core.cuh"
+#include "../../ab-initio-flexible-gaussian-basis-neural-network-quantum-monte-carlo_b200/csrc/deriv_split.cuh"
 #include "../../ab-initio-flexible-gaussian-basis-neural-network-quantum-monte-carlo_b200/csrc/dispatch.h"
+#include <vector>
 
 using namespace aiqmc;
 
@@ -17,8 +19,13 @@ static void run(const AiqmcSystem* sys, const double* P, const double* pos, long
     } else if (mode == 1) {
       double dummy;
       Psi<NE, NA>::template eval_deriv<false>(*sys, P, x, phase[t], logabs[t], grad + t * 3 * NE, dummy);
-    } else {
+    } else if (mode == 2) {
       Psi<NE, NA>::template eval_deriv<true>(*sys, P, x, phase[t], logabs[t], grad + t * 3 * NE, lap[t]);
+    } else {      // 3 / 4: gradient / gradient + Laplacian through the two-pass path (deriv_split.cuh)
+      std::vector<double> scratch(DerivCache<NE, NA>::SIZE_LAP);
+      double dummy;
+      if (mode == 3) DerivSplit<NE, NA>::template eval<false>(*sys, P, x, scratch.data(), phase[t], logabs[t], grad + t * 3 * NE, dummy);
+      else DerivSplit<NE, NA>::template eval<true>(*sys, P, x, scratch.data(), phase[t], logabs[t], grad + t * 3 * NE, lap[t]);
     }
   }
 }
@@ -32,4 +39,17 @@ extern "C" int hc_psi(const AiqmcSystem* sys, const double* P, const double* pos
   AIQMC_FOR_EACH_SYSTEM(X)
 #undef X
   return -1;
+}
+
+// fastmath.cuh bodies, element-wise (host build: the MUFU seeds are replaced by float-precision ones)
+extern "C" void hc_fastmath(int which, const double* x, long n, double* out) {
+  const double* tab = host_exp_table();
+  if (which == 4 || which == 5) {           // batched variants, 4 at a time (n must be a multiple of 4)
+    for (long i = 0; i + 4 <= n; i += 4) {
+      if (which == 4) ftanh_n<4, 0>(x + i, out + i, tab); else ftanh_n<4, 1>(x + i, out + i, tab);
+    }
+    return;
+  }
+  for (long i = 0; i < n; ++i)
+    out[i] = which == 0 ? fexp(x[i], tab) : which == 1 ? ftanh(x[i], tab) : which == 2 ? frcp(x[i]) : frsqrt(x[i]);
 }

@@ -205,16 +205,20 @@ def test_unsupported_system_and_bad_args_fail_loudly():
         eng.local_energy(torch.tensor(case.pos))           # rotation missing
 
 
-@pytest.mark.parametrize("name,rich", [("C_ecp", True), ("N2_ecp", True), ("odd", True), ("h2like", False)])
-def test_coop_quadrature_matches_thread_per_point_kernel(name, rich):
-    """The lane-per-electron cached kernel (ecp_coop.cuh) against the plain one-thread-per-point kernel."""
+@pytest.mark.parametrize("name,rich", [("C_ecp", True), ("C_ecp", False), ("N2_ecp", True), ("odd", True), ("h2like", False)])
+def test_cached_quadrature_kernels_match_full_evaluation_kernel(name, rich):
+    """The three quadrature kernels against each other: default (thread-per-point on the single-electron-move
+    cache, ecp_pt.cuh, N <= 4; else lane-per-electron), forced lane-per-electron (ecp_coop.cuh, stage bit 16)
+    and the plain full-evaluation one-thread-per-point kernel (stage bit 8)."""
     case = Case(**CASES[name], nwalkers=33, width=0.8)
     tabs = ecp_tables(case.a, rich=rich)
     eng = engine(case, ecp=aiqmc_b200.make_ecp(case.a, list_l=2, **tabs))
     rot = torch.tensor(O.random_rotations(case.rng, case.B))
-    e_coop = eng.local_energy(torch.tensor(case.pos), rot, stages=7).cpu().numpy()
-    e_ref = eng.local_energy(torch.tensor(case.pos), rot, stages=15).cpu().numpy()
-    np.testing.assert_allclose(e_coop, e_ref, rtol=1e-11, atol=1e-11)
-    # run-to-run bit reproducibility of the deterministic reduction
-    e_again = eng.local_energy(torch.tensor(case.pos), rot, stages=7).cpu().numpy()
-    assert np.array_equal(e_coop, e_again)
+    e_def = eng.local_energy(torch.tensor(case.pos), rot, stages=7).cpu().numpy()
+    e_coop = eng.local_energy(torch.tensor(case.pos), rot, stages=7 | 16).cpu().numpy()
+    e_ref = eng.local_energy(torch.tensor(case.pos), rot, stages=7 | 8).cpu().numpy()
+    np.testing.assert_allclose(e_def, e_ref, rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(e_coop, e_ref, rtol=1e-10, atol=1e-10)
+    # run-to-run bit reproducibility of the deterministic reductions
+    assert np.array_equal(e_def, eng.local_energy(torch.tensor(case.pos), rot, stages=7).cpu().numpy())
+    assert np.array_equal(e_coop, eng.local_energy(torch.tensor(case.pos), rot, stages=7 | 16).cpu().numpy())

@@ -37,6 +37,13 @@ def test_value_grad_laplacian_match_oracle(hostlib, name):
     np.testing.assert_allclose(la0, la, rtol=1e-13, atol=1e-13)
     _, _, g1, _ = H.host_psi(hostlib, case.spec().c_struct(), packed, case.pos, 1)
     np.testing.assert_allclose(g1, g, rtol=1e-12, atol=1e-12)
+    # the two-pass derivative path the kernels use (deriv_split.cuh: primal cache + tangent pass)
+    ph3, la3, g3, _ = H.host_psi(hostlib, case.spec().c_struct(), packed, case.pos, 3)
+    ph4, la4, g4, lp4 = H.host_psi(hostlib, case.spec().c_struct(), packed, case.pos, 4)
+    np.testing.assert_allclose(la3, la, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(g3, gt.numpy(), rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(g4, g3, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(lp4, dt.sum(-1).numpy(), rtol=1e-9, atol=1e-9)
 
 
 def test_benzene_sized_system_value(hostlib):
