@@ -34,8 +34,16 @@ constexpr int kAcc = AIQMC_PT_ACC;
 constexpr int kConstParMax = 3072;           // doubles of packed parameters kept in constant memory (24 kB)
 static __constant__ double c_par[kConstParMax];
 
-template <int NE, int NA, int WPC>
-constexpr int pt_threads() { return ((WPC * NE * NA * AIQMC_NQUAD + 31) / 32) * 32; }
+#ifndef AIQMC_PT_WPCI
+#define AIQMC_PT_WPCI 5            // walkers per CTA of the per-electron specialisations: 5 x 50 points = 8 warps (97.6 % of lanes busy, no warp-allocation waste)
+#endif
+// IFIX >= 0: the kernel handles the points of electron IFIX only (one launch per electron): every `k == i`
+// test, cache offset and chain skip becomes a compile-time decision -- no selects, no branches.
+// IFIX < 0: one launch, i decoded per thread (kept for cross-checks).
+template <int NE, int NA, int WPC, int IFIX>
+constexpr int pt_points() { return (IFIX >= 0 ? 1 : NE) * NA * AIQMC_NQUAD; }
+template <int NE, int NA, int WPC, int IFIX>
+constexpr int pt_threads() { return ((WPC * pt_points<NE, NA, WPC, IFIX>() + 31) / 32) * 32; }
 
 AQ_HD cplx cminor(cplx a0, cplx a1, cplx b0, cplx b1) { return csub(cmul(a0, b1), cmul(a1, b0)); }
 
@@ -94,14 +102,14 @@ __device__ __forceinline__ void orbital_row(const double* __restrict__ P, const 
 #ifdef AIQMC_PT_MAXREG
 #define AIQMC_PT_BOUNDS __maxnreg__(AIQMC_PT_MAXREG)
 #else
-#define AIQMC_PT_BOUNDS __launch_bounds__((pt_threads<NE, NA, WPC>()), AIQMC_PT_MINB)
+#define AIQMC_PT_BOUNDS __launch_bounds__((pt_threads<NE, NA, WPC, IFIX>()), AIQMC_PT_MINB)
 #endif
-template <int NE, int NA, int WPC>
+template <int NE, int NA, int WPC, int IFIX>
 __global__ void AIQMC_PT_BOUNDS
 k_ecp_pt(AiqmcSystem sys, const double* __restrict__ pos, const double* __restrict__ rot, int64_t B,
          const double* __restrict__ cache_all, EnergyWs w) {
   constexpr int N = NE, A = NA;
-  constexpr int E = N * A * AIQMC_NQUAD;
+  constexpr int E = pt_points<NE, NA, WPC, IFIX>();
   using MC = MoveCache<NE, NA>;
   constexpr LayoutC<NE, NA> L{};
   constexpr int kCachePad = (MC::SIZE + 1) & ~1;
@@ -137,9 +145,9 @@ k_ecp_pt(AiqmcSystem sys, const double* __restrict__ pos, const double* __restri
   if (wl < WPC && b < B) {
     const double* C = sC[wl];
     const double* X = sX[wl];
-    const int i = ev / (A * AIQMC_NQUAD);
-    const int a = (ev - i * A * AIQMC_NQUAD) / AIQMC_NQUAD;
-    const int p = ev - (i * A + a) * AIQMC_NQUAD;
+    const int i = IFIX >= 0 ? IFIX : ev / (A * AIQMC_NQUAD);
+    const int a = (IFIX >= 0 ? ev : ev - i * A * AIQMC_NQUAD) / AIQMC_NQUAD;
+    const int p = (IFIX >= 0 ? ev : ev - i * A * AIQMC_NQUAD) - a * AIQMC_NQUAD;
     const double* vl = w.vl + ((b * N + i) * A + a) * 4;
     const double v0 = vl[0], v1 = vl[1], v2 = vl[2], v3 = vl[3];
     double out_re = 0.0, out_im = 0.0;
@@ -313,7 +321,10 @@ k_ecp_pt(AiqmcSystem sys, const double* __restrict__ pos, const double* __restri
       sr += __shfl_xor_sync(0xffffffffu, sr, o);
       si2 += __shfl_xor_sync(0xffffffffu, si2, o);
     }
-    if (lane == 0) { w.epp[2 * (b0 + wv)] = sr; w.epp[2 * (b0 + wv) + 1] = si2; }
+    if (lane == 0) {
+      if (IFIX <= 0) { w.epp[2 * (b0 + wv)] = sr; w.epp[2 * (b0 + wv) + 1] = si2; }
+      else { w.epp[2 * (b0 + wv)] += sr; w.epp[2 * (b0 + wv) + 1] += si2; }     // launches are stream-ordered: fixed order
+    }
   }
 }
 

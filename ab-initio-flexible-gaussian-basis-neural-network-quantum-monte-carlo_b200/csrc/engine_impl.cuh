@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 #include <string.h>
 
+#include <utility>
+
 #include "fastmath.cuh"
 #include "ops_table.h"
 #include "psi_core.cuh"
@@ -108,7 +110,8 @@ inline int64_t deriv_cache_bytes(int n, int a, bool lap, int64_t n_cfg) {
 inline int64_t tangent_rows(int n, int a, bool lap, int64_t n_cfg) {
   const int64_t c = deriv_chunk(n, a, lap);
   const int64_t full = n_cfg / c, rest = n_cfg - full * c;
-  return full * ((c * 3 * n + kThreads - 1) / kThreads) + (rest * 3 * n + kThreads - 1) / kThreads;
+  const int64_t groups = 3 * n <= 24 ? 1 : (3 * n + 14) / 15;          // >= tan_groups<n>()
+  return (full * ((c + 31) / 32) + (rest + 31) / 32) * groups;
 }
 inline int64_t sweep_partial_rows(int n, int a, int64_t B) {
   const int64_t r = tangent_rows(n, a, false, B * n), r3 = (B * n + kRedThreads - 1) / kRedThreads;
@@ -188,23 +191,42 @@ __global__ void __launch_bounds__(kThreads) k_primal(AiqmcSystem sys, const doub
   logabs[t] = la;
 }
 
-// tangent pass: one thread per (configuration, electron, direction); a warp = 32 configurations of one
-// (electron, direction).  OUT == 0: grad (n_cfg,3N) [+ lap_parts (3N,n_cfg)];  OUT == 1: configurations are
-// (walker, moved electron i): only electron i's components are kept, gnew (n_cfg,3).
-// Always: block partial of sum g^2 -> partials[blockIdx*4 + pcol]   (limdrift's batch-global v2, quirk Q6).
+// tangent pass: one thread per (configuration, electron, direction).  A CTA owns a tile of 32 consecutive
+// configurations and kTanWarps<N> of the 3N (electron, direction) pairs: warp = one pair, lane = one
+// configuration -> coalesced cache reads, no divergence, and the tile's cache lines are fetched from DRAM once
+// and re-used by the other warps through L1/L2 (with the pairs spread over the grid the cache was re-read
+// 3N times: 5.9 GB per sweep at N=4).
+// OUT == 0: grad (n_cfg,3N) [+ lap_parts (3N,lap_stride)];  OUT == 1: configurations are (walker, moved
+// electron i): only electron i's components are kept, gnew (n_cfg,3).
+// Always: block partial of sum g^2 -> partials[block*4 + pcol]   (limdrift's batch-global v2, quirk Q6).
+template <int NE> constexpr int tan_warps() { return 3 * NE <= 24 ? 3 * NE : (3 * NE % 15 == 0 ? 15 : 18); }
+template <int NE> constexpr int tan_groups() { return (3 * NE + tan_warps<NE>() - 1) / tan_warps<NE>(); }
+
 template <int NE, int NA, bool LAP, int OUT>
-__global__ void __launch_bounds__(kThreads) k_tangent(AiqmcSystem sys, const double* __restrict__ params,
+__global__ void __launch_bounds__(32 * tan_warps<NE>()) k_tangent(AiqmcSystem sys, const double* __restrict__ params,
                                                       const double* __restrict__ dc, int64_t cfg0, int64_t n_cfg,
                                                       double* __restrict__ gout, double* __restrict__ lap_parts,
                                                       int64_t lap_stride, double* __restrict__ partials, int pcol) {
   extern __shared__ double sP[];
-  __shared__ double red[kThreads / 32];
+  __shared__ double red[tan_warps<NE>()];
   const double* P = stage_params<NE, NA>(params, sP);
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t tile = (int64_t)blockIdx.x / tan_groups<NE>();
+  const int grp = (int)(blockIdx.x - tile * tan_groups<NE>());
+  const int64_t cfg = tile * 32 + (threadIdx.x & 31);
+  const int ed = grp * tan_warps<NE>() + (threadIdx.x >> 5);
+#ifndef AIQMC_NO_TAN_PREFETCH
+  {   // pull the tile's cache rows (32 configurations x 8 B = two 128-byte lines per slot) into L1 up front:
+      // the pass is otherwise bound by the latency of ~250 dependent-issue loads per thread
+    constexpr int kSlots = LAP ? DerivCache<NE, NA>::SIZE_LAP : DerivCache<NE, NA>::SIZE_GRAD;
+    const int64_t c0 = tile * 32;
+    for (int q = threadIdx.x; q < 2 * kSlots; q += blockDim.x) {
+      const int64_t c = c0 + 16 * (q & 1);
+      if (c < n_cfg) asm volatile("prefetch.global.L1 [%0];" ::"l"(dc + (int64_t)(q >> 1) * n_cfg + c));
+    }
+  }
+#endif
   double g2 = 0.0;
-  if (t < n_cfg * 3 * NE) {
-    const int ed = (int)(t / n_cfg);
-    const int64_t cfg = t - (int64_t)ed * n_cfg;
+  if (cfg < n_cfg && ed < 3 * NE) {
     const int e = ed / 3, dir = ed - 3 * e;
     double g, l2 = 0.0;
     DerivSplit<NE, NA>::template tangent<LAP>(sys, P, dc + cfg, n_cfg, e, dir, g, l2);
@@ -218,7 +240,7 @@ __global__ void __launch_bounds__(kThreads) k_tangent(AiqmcSystem sys, const dou
     }
   }
   if (partials) {
-    const double s = block_sum<kThreads>(g2, red);
+    const double s = block_sum<32 * tan_warps<NE>()>(g2, red);
     if (threadIdx.x == 0) partials[blockIdx.x * 4 + pcol] = s;
   }
 }
@@ -509,14 +531,22 @@ struct Launch {
     for (int64_t c0 = 0; c0 < n_cfg; c0 += chunk) {
       const int64_t nc = (n_cfg - c0 < chunk) ? n_cfg - c0 : chunk;
       const unsigned gp = (unsigned)((nc + kThreads - 1) / kThreads);
-      const unsigned gt = (unsigned)((nc * 3 * NE + kThreads - 1) / kThreads);
+      const unsigned gt = (unsigned)(((nc + 31) / 32) * tan_groups<NE>());
       k_primal<NE, NA, LAP, SRC><<<gp, kThreads, kSmem, st>>>(*sys, params, pos, c0, nc, ms, dcache, mc, phase, logabs);
-      k_tangent<NE, NA, LAP, OUT><<<gt, kThreads, kSmem, st>>>(*sys, params, dcache, c0, nc, gout, lap_parts, lap_stride,
+      k_tangent<NE, NA, LAP, OUT><<<gt, 32 * tan_warps<NE>(), kSmem, st>>>(*sys, params, dcache, c0, nc, gout, lap_parts, lap_stride,
                                                               partials ? partials + *rows * 4 : nullptr, pcol);
       if (rows) *rows += gt;
     }
     AQ_CUDA_OK(cudaGetLastError());
     return AIQMC_OK;
+  }
+
+  template <int... I>
+  static void launch_pt(const AiqmcSystem* sys, const double* pos, const double* rot, int64_t B, const EnergyWs& w,
+                        cudaStream_t st, std::integer_sequence<int, I...>) {
+    constexpr int WPC = AIQMC_PT_WPCI;
+    (k_ecp_pt<NE, NA, WPC, I><<<(unsigned)((B + WPC - 1) / WPC), pt_threads<NE, NA, WPC, I>(), 0, st>>>(
+         *sys, pos, rot, B, w.cache, w), ...);
   }
 
   static int psi(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_cfg, int mode,
@@ -619,12 +649,15 @@ struct Launch {
         bool done = false;
         if constexpr (kPt) {
           if (!(stages & (8 | 16))) {
-            constexpr int WPC = AIQMC_PT_WPC;
             AQ_CUDA_OK(cudaMemcpyToSymbolAsync(c_par, params, make_layout(NE, NA).total * sizeof(double), 0,
                                                cudaMemcpyDeviceToDevice, st));
-            AQ_CUDA_OK(cudaFuncSetAttribute(k_ecp_pt<NE, NA, WPC>, cudaFuncAttributePreferredSharedMemoryCarveout, 25));
-            k_ecp_pt<NE, NA, WPC><<<(unsigned)((B + WPC - 1) / WPC), pt_threads<NE, NA, WPC>(), 0, st>>>(
+#ifdef AIQMC_PT_SINGLE_LAUNCH
+            constexpr int WPC = AIQMC_PT_WPC;
+            k_ecp_pt<NE, NA, WPC, -1><<<(unsigned)((B + WPC - 1) / WPC), pt_threads<NE, NA, WPC, -1>(), 0, st>>>(
                 *sys, pos, rot, B, w.cache, w);
+#else
+            launch_pt(sys, pos, rot, B, w, st, std::make_integer_sequence<int, NE>{});   // one launch per moved electron
+#endif
             done = true;
           }
         }
