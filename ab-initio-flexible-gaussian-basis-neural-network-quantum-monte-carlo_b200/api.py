@@ -22,6 +22,7 @@ from typing import Any, Callable, Dict, Optional, Sequence
 import numpy as np
 import torch
 
+from . import parallel
 from .engine import WalkerEngine
 from .system import SystemSpec, make_ecp
 
@@ -213,11 +214,7 @@ def total_energy(local_energy_fn, process_group=None):
         e_l, _ = local_energy_fn(params, key, data)
         eng = local_energy_fn.engine_of(params, data)
         stats = eng.energy_stats(e_l)
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            torch.distributed.all_reduce(stats, group=process_group)
-        cnt = stats[3]
-        mean = torch.complex(stats[0], stats[1]) / cnt
-        variance = stats[2] / cnt - (mean.real ** 2 + mean.imag ** 2)
+        mean, variance, _ = parallel.allreduce_energy_stats(stats, process_group)
         return e_l, mean, variance
     return _total
 
@@ -242,12 +239,18 @@ def propose_drift_diffusion(f, tstep: float, ndim: int, nelectrons: int, batch_s
 
 def comput_S(engine: WalkerEngine, e_trial, e_est, branchcut, drift, tau, eloc, process_group=None):
     """DMC/S_matrix.py:4-25; `drift` is the limited drift whose square the reference passes as v2."""
-    m = engine.dmc_ecut_min(eloc, float(e_est), branchcut)
-    if process_group is not None:
-        torch.distributed.all_reduce(m, op=torch.distributed.ReduceOp.MIN, group=process_group)   # quirk Q20
+    m = parallel.allreduce_min(engine.dmc_ecut_min(eloc, float(e_est), branchcut), process_group)   # quirk Q20
     return engine.dmc_s(eloc, drift, float(e_trial), float(e_est), m, tau)
 
 
 def branch(engine: WalkerEngine, weights: torch.Tensor, key):
     """DMC/branch.py:10-34 -> (new weight scalar, newinds); `key` is the uniform u in [0,1)."""
     return engine.branch_comb(weights, float(key))
+
+
+def branch_global(engine: WalkerEngine, weights: torch.Tensor, positions: torch.Tensor, key, process_group=None):
+    """Population control across all GPUs of the job (the reference combs per device only): the
+    systematic comb of DMC/branch.py:10-34 over the all-gathered weights + migration of the selected walkers.
+    Returns (new weight scalar, new positions (B,3N), global source indices (B,), walkers imported)."""
+    return parallel.global_branch(lambda w, u: engine.branch_comb(w, u), engine.gather_walkers, weights, positions,
+                                  float(key), process_group)

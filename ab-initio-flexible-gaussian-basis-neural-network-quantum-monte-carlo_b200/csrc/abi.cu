@@ -12,6 +12,7 @@
 
 namespace aiqmc {
 int g_last_cuda_error = 0;
+int64_t g_launch_count = 0;
 
 int64_t sweep_ws_bytes_rt(int n, int a, int64_t B);
 int64_t energy_ws_bytes_rt(int n, int a, int64_t B, int with_ecp);
@@ -23,6 +24,7 @@ AIQMC_FOR_EACH_SYSTEM(X)
 #undef X
 
 using aiqmc::g_last_cuda_error;
+using aiqmc::g_launch_count;
 
 static const aiqmc::OpsTable* find_ops(int n, int a) {
 #define X(NE, NA) if (n == NE && a == NA) return aiqmc_ops_##NE##_##NA();
@@ -178,6 +180,7 @@ int aiqmc_param_layout(int32_t n_elec, int32_t n_atoms, AiqmcLayout* out) {
 }
 int aiqmc_supported(int32_t n_elec, int32_t n_atoms) { return find_ops(n_elec, n_atoms) != nullptr; }
 int aiqmc_last_cuda_error(void) { return g_last_cuda_error; }
+int64_t aiqmc_launch_count(void) { return g_launch_count; }
 const char* aiqmc_version(void) { return "aiqmc_b200 0.2 (sm_100a, fp64, two-pass derivatives, cached single-electron-move quadrature)"; }
 
 static int psi_any(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_cfg, int mode,
@@ -255,6 +258,7 @@ int aiqmc_local_energy_ecp(const AiqmcSystem* sys, const AiqmcEcp* ecp, const do
 
 int aiqmc_energy_stats(const double* e_l, int32_t e_l_stride, int64_t n_walkers, double* stats, void* stream) {
   if (!e_l || !stats || n_walkers < 0 || (e_l_stride != 1 && e_l_stride != 2)) return AIQMC_E_BADARG;
+  ++g_launch_count;
   k_energy_stats<<<1, kBig, 0, (cudaStream_t)stream>>>(e_l, e_l_stride, n_walkers, stats);
   AQ_CUDA_OK(cudaGetLastError());
   return AIQMC_OK;
@@ -263,6 +267,7 @@ int aiqmc_energy_stats(const double* e_l, int32_t e_l_stride, int64_t n_walkers,
 int aiqmc_dmc_ecut_min(const double* e_l, int32_t e_l_stride, int64_t n_walkers, double e_est, const double* branchcut,
                        double* ecut_min, void* stream) {
   if (!e_l || !branchcut || !ecut_min || n_walkers < 0 || (e_l_stride != 1 && e_l_stride != 2)) return AIQMC_E_BADARG;
+  ++g_launch_count;
   k_ecut_min<<<1, kBig, 0, (cudaStream_t)stream>>>(e_l, e_l_stride, n_walkers, e_est, branchcut, ecut_min);
   AQ_CUDA_OK(cudaGetLastError());
   return AIQMC_OK;
@@ -272,6 +277,7 @@ int aiqmc_dmc_s(const double* e_l, int32_t e_l_stride, const double* drift, int6
   if (!e_l || !drift || !ecut_min || !s_out || n_walkers < 0 || n_elec < 1 || (e_l_stride != 1 && e_l_stride != 2))
     return AIQMC_E_BADARG;
   if (n_walkers == 0) return AIQMC_OK;
+  ++g_launch_count;
   k_dmc_s<<<(unsigned)((n_walkers + 255) / 256), 256, 0, (cudaStream_t)stream>>>(e_l, e_l_stride, drift, n_walkers,
                                                                                  n_elec, e_trial, e_est, ecut_min, tau,
                                                                                  s_out);
@@ -282,6 +288,7 @@ int aiqmc_dmc_weights(double* weights, const double* s_old, const double* s_new,
                       double tdamp, void* stream) {
   if (!weights || !s_old || !s_new || n_walkers < 0) return AIQMC_E_BADARG;
   if (n_walkers == 0) return AIQMC_OK;
+  ++g_launch_count;
   k_dmc_weights<<<(unsigned)((n_walkers + 255) / 256), 256, 0, (cudaStream_t)stream>>>(weights, s_old, s_new,
                                                                                        n_walkers, tau, tdamp);
   AQ_CUDA_OK(cudaGetLastError());
@@ -294,7 +301,9 @@ int aiqmc_branch_comb(const double* weights, int64_t n_walkers, double u, int32_
   if (!weights || !newinds || !new_weight || !workspace || n_walkers <= 0) return AIQMC_E_BADARG;
   if (workspace_bytes < aiqmc_branch_workspace_bytes(n_walkers)) return AIQMC_E_WORKSPACE;
   double* cum = (double*)workspace;
+  ++g_launch_count;
   k_cumsum<<<1, kBig, 0, (cudaStream_t)stream>>>(weights, n_walkers, cum);
+  ++g_launch_count;
   k_comb<<<(unsigned)((n_walkers + 255) / 256), 256, 0, (cudaStream_t)stream>>>(cum, n_walkers, u, newinds, new_weight);
   AQ_CUDA_OK(cudaGetLastError());
   return AIQMC_OK;
@@ -302,6 +311,7 @@ int aiqmc_branch_comb(const double* weights, int64_t n_walkers, double u, int32_
 int aiqmc_bench_dfma(int64_t iters, double* sink, double* flops_out, void* stream) {
   if (iters <= 0 || !sink || !flops_out) return AIQMC_E_BADARG;
   const int grid = 148 * 8;
+  ++g_launch_count;
   k_bench_dfma<<<grid, 256, 0, (cudaStream_t)stream>>>(iters, sink);
   AQ_CUDA_OK(cudaGetLastError());
   *flops_out = (double)grid * 256.0 * 8.0 * 2.0 * (double)iters;
@@ -312,6 +322,7 @@ int aiqmc_gather_walkers(const double* pos_in, const int32_t* newinds, int64_t n
   if (!pos_in || !newinds || !pos_out || n_walkers < 0 || row_doubles < 1) return AIQMC_E_BADARG;
   if (n_walkers == 0) return AIQMC_OK;
   const int64_t nt = n_walkers * row_doubles;
+  ++g_launch_count;
   k_gather<<<(unsigned)((nt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pos_in, newinds, n_walkers, row_doubles,
                                                                            pos_out);
   AQ_CUDA_OK(cudaGetLastError());

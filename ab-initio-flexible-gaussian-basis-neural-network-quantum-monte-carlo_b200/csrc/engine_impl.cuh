@@ -506,6 +506,7 @@ namespace aiqmc {
   } while (0)
 
 extern int g_last_cuda_error;
+extern int64_t g_launch_count;      // kernels launched by this library (aiqmc_launch_count)
 
 template <int NE, int NA>
 struct Launch {
@@ -532,7 +533,9 @@ struct Launch {
       const int64_t nc = (n_cfg - c0 < chunk) ? n_cfg - c0 : chunk;
       const unsigned gp = (unsigned)((nc + kThreads - 1) / kThreads);
       const unsigned gt = (unsigned)(((nc + 31) / 32) * tan_groups<NE>());
+      ++g_launch_count;
       k_primal<NE, NA, LAP, SRC><<<gp, kThreads, kSmem, st>>>(*sys, params, pos, c0, nc, ms, dcache, mc, phase, logabs);
+      ++g_launch_count;
       k_tangent<NE, NA, LAP, OUT><<<gt, 32 * tan_warps<NE>(), kSmem, st>>>(*sys, params, dcache, c0, nc, gout, lap_parts, lap_stride,
                                                               partials ? partials + *rows * 4 : nullptr, pcol);
       if (rows) *rows += gt;
@@ -545,6 +548,7 @@ struct Launch {
   static void launch_pt(const AiqmcSystem* sys, const double* pos, const double* rot, int64_t B, const EnergyWs& w,
                         cudaStream_t st, std::integer_sequence<int, I...>) {
     constexpr int WPC = AIQMC_PT_WPCI;
+    g_launch_count += sizeof...(I);
     (k_ecp_pt<NE, NA, WPC, I><<<(unsigned)((B + WPC - 1) / WPC), pt_threads<NE, NA, WPC, I>(), 0, st>>>(
          *sys, pos, rot, B, w.cache, w), ...);
   }
@@ -556,6 +560,7 @@ struct Launch {
     if (mode == 0) {
       const unsigned grid = (unsigned)((n_cfg + kThreads - 1) / kThreads);
       AQ_CUDA_OK(prep(k_psi<NE, NA>));
+      ++g_launch_count;
       k_psi<NE, NA><<<grid, kThreads, kSmem, st>>>(*sys, params, pos, n_cfg, phase, logabs);
       AQ_CUDA_OK(cudaGetLastError());
       return AIQMC_OK;
@@ -574,6 +579,7 @@ struct Launch {
       const int rc = deriv<true, 0, 0>(sys, params, pos + c0 * 3 * NE, nc, ms, dcache, nullptr, phase + c0, logabs + c0,
                                        grad + c0 * 3 * NE, parts, nc, nullptr, 0, nullptr, st);
       if (rc != AIQMC_OK) return rc;
+      ++g_launch_count;
       k_sum_lap_parts<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(3 * NE, parts, nc, nc, lap + c0);
     }
     AQ_CUDA_OK(cudaGetLastError());
@@ -595,15 +601,19 @@ struct Launch {
     int rc = deriv<false, 0, 0>(sys, params, pos, B, ms, w.dcache, nullptr, nullptr, w.logabs1, w.grad, nullptr, 0,
                                 w.partials, 0, &rows, st);
     if (rc != AIQMC_OK) return rc;
+    ++g_launch_count;
     k_reduce_partials<<<1, kRedThreads, 0, st>>>(w.partials, (int)rows, 0, 1, w.scal, 0);
     // the N single-electron-moved configurations of every walker
     rows = 0;
     rc = deriv<false, 1, 1>(sys, params, pos, n2, ms, w.dcache, nullptr, nullptr, w.logabs2, w.gnew, nullptr, 0,
                             w.partials, 1, &rows, st);
     if (rc != AIQMC_OK) return rc;
+    ++g_launch_count;
     k_reduce_partials<<<1, kRedThreads, 0, st>>>(w.partials, (int)rows, 1, 1, w.scal, 1);
+    ++g_launch_count;
     k_sweep_accept<<<g3, kRedThreads, 0, st>>>(NE, pos, gauss2, rnd, B, tau, acyrus, signed_ratio, accept,
                                                grad_eff_old, w);
+    ++g_launch_count;
     k_reduce_partials<<<1, kRedThreads, 0, st>>>(w.partials, (int)g3, 2, 2, w.scal, 2);
     if (aux_out) {
       // aux_out = [sum x_new, sum x_prop, v2_old, v2_new]
@@ -627,6 +637,7 @@ struct Launch {
       const int rc = deriv<true, 0, 0>(sys, params, pos, B, ms, w.dcache, nullptr, w.phase, w.logabs, w.grad, w.lap_parts,
                                        B, nullptr, 0, nullptr, st);
       if (rc != AIQMC_OK) return rc;
+      ++g_launch_count;
       k_energy_rest<NE, NA, false><<<g1, kThreads, kSmem, st>>>(*sys, params, pos, nullptr, B, e_l, w);
     } else {
       static AiqmcEcp h_ecp;                 // last table uploaded to this TU's __constant__ copy
@@ -641,6 +652,7 @@ struct Launch {
         const int rc = deriv<true, 0, 0>(sys, params, pos, B, ms, w.dcache, w.cache, w.phase, w.logabs, w.grad,
                                          w.lap_parts, B, nullptr, 0, nullptr, st);
         if (rc != AIQMC_OK) return rc;
+        ++g_launch_count;
         k_energy_rest<NE, NA, true><<<g1, kThreads, kSmem, st>>>(*sys, params, pos, rot, B, e_l, w);
       }
       if (stages & 2) {
@@ -653,6 +665,7 @@ struct Launch {
                                                cudaMemcpyDeviceToDevice, st));
 #ifdef AIQMC_PT_SINGLE_LAUNCH
             constexpr int WPC = AIQMC_PT_WPC;
+            ++g_launch_count;
             k_ecp_pt<NE, NA, WPC, -1><<<(unsigned)((B + WPC - 1) / WPC), pt_threads<NE, NA, WPC, -1>(), 0, st>>>(
                 *sys, pos, rot, B, w.cache, w);
 #else
@@ -668,6 +681,7 @@ struct Launch {
             AQ_CUDA_OK(cudaFuncSetAttribute(k_ecp_coop<NE, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             AQ_CUDA_OK(cudaFuncSetAttribute(k_ecp_coop<NE, NA>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                             cudaSharedmemCarveoutMaxShared));
+            ++g_launch_count;
             k_ecp_coop<NE, NA><<<(unsigned)B, T, smem, st>>>(*sys, params, pos, rot, B, w.cache, w);
             done = true;
           }
@@ -676,9 +690,11 @@ struct Launch {
           AQ_CUDA_OK(prep(k_ecp_quad<NE, NA>));
           const int64_t nt = B * NE * NA * AIQMC_NQUAD;
           const unsigned g2 = (unsigned)((nt + kThreads - 1) / kThreads);
+          ++g_launch_count;
           k_ecp_quad<NE, NA><<<g2, kThreads, kSmem, st>>>(*sys, params, pos, rot, B, w);
         }
       }
+      if (stages & 4) ++g_launch_count;
       if (stages & 4) k_energy_final<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(B, e_l, w);
     }
     AQ_CUDA_OK(cudaGetLastError());

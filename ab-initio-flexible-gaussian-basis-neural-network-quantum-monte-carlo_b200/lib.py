@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("AIQMC_LIB", os.path.join(HERE, "libaiqmc_b200.so"))
 ERRORS = {-1: "AIQMC_E_UNSUPPORTED: no compiled instantiation for this (n_elec, n_atoms); add it to csrc/dispatch.h",
           -2: "AIQMC_E_BADARG", -3: "AIQMC_E_CUDA", -4: "AIQMC_E_WORKSPACE"}
 
-EXPORTS = ["aiqmc_param_layout", "aiqmc_supported", "aiqmc_last_cuda_error", "aiqmc_version", "aiqmc_psi_fwd",
+EXPORTS = ["aiqmc_param_layout", "aiqmc_supported", "aiqmc_last_cuda_error", "aiqmc_launch_count", "aiqmc_version", "aiqmc_psi_fwd",
            "aiqmc_psi_workspace_bytes", "aiqmc_psi_grad", "aiqmc_psi_fwdlap", "aiqmc_vmc_workspace_bytes", "aiqmc_vmc_sweep",
            "aiqmc_energy_workspace_bytes", "aiqmc_local_energy_ae", "aiqmc_local_energy_ecp", "aiqmc_local_energy_ecp_stages", "aiqmc_energy_stats",
            "aiqmc_dmc_ecut_min", "aiqmc_dmc_s", "aiqmc_dmc_weights", "aiqmc_branch_workspace_bytes",
@@ -44,6 +44,7 @@ def load() -> C.CDLL:
         "aiqmc_param_layout": (C.c_int, [i32, i32, C.POINTER(AiqmcLayout)]),
         "aiqmc_supported": (C.c_int, [i32, i32]),
         "aiqmc_last_cuda_error": (C.c_int, []),
+        "aiqmc_launch_count": (i64, []),
         "aiqmc_version": (C.c_char_p, []),
         "aiqmc_psi_fwd": (C.c_int, [sysp, vp, vp, i64, vp, vp, vp]),
         "aiqmc_psi_workspace_bytes": (i64, [sysp, i64, i32]),

@@ -231,7 +231,6 @@ def run_gpu(args):
             dist.all_reduce(stats)                          # the path's only collective (pploss.py:165-167)
         return stats
 
-    launches_per_step = 6 + 3 + 1
 
     def barrier():
         if world > 1:
@@ -249,11 +248,13 @@ def run_gpu(args):
     evq = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_wall0 = time.perf_counter()
     last = None
+    launches0 = lib.aiqmc_launch_count()
     for k in range(args.steps):
         flush.zero_()                                       # L2 flush between timed iterations (untimed)
         ev[k][0].record()
         last = step(pos, dev_sets[args.warmup + k], timed_quad=evq[k])
         ev[k][1].record()
+    gpu_launches = int(lib.aiqmc_launch_count() - launches0)     # counted by the library itself, per kernel launch
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
@@ -300,7 +301,7 @@ def run_gpu(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (k_ecp_quad): FP64 FMA peak measured live --------------
+    # ---- roofline of the dominant kernel (k_ecp_pt, the ccECP quadrature): FP64 FMA peak measured live ---
     sink = torch.zeros(8, dtype=torch.float64, device=dev)
     fl = C.c_double(0.0)
     st_ptr = C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -314,21 +315,22 @@ def run_gpu(args):
         if it >= 1:
             best = max(best, fl.value / (a0.elapsed_time(a1) * 1e-3) / 1e12)
     quad_s = float(np.mean(ms_quad)) * 1e-3
-    quad_flops = 50.0 * n * a * flops_psi(n, a) * B            # algorithmic flops of one k_ecp_quad launch
+    quad_flops = 50.0 * n * a * flops_psi(n, a) * B            # algorithmic flops of the N k_ecp_pt launches of one step
     achieved = quad_flops / quad_s / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("k_ecp_quad_dram_bytes_per_launch")
+            traffic = json.load(open(tpath)).get("k_ecp_pt_dram_bytes_per_step")
         except Exception:
             traffic = None
-    roofline = {"bound": "fp64", "kernel": "k_ecp_quad<4,1>", "achieved": achieved, "peak": best, "unit": "TFLOP/s",
+    roofline = {"bound": "fp64", "kernel": "k_ecp_pt<4,1,5,i> x4 (one launch per moved electron)", "achieved": achieved, "peak": best, "unit": "TFLOP/s",
                 "frac": achieved / best if best > 0 else None, "traffic": traffic,
                 "share_of_step": float(np.mean(ms_quad) / np.mean(ms_steps)),
                 "whole_step_frac": (value / world) * flops_walker_step_ecp(n, a) / 1e12 / best if best > 0 else None,
                 "note": "compute-bound on the FP64 pipe (SURVEY 8d), not HBM/tensor; achieved = SURVEY's fixed "
-                        "algorithmic flops 50*N*A*F(N,A) per walker / CUDA-event time of the kernel; peak = DFMA "
+                        "algorithmic flops 50*N*A*F(N,A) per walker / CUDA-event time of the quadrature stage "
+                        "(its 4 launches + the 5.7 kB parameter copy to constant memory); peak = DFMA "
                         "microbenchmark measured in this run (nominal B200 FP64 ~37 TFLOP/s; MEASURED_PEAKS.json "
                         "has no FP64 entry)"}
 
@@ -349,7 +351,7 @@ def run_gpu(args):
                        "params": "random-init (reference init scales)", "parallelism": f"walker-sharded x{world}",
                        "l2": "256 MiB flush write between timed iterations (untimed)",
                        "rng": "per-step gauss/uniform/rotation arrays pre-generated (parity-mode inputs)"},
-            "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks, "gpu_launches": gpu_launches,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": t_wall, "energy_mean_last_step": e_mean}
     print(json.dumps(line), flush=True)

@@ -84,6 +84,8 @@ int aiqmc_param_layout(int32_t n_elec, int32_t n_atoms, AiqmcLayout* out);
 /* 1 if (n_elec,n_atoms) has a compiled kernel instantiation, else 0. */
 int aiqmc_supported(int32_t n_elec, int32_t n_atoms);
 int aiqmc_last_cuda_error(void);
+/* Number of CUDA kernels this library has launched so far in this process (all entry points). */
+int64_t aiqmc_launch_count(void);
 const char* aiqmc_version(void);
 
 /* ---- wavefunction: replaces Network.apply == signed_network (nn.py:545-551) ------------ */
