@@ -237,6 +237,23 @@ def propose_drift_diffusion(f, tstep: float, ndim: int, nelectrons: int, batch_s
     return drift_diffusion
 
 
+def compute_tmoves(list_l, tstep: float, nelectrons: int, natoms: int, ndim: int, lognetwork, Rn_non_local,
+                   Non_local_coes, Non_local_exps):
+    """DMC/Tmoves.py:32-225 -> calculate_ratio_weight_tmoves(data, params, key) -> (final_configuration, acceptance),
+    natively batched over walkers.  `lognetwork` is the `apply` of make_ai_net (its complex log is taken inside the
+    kernels); key = dict(rot (B,3,3), u (B,), rnd (B,N)): the three draws the reference makes from its key."""
+    zeros = np.zeros((natoms, 3))
+    ecp = make_ecp(natoms, zeros, zeros, zeros, Rn_non_local, Non_local_coes, Non_local_exps, list_l)
+
+    def calculate_ratio_weight_tmoves(data: AINetData, params, key):
+        eng = _engine_of(lognetwork, params, data)
+        eng.ecp = ecp
+        pos = _positions(eng, data)
+        new_pos, acceptance, _ = eng.dmc_tmove(pos, key['rot'], key['u'], key['rnd'], tstep)
+        return new_pos, acceptance
+    return calculate_ratio_weight_tmoves
+
+
 def comput_S(engine: WalkerEngine, e_trial, e_est, branchcut, drift, tau, eloc, process_group=None):
     """DMC/S_matrix.py:4-25; `drift` is the limited drift whose square the reference passes as v2."""
     m = parallel.allreduce_min(engine.dmc_ecut_min(eloc, float(e_est), branchcut), process_group)   # quirk Q20

@@ -17,6 +17,7 @@ int64_t g_launch_count = 0;
 int64_t sweep_ws_bytes_rt(int n, int a, int64_t B);
 int64_t energy_ws_bytes_rt(int n, int a, int64_t B, int with_ecp);
 int64_t psi_ws_bytes_rt(int n, int a, int64_t n_cfg, int with_lap);
+int64_t tmove_ws_bytes_rt(int n, int a, int64_t B);
 }  // namespace aiqmc
 
 #define X(NE, NA) extern "C" const aiqmc::OpsTable* aiqmc_ops_##NE##_##NA();
@@ -248,6 +249,22 @@ int aiqmc_local_energy_ecp_stages(const AiqmcSystem* sys, const AiqmcEcp* ecp, c
   if (!ops) return AIQMC_E_UNSUPPORTED;
   return ops->energy(sys, ecp, params, pos, rot, n_walkers, e_l, workspace, workspace_bytes, stage_mask,
                      (cudaStream_t)stream);
+}
+int64_t aiqmc_dmc_tmove_workspace_bytes(const AiqmcSystem* sys, int64_t n_walkers) {
+  if (!sys_ok(sys) || n_walkers < 0) return AIQMC_E_BADARG;
+  return aiqmc::tmove_ws_bytes_rt(sys->n_elec, sys->n_atoms, n_walkers);
+}
+int aiqmc_dmc_tmove(const AiqmcSystem* sys, const AiqmcEcp* ecp, const double* params, const double* pos,
+                    const double* rot, const double* u, const double* rnd, int64_t n_walkers, double tstep,
+                    double* pos_out, double* acceptance, int32_t* selected, void* workspace, int64_t workspace_bytes,
+                    void* stream) {
+  if (!sys_ok(sys) || !ecp || !params || n_walkers < 0 || !(tstep > 0.0)) return AIQMC_E_BADARG;
+  if (n_walkers > 0 && (!pos || !rot || !u || !rnd || !pos_out || !acceptance || !workspace)) return AIQMC_E_BADARG;
+  if (ecp->k_nl < 0 || ecp->k_nl > AIQMC_ECP_MAX_K || ecp->n_l < 1 || ecp->n_l > AIQMC_ECP_MAX_L) return AIQMC_E_BADARG;
+  const aiqmc::OpsTable* ops = find_ops(sys->n_elec, sys->n_atoms);
+  if (!ops) return AIQMC_E_UNSUPPORTED;
+  return ops->tmove(sys, ecp, params, pos, rot, u, rnd, n_walkers, tstep, pos_out, acceptance, selected, workspace,
+                    workspace_bytes, (cudaStream_t)stream);
 }
 int aiqmc_local_energy_ecp(const AiqmcSystem* sys, const AiqmcEcp* ecp, const double* params, const double* pos,
                            const double* rot, int64_t n_walkers, double* e_l, void* workspace,

@@ -77,6 +77,22 @@ AQ_HD cplx det_small(const cplx (*m)[N]) {
   }
 }
 
+// T-move record of one quadrature point (DMC/Tmoves.py:88-112): amplitude = ratio * sum_l (exp(-tau v_l) - 1) P_l(cos),
+// kept only if it is "> 0" in jnp's lexicographic complex order (quirk Q25); out = [fwd.re, fwd.im, ratio.re, ratio.im]
+__device__ __forceinline__ void tmove_point_out(double* __restrict__ out, double v0, double v1, double v2, double v3,
+                                                double cs, double rr, double ri, double tau) {
+  const double k4 = 0.07957747154594767;   // 1/(4 pi)
+  const double ws = (exp(-tau * v0) - 1.0) * k4 + (exp(-tau * v1) - 1.0) * (3.0 * k4 * cs) +
+                    (exp(-tau * v2) - 1.0) * (2.5 * k4 * (3.0 * cs * cs - 1.0)) +
+                    (exp(-tau * v3) - 1.0) * (3.5 * k4 * (5.0 * cs * cs * cs - 3.0 * cs));
+  const double tr = rr * ws, ti = ri * ws;
+  const bool keep = (tr > 0.0) || (tr == 0.0 && ti > 0.0);
+  out[0] = keep ? tr : 0.0;
+  out[1] = keep ? ti : 0.0;
+  out[2] = rr;
+  out[3] = ri;
+}
+
 // Orbital-matrix row (nn.py:432-504): out[j] = (h . W[:, j] + b[j]) * env * (y . Yw[:, j]); SROW picks the
 // spin block's weights at compile time so every weight stays an immediate constant-bank operand.
 template <int NE, int NA, int SROW>
@@ -107,7 +123,7 @@ __device__ __forceinline__ void orbital_row(const double* __restrict__ P, const 
 template <int NE, int NA, int WPC, int IFIX>
 __global__ void AIQMC_PT_BOUNDS
 k_ecp_pt(AiqmcSystem sys, const double* __restrict__ pos, const double* __restrict__ rot, int64_t B,
-         const double* __restrict__ cache_all, EnergyWs w) {
+         const double* __restrict__ cache_all, EnergyWs w, double* __restrict__ tm_out, double tm_tau) {
   constexpr int N = NE, A = NA;
   constexpr int E = pt_points<NE, NA, WPC, IFIX>();
   using MC = MoveCache<NE, NA>;
@@ -151,7 +167,7 @@ k_ecp_pt(AiqmcSystem sys, const double* __restrict__ pos, const double* __restri
     const double* vl = w.vl + ((b * N + i) * A + a) * 4;
     const double v0 = vl[0], v1 = vl[1], v2 = vl[2], v3 = vl[3];
     double out_re = 0.0, out_im = 0.0;
-    if (!(v0 == 0.0 && v1 == 0.0 && v2 == 0.0 && v3 == 0.0)) {        // exact zero channel contributes exactly 0
+    if (tm_out || !(v0 == 0.0 && v1 == 0.0 && v2 == 0.0 && v3 == 0.0)) {   // exact zero channel contributes exactly 0
       const double inv_n[2] = {1.0 / sys.n_up, 1.0 / sys.n_dn};
       const int si = i < sys.n_up ? 0 : 1;
       // ---- rotated point and cos(theta)  (quirks Q13, Q14)
@@ -306,6 +322,7 @@ k_ecp_pt(AiqmcSystem sys, const double* __restrict__ pos, const double* __restri
                        v3 * (3.5 * k4 * (5.0 * cs * cs * cs - 3.0 * cs));
       out_re = f * rr;
       out_im = f * ri;
+      if (tm_out) tmove_point_out(tm_out + (((b * N + i) * A + a) * AIQMC_NQUAD + p) * 4, v0, v1, v2, v3, cs, rr, ri, tm_tau);
     }
     sAcc[wl][ev][0] = out_re;
     sAcc[wl][ev][1] = out_im;
@@ -313,7 +330,7 @@ k_ecp_pt(AiqmcSystem sys, const double* __restrict__ pos, const double* __restri
   __syncthreads();
   // fixed-order sum of the E contributions of each walker: warp wv handles walker wv
   const int wv = tid >> 5, lane = tid & 31;
-  if (wv < WPC && b0 + wv < B) {
+  if (!tm_out && wv < WPC && b0 + wv < B) {
     double sr = 0.0, si2 = 0.0;
     for (int q = lane; q < E; q += 32) { sr += sAcc[wv][q][0]; si2 += sAcc[wv][q][1]; }
 #pragma unroll

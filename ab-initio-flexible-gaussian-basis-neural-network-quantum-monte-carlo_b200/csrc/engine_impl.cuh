@@ -336,6 +336,10 @@ inline int64_t energy_ws_bytes(int n, int a, int64_t B, int with_ecp) {
   return s;
 }
 
+inline int64_t tmove_ws_bytes(int n, int a, int64_t B) {
+  return energy_ws_bytes(n, a, B, 1) + align256(B * n * a * AIQMC_NQUAD * 4 * 8);
+}
+
 inline EnergyWs carve_energy_ws(void* ws, int n, int a, int64_t B, int with_ecp) {
   char* p = (char*)ws;
   EnergyWs w;
@@ -430,11 +434,15 @@ __global__ void __launch_bounds__(kThreads) k_energy_rest(AiqmcSystem sys, const
   }
 }
 
+__device__ __forceinline__ void tmove_point_out(double* __restrict__ out, double v0, double v1, double v2, double v3,
+                                                double cs, double rr, double ri, double tau);
+
 // one thread = one quadrature point of one (electron, atom) pair of one walker
 template <int NE, int NA>
 __global__ void __launch_bounds__(kThreads, AIQMC_QUAD_MINB) k_ecp_quad(AiqmcSystem sys, const double* __restrict__ params,
                                                        const double* __restrict__ pos,
-                                                       const double* __restrict__ rot, int64_t B, EnergyWs w) {
+                                                       const double* __restrict__ rot, int64_t B, EnergyWs w,
+                                                       double* __restrict__ tm_out, double tm_tau) {
   extern __shared__ double sP[];
   const double* P = stage_params<NE, NA>(params, sP);
   constexpr LayoutC<NE, NA> L{};
@@ -449,7 +457,7 @@ __global__ void __launch_bounds__(kThreads, AIQMC_QUAD_MINB) k_ecp_quad(AiqmcSys
   const double* vl = w.vl + ((b * NE + i) * NA + a) * 4;
   bool any = false;
   for (int l = 0; l < AIQMC_ECP_MAX_L; ++l) any = any || (vl[l] != 0.0);
-  if (!any) return;                       // exact zero coefficient: contributes exactly 0
+  if (!any && !tm_out) return;            // exact zero coefficient: contributes exactly 0
   double ae[3], nh[3];
   for (int c = 0; c < 3; ++c) ae[c] = pos[b * 3 * NE + 3 * i + c] - P[L.atoms + 3 * a + c];
   const double r = sqrt(ae[0] * ae[0] + ae[1] * ae[1] + ae[2] * ae[2]);
@@ -480,8 +488,151 @@ __global__ void __launch_bounds__(kThreads, AIQMC_QUAD_MINB) k_ecp_quad(AiqmcSys
 #ifdef AIQMC_DEBUG_QUAD
   if (t < 64) { double* d = w.vl + B * NE * NA * 4 + t * 8; d[0] = la; d[1] = ph; d[2] = cs; d[3] = f; d[4] = rr; d[5] = ri; d[6] = r; d[7] = dr; }
 #endif
+  if (tm_out) {
+    tmove_point_out(tm_out + t * 4, vl[0], vl[1], vl[2], vl[3], cs, rr, ri, tm_tau);
+    return;
+  }
   atomicAdd(&w.epp[2 * b], f * rr);
   atomicAdd(&w.epp[2 * b + 1], f * ri);
+}
+
+// T-move preparation (DMC/Tmoves.py:32-66): the single-electron-move cache, log psi of the walker, v_l tables and
+// point-group norms -- the energy stage without any derivative.  One thread per walker.
+template <int NE, int NA>
+__global__ void __launch_bounds__(kThreads) k_tmove_prep(AiqmcSystem sys, const double* __restrict__ params,
+                                                         const double* __restrict__ pos,
+                                                         const double* __restrict__ rot, int64_t B, EnergyWs w) {
+  extern __shared__ double sP[];
+  const double* P = stage_params<NE, NA>(params, sP);
+  constexpr LayoutC<NE, NA> L{};
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double x[3 * NE];
+  for (int q = 0; q < 3 * NE; ++q) x[q] = pos[b * 3 * NE + q];
+  {
+    typename Psi<NE, NA>::Primal pr;
+    cplx M[NE * NE];
+    double* mc = w.cache + b * MoveCache<NE, NA>::SIZE;
+    Psi<NE, NA>::forward(sys, P, x, pr, M, mc + MoveCache<NE, NA>::HP, 1);
+    double ld, ph;
+    Psi<NE, NA>::lu_logdet(M, ld, ph);
+    Psi<NE, NA>::write_cache(pr, ld + pr.jastrow, ph, mc);
+    w.logabs[b] = ld + pr.jastrow;
+    w.phase[b] = ph;
+  }
+  for (int i = 0; i < NE; ++i)
+    for (int a = 0; a < NA; ++a) {
+      const double dx = x[3 * i] - P[L.atoms + 3 * a], dy = x[3 * i + 1] - P[L.atoms + 3 * a + 1],
+                   dz = x[3 * i + 2] - P[L.atoms + 3 * a + 2];
+      const double r = sqrt(dx * dx + dy * dy + dz * dz);
+      for (int l = 0; l < AIQMC_ECP_MAX_L; ++l) {              // pseudopotential.py:150, r^n
+        double v = 0.0;
+        if (l < c_ecp.n_l)
+          for (int k = 0; k < c_ecp.k_nl; ++k)
+            v += c_ecp.non_local_coes[a][l][k] * pow(r, c_ecp.rn_non_local[a][l][k]) *
+                 exp(-c_ecp.non_local_exps[a][l][k] * r * r);
+        w.vl[((b * NE + i) * NA + a) * 4 + l] = v;
+      }
+    }
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int p = 0; p < AIQMC_NQUAD; ++p) {
+    double n2 = 0.0;
+    for (int l = 0; l < 3; ++l) {
+      double v = 0.0;
+      for (int k = 0; k < 3; ++k) v += c_ecp.quad_pts[p][k] * rot[b * 9 + 3 * k + l];
+      n2 += v * v;
+    }
+    acc[quad_group(p)] += n2;
+  }
+  for (int q = 0; q < 4; ++q) w.gnorm[4 * b + q] = sqrt(acc[q]);
+}
+
+// T-move selection (DMC/Tmoves.py:114-222), one thread per (walker, electron).  tm (B,N,A,50,4) holds
+// [fwd.re, fwd.im, ratio.re, ratio.im] per quadrature point.  Complex comparisons are lexicographic (quirk Q25);
+// the selection is jnp.searchsorted's fixed-trip-count bisection on the (unsorted) complex cdf; the back
+// amplitude indexes the ELECTRON axis with the move index and the slices 1:19:55:79:151 are the reference's
+// hard-coded A = 3 layout (quirk Q18) -- both replicated.
+template <int NE, int NA>
+__global__ void __launch_bounds__(kThreads) k_tmove_select(const double* __restrict__ pos, const double* __restrict__ rot,
+                                                           const double* __restrict__ params,
+                                                           const double* __restrict__ tm, const double* __restrict__ u,
+                                                           const double* __restrict__ rnd, int64_t B,
+                                                           double* __restrict__ pos_out, double* __restrict__ acceptance,
+                                                           int32_t* __restrict__ selected) {
+  constexpr int N = NE, A = NA, PW = A * AIQMC_NQUAD, NMOV = 1 + PW;
+  constexpr LayoutC<NE, NA> L{};
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * N) return;
+  const int64_t b = t / N;
+  const int i = (int)(t - b * N);
+  const double* tw = tm + b * N * PW * 4;
+  // norm = 1 + sum_g w_g sum fwd_g
+  cplx norm = {1.0, 0.0};
+  for (int e = 0; e < N; ++e)
+    for (int a = 0; a < A; ++a)
+      for (int p = 0; p < AIQMC_NQUAD; ++p) {
+        const double* q = tw + ((e * A + a) * AIQMC_NQUAD + p) * 4;
+        norm.re += c_ecp.quad_wts[p] * q[0];
+        norm.im += c_ecp.quad_wts[p] * q[1];
+      }
+  const cplx ninv = cinv(norm);
+  auto total = [&](int e, int m) -> cplx {       // forward_probability_output_total_final[e][m]
+    if (m == 0) return cplx{1.0, 0.0};
+    const double* q = tw + (e * PW + (m - 1)) * 4;
+    return cplx{q[0], q[1]};
+  };
+  auto cdf_at = [&](int m) -> cplx {             // cumsum(total[i] / norm)[m]
+    cplx s = {0.0, 0.0};
+    for (int k = 0; k <= m; ++k) s = cadd(s, cmul(total(i, k), ninv));
+    return s;
+  };
+  // cumulative sums once, in order (matches jnp.cumsum's sequential association)
+  // bisection with ceil(log2(NMOV + 1)) trips
+  const double r = u[b] + 1.0;
+  int low = 0, high = NMOV;
+  int trips = 0;
+  for (int v = NMOV; v > 0; v >>= 1) ++trips;     // bit length of NMOV == ceil(log2(NMOV + 1))
+  // running prefix for the bisection: recomputing the prefix is O(NMOV) per probe; NMOV <= 1 + 50 A
+  for (int it = 0; it < trips; ++it) {
+    const int mid = (low + high) / 2;
+    const cplx c = cdf_at(mid < NMOV ? mid : NMOV - 1);
+    const bool le = (r < c.re) || (r == c.re && 0.0 <= c.im);     // r + 0j <= cdf[mid], lexicographic
+    if (le) high = mid; else low = mid;
+  }
+  int mv = high < NMOV ? high : 0;
+  if (selected) selected[t] = mv;
+  // selected coordinates and ratio
+  double xo[3], xs[3];
+  for (int c = 0; c < 3; ++c) { xo[c] = pos[b * 3 * N + 3 * i + c]; xs[c] = xo[c]; }
+  cplx rsel = {1.0, 0.0};
+  if (mv > 0) {
+    const int a = (mv - 1) / AIQMC_NQUAD, p = (mv - 1) - a * AIQMC_NQUAD;
+    double ae[3];
+    for (int c = 0; c < 3; ++c) ae[c] = xo[c] - params[L.atoms + 3 * a + c];
+    const double rr = sqrt(ae[0] * ae[0] + ae[1] * ae[1] + ae[2] * ae[2]);
+    for (int l = 0; l < 3; ++l)          // quirk Q13: the electron is placed at r_ia * n_hat (atom position not added)
+      xs[l] = rr * (c_ecp.quad_pts[p][0] * rot[b * 9 + l] + c_ecp.quad_pts[p][1] * rot[b * 9 + 3 + l] +
+                    c_ecp.quad_pts[p][2] * rot[b * 9 + 6 + l]);
+    const double* q = tw + (i * PW + (mv - 1)) * 4;
+    rsel = cplx{q[2], q[3]};
+  }
+  const cplx rinv = cinv(rsel);
+  // back amplitudes: t_amp[move] indexes the electron axis (clamped), quirk Q18
+  const int erow = mv < N - 1 ? mv : N - 1;
+  cplx bn = {1.0, 0.0};
+  const int lo[4] = {1, 19, 55, 79}, hi[4] = {19, 55, 79, 151};
+  const int gfirst[4] = {0, 6, 18, 26};
+  for (int g = 0; g < 4; ++g) {
+    cplx sg = {0.0, 0.0};
+    for (int m = lo[g]; m < hi[g] && m < NMOV; ++m) sg = cadd(sg, cmul(total(erow, m), rinv));
+    bn.re += c_ecp.quad_wts[gfirst[g]] * sg.re;
+    bn.im += c_ecp.quad_wts[gfirst[g]] * sg.im;
+  }
+  const cplx ratio = cmul(norm, cinv(bn));
+  const double acc = ratio.re;
+  acceptance[t] = acc;
+  const bool ok = acc > rnd[t];
+  for (int c = 0; c < 3; ++c) pos_out[b * 3 * N + 3 * i + c] = ok ? xs[c] : xo[c];
 }
 
 static __global__ void k_energy_final(int64_t B, double* __restrict__ e_l, EnergyWs w) {
@@ -546,11 +697,11 @@ struct Launch {
 
   template <int... I>
   static void launch_pt(const AiqmcSystem* sys, const double* pos, const double* rot, int64_t B, const EnergyWs& w,
-                        cudaStream_t st, std::integer_sequence<int, I...>) {
+                        double* tm_out, double tm_tau, cudaStream_t st, std::integer_sequence<int, I...>) {
     constexpr int WPC = AIQMC_PT_WPCI;
     g_launch_count += sizeof...(I);
     (k_ecp_pt<NE, NA, WPC, I><<<(unsigned)((B + WPC - 1) / WPC), pt_threads<NE, NA, WPC, I>(), 0, st>>>(
-         *sys, pos, rot, B, w.cache, w), ...);
+         *sys, pos, rot, B, w.cache, w, tm_out, tm_tau), ...);
   }
 
   static int psi(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_cfg, int mode,
@@ -640,13 +791,7 @@ struct Launch {
       ++g_launch_count;
       k_energy_rest<NE, NA, false><<<g1, kThreads, kSmem, st>>>(*sys, params, pos, nullptr, B, e_l, w);
     } else {
-      static AiqmcEcp h_ecp;                 // last table uploaded to this TU's __constant__ copy
-      static bool h_valid = false;
-      if (!h_valid || memcmp(&h_ecp, ecp, sizeof(AiqmcEcp)) != 0) {
-        AQ_CUDA_OK(cudaMemcpyToSymbolAsync(c_ecp, ecp, sizeof(AiqmcEcp), 0, cudaMemcpyHostToDevice, st));
-        h_ecp = *ecp;
-        h_valid = true;
-      }
+      AQ_CUDA_OK(upload_ecp(ecp, st));
       if (stages & 1) {
         AQ_CUDA_OK(prep(k_energy_rest<NE, NA, true>));
         const int rc = deriv<true, 0, 0>(sys, params, pos, B, ms, w.dcache, w.cache, w.phase, w.logabs, w.grad,
@@ -667,9 +812,9 @@ struct Launch {
             constexpr int WPC = AIQMC_PT_WPC;
             ++g_launch_count;
             k_ecp_pt<NE, NA, WPC, -1><<<(unsigned)((B + WPC - 1) / WPC), pt_threads<NE, NA, WPC, -1>(), 0, st>>>(
-                *sys, pos, rot, B, w.cache, w);
+                *sys, pos, rot, B, w.cache, w, nullptr, 0.0);
 #else
-            launch_pt(sys, pos, rot, B, w, st, std::make_integer_sequence<int, NE>{});   // one launch per moved electron
+            launch_pt(sys, pos, rot, B, w, nullptr, 0.0, st, std::make_integer_sequence<int, NE>{});   // one launch per moved electron
 #endif
             done = true;
           }
@@ -691,7 +836,7 @@ struct Launch {
           const int64_t nt = B * NE * NA * AIQMC_NQUAD;
           const unsigned g2 = (unsigned)((nt + kThreads - 1) / kThreads);
           ++g_launch_count;
-          k_ecp_quad<NE, NA><<<g2, kThreads, kSmem, st>>>(*sys, params, pos, rot, B, w);
+          k_ecp_quad<NE, NA><<<g2, kThreads, kSmem, st>>>(*sys, params, pos, rot, B, w, nullptr, 0.0);
         }
       }
       if (stages & 4) ++g_launch_count;
@@ -701,8 +846,51 @@ struct Launch {
     return AIQMC_OK;
   }
 
+  // T-moves (DMC/Tmoves.py:32-225): prep -> per-point amplitudes (the quadrature kernel in record mode) -> select
+  static int tmove(const AiqmcSystem* sys, const AiqmcEcp* ecp, const double* params, const double* pos,
+                   const double* rot, const double* u, const double* rnd, int64_t B, double tau, double* pos_out,
+                   double* acceptance, int32_t* selected, void* ws, int64_t ws_bytes, cudaStream_t st) {
+    if (B <= 0) return AIQMC_OK;
+    if (ws_bytes < tmove_ws_bytes(NE, NA, B)) return AIQMC_E_WORKSPACE;
+    EnergyWs w = carve_energy_ws(ws, NE, NA, B, 1);
+    double* tm = (double*)((char*)ws + energy_ws_bytes(NE, NA, B, 1));
+    AQ_CUDA_OK(upload_ecp(ecp, st));
+    const unsigned g1 = (unsigned)((B + kThreads - 1) / kThreads);
+    AQ_CUDA_OK(prep(k_tmove_prep<NE, NA>));
+    ++g_launch_count;
+    k_tmove_prep<NE, NA><<<g1, kThreads, kSmem, st>>>(*sys, params, pos, rot, B, w);
+    if constexpr (kPt) {
+      AQ_CUDA_OK(cudaMemcpyToSymbolAsync(c_par, params, make_layout(NE, NA).total * sizeof(double), 0,
+                                         cudaMemcpyDeviceToDevice, st));
+      launch_pt(sys, pos, rot, B, w, tm, tau, st, std::make_integer_sequence<int, NE>{});
+    } else {
+      AQ_CUDA_OK(prep(k_ecp_quad<NE, NA>));
+      const int64_t nt = B * NE * NA * AIQMC_NQUAD;
+      ++g_launch_count;
+      k_ecp_quad<NE, NA><<<(unsigned)((nt + kThreads - 1) / kThreads), kThreads, kSmem, st>>>(*sys, params, pos, rot, B, w,
+                                                                                          tm, tau);
+    }
+    ++g_launch_count;
+    k_tmove_select<NE, NA><<<(unsigned)((B * NE + kThreads - 1) / kThreads), kThreads, 0, st>>>(
+        pos, rot, params, tm, u, rnd, B, pos_out, acceptance, selected);
+    AQ_CUDA_OK(cudaGetLastError());
+    return AIQMC_OK;
+  }
+
+  static cudaError_t upload_ecp(const AiqmcEcp* ecp, cudaStream_t st) {
+    static AiqmcEcp h_ecp;                 // last table uploaded to this TU's __constant__ copy
+    static bool h_valid = false;
+    if (!h_valid || memcmp(&h_ecp, ecp, sizeof(AiqmcEcp)) != 0) {
+      const cudaError_t e = cudaMemcpyToSymbolAsync(c_ecp, ecp, sizeof(AiqmcEcp), 0, cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) return e;
+      h_ecp = *ecp;
+      h_valid = true;
+    }
+    return cudaSuccess;
+  }
+
   static const OpsTable* table() {
-    static const OpsTable t = {NE, NA, &Launch::psi, &Launch::sweep, &Launch::energy};
+    static const OpsTable t = {NE, NA, &Launch::psi, &Launch::sweep, &Launch::energy, &Launch::tmove};
     return &t;
   }
 };

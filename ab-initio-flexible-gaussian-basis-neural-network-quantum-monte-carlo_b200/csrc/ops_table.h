@@ -14,5 +14,7 @@ struct OpsTable {
                double, double, int, uint8_t*, double*, double*, void*, int64_t, cudaStream_t);
   int (*energy)(const AiqmcSystem*, const AiqmcEcp*, const double*, const double*, const double*, int64_t, double*,
                 void*, int64_t, int, cudaStream_t);
+  int (*tmove)(const AiqmcSystem*, const AiqmcEcp*, const double*, const double*, const double*, const double*,
+               const double*, int64_t, double, double*, double*, int32_t*, void*, int64_t, cudaStream_t);
 };
 }  // namespace aiqmc

@@ -187,8 +187,28 @@ class WalkerEngine:
         return neww, inds
 
     def gather_walkers(self, pos: torch.Tensor, inds: torch.Tensor) -> torch.Tensor:
-        out = torch.empty_like(pos)
+        """out[k] = pos[inds[k]]; pos may hold more rows than inds selects (cross-GPU population control)."""
+        out = torch.empty((inds.shape[0], pos.shape[1]), dtype=pos.dtype, device=pos.device)
+        inds = inds.to(torch.int32).contiguous()
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.aiqmc_gather_walkers(_ptr(pos), _ptr(inds), pos.shape[0], pos.shape[1], _ptr(out),
-                                                     _stream()), "aiqmc_gather_walkers")
+            _lib.check(self.lib.aiqmc_gather_walkers(_ptr(pos.contiguous()), _ptr(inds), inds.shape[0], pos.shape[1],
+                                                     _ptr(out), _stream()), "aiqmc_gather_walkers")
         return out
+
+    def dmc_tmove(self, pos: torch.Tensor, rot: torch.Tensor, u: torch.Tensor, rnd: torch.Tensor, tstep: float):
+        """DMC/Tmoves.py:32-225 for the whole batch: (new positions (B,3N), acceptance (B,N), selected move (B,N))."""
+        if self.ecp is None:
+            raise ValueError("T-moves need the ccECP tables (engine.ecp)")
+        p = self._pos(pos).reshape(-1, 3 * self.n)
+        B = p.shape[0]
+        cv = lambda a, shape: torch.as_tensor(a).to(device=self.device, dtype=torch.float64).reshape(shape).contiguous()
+        r, uu, rr = cv(rot, (B, 9)), cv(u, (B,)), cv(rnd, (B, self.n))
+        ws = self._workspace("tmove", self.lib.aiqmc_dmc_tmove_workspace_bytes(C.byref(self.sys), B))
+        out = torch.empty_like(p)
+        acc = torch.empty((B, self.n), dtype=torch.float64, device=self.device)
+        sel = torch.empty((B, self.n), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.aiqmc_dmc_tmove(C.byref(self.sys), C.byref(self.ecp), _ptr(self.params_dev), _ptr(p),
+                                                _ptr(r), _ptr(uu), _ptr(rr), B, float(tstep), _ptr(out), _ptr(acc),
+                                                _ptr(sel), _ptr(ws), ws.numel(), _stream()), "aiqmc_dmc_tmove")
+        return out, acc, sel

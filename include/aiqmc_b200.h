@@ -143,6 +143,18 @@ int aiqmc_local_energy_ecp_stages(const AiqmcSystem* sys, const AiqmcEcp* ecp, c
                                   const double* pos, const double* rot, int64_t n_walkers, double* e_l,
                                   void* workspace, int64_t workspace_bytes, int32_t stage_mask,
                                   void* stream);
+/* ---- DMC T-moves: replaces compute_tmoves / calculate_ratio_weight_tmoves (DMC/Tmoves.py:32-225) ------
+ * One non-local move attempt per electron of every walker: amplitudes (exp(-tstep v_l) - 1) P_l(cos) * ratio on
+ * the 50-point quadrature of every (electron, atom), clipped at 0 in jnp's lexicographic complex order, the cdf /
+ * searchsorted selection driven by u (B) (the jax.random.uniform(key) of :146), the back-amplitude norm with the
+ * reference's electron-axis indexing and hard-coded 1:19:55:79:151 slices (quirk Q18), and the accept test against
+ * rnd (B,N) (:216-217).  rot (B,3,3) as in aiqmc_local_energy_ecp.  pos_out (B,3N), acceptance (B,N),
+ * selected (B,N) int32 move index (0 = stay; may be NULL). */
+int64_t aiqmc_dmc_tmove_workspace_bytes(const AiqmcSystem* sys, int64_t n_walkers);
+int aiqmc_dmc_tmove(const AiqmcSystem* sys, const AiqmcEcp* ecp, const double* params, const double* pos,
+                    const double* rot, const double* u, const double* rnd, int64_t n_walkers, double tstep,
+                    double* pos_out, double* acceptance, int32_t* selected, void* workspace,
+                    int64_t workspace_bytes, void* stream);
 /* Block-reduced [sum Re E, sum Im E, sum |E|^2, count] -> stats[4] (device), the partials of
  * pmean(mean(e_l)) and the variance at Loss/pploss.py:165-167; all-reduced over GPUs by the host
  * (NCCL sum of 4 doubles).  e_l_stride = 1 (real) or 2 (complex interleaved). */

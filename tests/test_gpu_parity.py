@@ -222,3 +222,39 @@ def test_cached_quadrature_kernels_match_full_evaluation_kernel(name, rich):
     # run-to-run bit reproducibility of the deterministic reductions
     assert np.array_equal(e_def, eng.local_energy(torch.tensor(case.pos), rot, stages=7).cpu().numpy())
     assert np.array_equal(e_coop, eng.local_energy(torch.tensor(case.pos), rot, stages=7 | 16).cpu().numpy())
+
+
+@pytest.mark.parametrize("name,rich,tstep,scale", [("C_ecp", False, 0.05, 1.0), ("C_ecp", True, 1.0, -3.0),
+                                                   ("N2_ecp", True, 1.0, -3.0), ("h2like", True, 1.0, -5.0)])
+def test_dmc_tmoves_match_oracle(name, rich, tstep, scale):
+    """compute_tmoves (DMC/Tmoves.py:32-225): selected move per electron bit-exact, acceptance to 1e-8, final
+    configuration identical.  The physical carbon table at tstep 0.05 never leaves move 0 ("stay"); the rich
+    tables with attractive (negative) coefficients and a long step make non-trivial moves common."""
+    case = Case(**CASES[name], nwalkers=24, width=0.6)
+    tabs = ecp_tables(case.a, rich=rich)
+    tabs['non_local_coes'] = tabs['non_local_coes'] * scale
+    rng = case.rng
+    rot = O.random_rotations(rng, case.B)
+    u = rng.uniform(size=case.B)
+    rnd = rng.uniform(size=(case.B, case.n))
+    net = aiqmc_b200.make_ai_net(**case.kw)
+    tm = aiqmc_b200.compute_tmoves(2, tstep, case.n, case.a, 3, net.apply, tabs['rn_non_local'], tabs['non_local_coes'],
+                                   tabs['non_local_exps'])
+    data = aiqmc_b200.AINetData(positions=torch.tensor(case.pos), spins=case.t_spins, atoms=case.t_atoms,
+                                charges=torch.tensor(case.charges))
+    new_pos, acc = tm(data, case.params, dict(rot=torch.tensor(rot), u=torch.tensor(u), rnd=torch.tensor(rnd)))
+    eng = net.apply.bind(case.params, case.t_atoms)        # the engine `tm` ran on (ECP table already attached)
+    _, _, sel = eng.dmc_tmove(torch.tensor(case.pos), torch.tensor(rot), torch.tensor(u), torch.tensor(rnd), tstep)
+    ref = O.compute_tmoves(2, tstep, case.n, case.a, 3, O.make_log_network(case.net.apply), tabs['rn_non_local'],
+                           tabs['non_local_coes'], tabs['non_local_exps'])
+    moved = 0
+    for b in range(case.B):
+        d1 = O.AINetData(positions=torch.tensor(case.pos[b]), spins=case.t_spins, atoms=case.t_atoms,
+                         charges=torch.tensor(case.charges))
+        final, acceptance, aux = ref(d1, case.params, dict(rot=torch.tensor(rot[b]), u=u[b], rnd=torch.tensor(rnd[b])))
+        assert np.array_equal(sel[b].cpu().numpy(), aux['selected'].numpy()), b          # bit-exact selection
+        np.testing.assert_allclose(acc[b].cpu().numpy(), acceptance.numpy().ravel(), rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(new_pos[b].cpu().numpy(), final.numpy(), rtol=1e-10, atol=1e-10)
+        moved += int((aux['selected'] > 0).sum())
+    if rich:
+        assert moved > 0, "test inputs never selected a non-trivial T-move"

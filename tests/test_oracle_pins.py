@@ -11,6 +11,7 @@ import pytest
 import scipy.special
 import torch
 
+from common import CASES, Case, ecp_tables
 from oracle import aiqmc_oracle as O
 
 torch.set_default_dtype(torch.float64)
@@ -174,3 +175,28 @@ def test_branch_comb_counts_dyadic_weights():
     assert counts.sum() == 8 and abs(float(new_w) - 1.0) < 1e-15
     assert np.all(np.abs(counts - w.numpy()) < 1.0 + 1e-12)      # systematic comb: |n_i - w_i/wbar| < 1
     assert counts[4] == 0
+
+
+def test_tmove_restatement_self_consistency():
+    """compute_tmoves (DMC/Tmoves.py:32-225) has no reference test; pin the restatement's invariants: with all
+    non-local coefficients zero every amplitude is 0, so norm == 1, move 0 ("stay") is selected, the acceptance is
+    exactly 1 and the configuration is unchanged; the bisection equals numpy.searchsorted on sorted real input."""
+    case = Case(**CASES["C_ecp"], nwalkers=2)
+    tabs = ecp_tables(1)
+    z = np.zeros_like(tabs['non_local_coes'])
+    tm = O.compute_tmoves(2, 0.1, case.n, case.a, 3, O.make_log_network(case.net.apply), tabs['rn_non_local'], z,
+                          tabs['non_local_exps'])
+    rot = O.random_rotations(case.rng, 1)[0]
+    d1 = O.AINetData(positions=torch.tensor(case.pos[0]), spins=case.t_spins, atoms=case.t_atoms,
+                     charges=torch.tensor(case.charges))
+    final, acc, aux = tm(d1, case.params, dict(rot=torch.tensor(rot), u=0.42, rnd=torch.tensor(case.rng.uniform(size=case.n))))
+    assert complex(aux['norm']) == 1.0
+    assert aux['selected'].tolist() == [0] * case.n
+    np.testing.assert_array_equal(acc.numpy().ravel(), np.ones(case.n))
+    np.testing.assert_array_equal(final.numpy(), case.pos[0])
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 51, 64, 101):
+        arr = np.sort(rng.uniform(size=n))
+        for q in list(rng.uniform(size=20)) + [arr[0], arr[-1], -1.0, 2.0]:
+            got = O.searchsorted_scan(torch.tensor(arr, dtype=torch.complex128), complex(q))
+            assert got == int(np.searchsorted(arr, q, side='left')), (n, q)
