@@ -265,6 +265,37 @@ def branch(engine: WalkerEngine, weights: torch.Tensor, key):
     return engine.branch_comb(weights, float(key))
 
 
+def dmc_propagate(signed_network, lognetwork, tstep: float, nelectrons: int, natoms: int, ndim: int, batch_size: int,
+                  charges, rn_local, local_coes, local_exps, rn_non_local, non_local_coes, non_local_exps,
+                  list_l: int = 2, process_group=None):
+    """DMC/dmc.py:13-93 -> dmc_propagate_run(params, key, data, weights, branchcut_start, e_trial, e_est)
+    -> (eloc_new, weights, new_data): T-move, drift-diffusion sweep, local energy at the old and new configurations,
+    the two S values and the weight update w *= exp(tstep * tdamp * (S_new + S_old) / 2).
+    key = dict(tmove=dict(rot, u, rnd), sweep=dict(gauss1, gauss2, rnd), rot=(B,3,3)): the draws the reference
+    makes from its single key, as explicit arrays (parity mode)."""
+    tm = compute_tmoves(list_l, tstep, nelectrons, natoms, ndim, lognetwork, rn_non_local, non_local_coes,
+                        non_local_exps)
+    dd = propose_drift_diffusion(signed_network, tstep, ndim, nelectrons, batch_size)
+    le = local_energy(signed_network, charges, lognetwork=lognetwork, rn_local=rn_local, local_coes=local_coes,
+                      local_exps=local_exps, rn_non_local=rn_non_local, non_local_coes=non_local_coes,
+                      non_local_exps=non_local_exps, natoms=natoms, nelectrons=nelectrons, ndim=ndim, list_l=list_l)
+
+    def dmc_propagate_run(params, key, data: AINetData, weights, branchcut_start, e_trial, e_est):
+        eng = _engine_of(signed_network, params, data)
+        pos, _ = tm(data, params, key['tmove'])
+        t_move_data = replace(data, positions=pos)
+        new_data, tdamp, grad_eff_old, grad_new_eff, _ = dd(params, key['sweep'], t_move_data)
+        eloc_old, _ = le(params, key['rot'], data)            # dmc.py:81: the configuration BEFORE the T-move
+        eloc_new, _ = le(params, key['rot'], new_data)
+        bc = torch.as_tensor(branchcut_start).to(device=eng.device, dtype=torch.float64).reshape(-1).contiguous()
+        s_old = comput_S(eng, e_trial, e_est, bc, grad_eff_old, tstep, eloc_old, process_group)
+        s_new = comput_S(eng, e_trial, e_est, bc, grad_new_eff, tstep, eloc_new, process_group)
+        w = torch.as_tensor(weights).to(device=eng.device, dtype=torch.float64).clone().contiguous()
+        eng.dmc_weights(w, s_old, s_new, tstep, float(tdamp))
+        return eloc_new, w, new_data
+    return dmc_propagate_run
+
+
 def branch_global(engine: WalkerEngine, weights: torch.Tensor, positions: torch.Tensor, key, process_group=None):
     """Population control across all GPUs of the job (the reference combs per device only): the
     systematic comb of DMC/branch.py:10-34 over the all-gathered weights + migration of the selected walkers.

@@ -779,3 +779,33 @@ def compute_tmoves(list_l, tstep, nelectrons, natoms, ndim, lognetwork, Rn_non_l
         aux = dict(selected=torch.tensor(sel), norm=norm, back_norm=back_norm, cdf=cdf, total=total, accept=cond)
         return final, acceptance, aux
     return calculate_ratio_weight_tmoves
+
+
+def dmc_propagate(signed_network, tstep, nelectrons, natoms, ndim, batch_size, charges, rn_local, local_coes,
+                  local_exps, rn_non_local, non_local_coes, non_local_exps, list_l=2):
+    """DMC/dmc.py:72-93 composed from the pieces above (single device).  key = dict(tmove=dict(rot (B,3,3), u (B,),
+    rnd (B,N)), sweep=dict(gauss1, gauss2, rnd), rot (B,3,3))."""
+    lognet = make_log_network(signed_network)
+    tm = compute_tmoves(list_l, tstep, nelectrons, natoms, ndim, lognet, rn_non_local, non_local_coes, non_local_exps)
+    dd = propose_drift_diffusion(select_output(signed_network, 1), tstep, ndim, nelectrons, batch_size)
+    le = local_energy_ecp(signed_network, lognet, charges, None, rn_local, local_coes, local_exps, rn_non_local,
+                          non_local_coes, non_local_exps, natoms, nelectrons, ndim, list_l)
+
+    def dmc_propagate_run(params, key, data: AINetData, weights, branchcut_start, e_trial, e_est):
+        B = data.positions.shape[0]
+        atoms, spins, ch = data.atoms[0], data.spins[0], data.charges[0]
+        pos = []
+        for b in range(B):                                   # tmoves_pmap: vmap over walkers
+            d1 = AINetData(positions=data.positions[b], spins=spins, atoms=atoms, charges=ch)
+            k = key['tmove']
+            final, _, _ = tm(d1, params, dict(rot=k['rot'][b], u=float(k['u'][b]), rnd=k['rnd'][b]))
+            pos.append(final)
+        t_move_data = AINetData(positions=torch.stack(pos), spins=data.spins, atoms=data.atoms, charges=data.charges)
+        new_data, tdamp, grad_eff_old, grad_new_eff, _ = dd(params, key['sweep'], t_move_data)
+        flat = lambda d: AINetData(positions=d.positions, spins=spins, atoms=atoms, charges=ch)
+        eloc_old, _ = le(params, key['rot'], flat(data))
+        eloc_new, _ = le(params, key['rot'], flat(new_data))
+        s_old = comput_S(e_trial, e_est, branchcut_start, grad_eff_old ** 2, tstep, eloc_old, nelectrons)
+        s_new = comput_S(e_trial, e_est, branchcut_start, grad_new_eff ** 2, tstep, eloc_new, nelectrons)
+        return eloc_new, torch.exp(tstep * tdamp * (0.5 * s_new + 0.5 * s_old)) * weights, new_data
+    return dmc_propagate_run

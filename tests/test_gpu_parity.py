@@ -258,3 +258,28 @@ def test_dmc_tmoves_match_oracle(name, rich, tstep, scale):
         moved += int((aux['selected'] > 0).sum())
     if rich:
         assert moved > 0, "test inputs never selected a non-trivial T-move"
+
+
+def test_dmc_propagate_one_full_step():
+    """dmc_propagate_run (DMC/dmc.py:72-93): T-move -> drift-diffusion -> E_L(old), E_L(new) -> S -> weights."""
+    tstep = 0.05
+    case = Case(**CASES["C_ecp"], nwalkers=20, width=0.7)
+    tabs = ecp_tables(1, rich=True)
+    rng = case.rng
+    key = dict(tmove=dict(rot=torch.tensor(O.random_rotations(rng, case.B)), u=torch.tensor(rng.uniform(size=case.B)),
+                          rnd=torch.tensor(rng.uniform(size=(case.B, case.n)))),
+               sweep=case.sweep_rand(tstep), rot=torch.tensor(O.random_rotations(rng, case.B)))
+    weights = torch.tensor(rng.uniform(0.5, 1.5, size=case.B))
+    branchcut = torch.full((case.B,), 10 * 0.3)
+    e_trial, e_est = -5.39, -5.41
+    ref = O.dmc_propagate(case.net.apply, tstep, case.n, 1, 3, case.B, case.charges, **tabs)
+    e_ref, w_ref, d_ref = ref(case.params, key, case.oracle_data(), weights, branchcut, e_trial, e_est)
+    net = aiqmc_b200.make_ai_net(**case.kw)
+    run = aiqmc_b200.dmc_propagate(net.apply, net.apply, tstep, case.n, 1, 3, case.B, case.charges, **tabs)
+    data = aiqmc_b200.AINetData(positions=torch.tensor(case.pos), spins=case.t_spins, atoms=case.t_atoms,
+                                charges=torch.tensor(case.charges))
+    e_gpu, w_gpu, d_gpu = run(case.params, key, data, weights, branchcut, e_trial, e_est)
+    np.testing.assert_allclose(d_gpu.positions.cpu().numpy(), d_ref.positions.numpy(), rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(e_gpu.cpu().numpy(), e_ref.numpy(), atol=1e-5, rtol=0)        # north_star: 1e-5 Ha
+    np.testing.assert_allclose(e_gpu.cpu().numpy(), e_ref.numpy(), atol=1e-8, rtol=1e-9)
+    np.testing.assert_allclose(w_gpu.cpu().numpy(), w_ref.numpy(), rtol=1e-9)
