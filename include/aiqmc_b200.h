@@ -143,6 +143,26 @@ int aiqmc_local_energy_ecp_stages(const AiqmcSystem* sys, const AiqmcEcp* ecp, c
                                   const double* pos, const double* rot, int64_t n_walkers, double* e_l,
                                   void* workspace, int64_t workspace_bytes, int32_t stage_mask,
                                   void* stream);
+/* ---- contracted Gaussian basis: replaces primitive_Gaussian_basis (AIQMC/Gaussian_orbitals.py:11-13) and
+ *      follows ferminet/utils/gto.py:117-135,338-389 (real solid harmonics, AO = radial * angular, m = -l..l) ----
+ * AO_k(r) = [sum_p coef_p exp(-alpha_p |r-R|^2)] * |r-R|^l Y_lm(r-R), l <= 3, with analytic gradient and Laplacian.
+ * shells / centres are HOST arrays (uploaded to constant memory); points (n,3) device.  val (n,nao), grad (n,nao,3)
+ * and lap (n,nao) are device outputs; grad and lap may be NULL. */
+#define AIQMC_GTO_MAX_PRIM 16
+#define AIQMC_GTO_MAX_SHELLS 48
+#define AIQMC_GTO_MAX_CENTRES 16
+typedef struct AiqmcGtoShell {
+  int32_t l;          /* angular momentum 0..3 */
+  int32_t n_prim;     /* primitives in the contraction */
+  int32_t centre;     /* index into centres */
+  int32_t ao_offset;  /* first AO column of this shell (its 2l+1 functions are consecutive, m = -l..l) */
+  double alpha[AIQMC_GTO_MAX_PRIM];
+  double coef[AIQMC_GTO_MAX_PRIM];
+} AiqmcGtoShell;
+int aiqmc_gto_eval(const AiqmcGtoShell* shells, int32_t n_shells, const double* centres, int32_t n_centres,
+                   const double* points, int64_t n_points, int32_t nao, double* val, double* grad, double* lap,
+                   void* stream);
+
 /* ---- DMC T-moves: replaces compute_tmoves / calculate_ratio_weight_tmoves (DMC/Tmoves.py:32-225) ------
  * One non-local move attempt per electron of every walker: amplitudes (exp(-tstep v_l) - 1) P_l(cos) * ratio on
  * the 50-point quadrature of every (electron, atom), clipped at 0 in jnp's lexicographic complex order, the cdf /
