@@ -296,6 +296,30 @@ def dmc_propagate(signed_network, lognetwork, tstep: float, nelectrons: int, nat
     return dmc_propagate_run
 
 
+def reconfigure(engine: WalkerEngine, positions: torch.Tensor, newinds: torch.Tensor, noise: torch.Tensor):
+    """DMC/main_dmc.py:218-231, on the device: keep the UNIQUE survivors of the comb (ascending index), then pad
+    the batch back to B rows with copies of the last survivor + `noise` rows (the jax.random.uniform(key, (n, 3N))
+    draw of :226).  Returns (new positions (B,3N), number of distinct survivors)."""
+    uniq = torch.unique(newinds.to(torch.int64))                      # sorted, as jnp.unique
+    kept = engine.gather_walkers(positions, uniq)
+    nmiss = positions.shape[0] - uniq.shape[0]
+    if nmiss > 0:
+        extra = kept[-1][None, :] + torch.as_tensor(noise).to(device=kept.device, dtype=kept.dtype)[:nmiss]
+        kept = torch.cat([kept, extra], dim=0)
+    return kept, int(uniq.shape[0])
+
+
+def estimate_energy(energy: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
+    """DMC/estimate_energy.py:4-5: weighted average over the whole (block, iteration, walker) history."""
+    e, w = torch.as_tensor(energy), torch.as_tensor(weights).to(torch.as_tensor(energy).device)
+    return (e * w).sum() / w.sum()
+
+
+def trial_energy(e_est, weights: torch.Tensor, feedback: float):
+    """DMC/main_dmc.py:242: E_T = E_est - feedback * log(mean w)."""
+    return e_est - feedback * torch.log(torch.as_tensor(weights).mean()).real
+
+
 def branch_global(engine: WalkerEngine, weights: torch.Tensor, positions: torch.Tensor, key, process_group=None):
     """Population control across all GPUs of the job (the reference combs per device only): the
     systematic comb of DMC/branch.py:10-34 over the all-gathered weights + migration of the selected walkers.

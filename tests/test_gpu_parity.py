@@ -1,6 +1,8 @@
 """GPU parity: the CUDA path (through the C ABI / aiqmc_b200 host mirror) against the oracle on the
 same seeded inputs.  Tolerances are north_star's: log|psi| 1e-6 relative, E_L 1e-5 Ha, accept
 masks and comb indices bit-exact."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -283,3 +285,24 @@ def test_dmc_propagate_one_full_step():
     np.testing.assert_allclose(e_gpu.cpu().numpy(), e_ref.numpy(), atol=1e-5, rtol=0)        # north_star: 1e-5 Ha
     np.testing.assert_allclose(e_gpu.cpu().numpy(), e_ref.numpy(), atol=1e-8, rtol=1e-9)
     np.testing.assert_allclose(w_gpu.cpu().numpy(), w_ref.numpy(), rtol=1e-9)
+
+
+def test_reconfigure_and_energy_estimators():
+    """main_dmc.py:218-242 + estimate_energy.py: unique survivors + noise padding, weighted average, E_trial."""
+    rng = np.random.default_rng(9)
+    B = 300
+    case = Case(**CASES["C_ecp"], nwalkers=2)
+    eng = engine(case)
+    pos = torch.tensor(rng.normal(size=(B, 12)))
+    w = torch.tensor(rng.uniform(0.0, 2.5, size=B))
+    noise = torch.tensor(rng.uniform(size=(B, 12)))
+    _, inds_ref = O.branch(w, 0.61)
+    ref, nuniq_ref = O.reconfigure(pos, inds_ref, noise)
+    _, inds = eng.branch_comb(w.cuda(), 0.61)
+    got, nuniq = aiqmc_b200.reconfigure(eng, pos.cuda(), inds, noise)
+    assert nuniq == nuniq_ref and nuniq < B
+    np.testing.assert_array_equal(got.cpu().numpy(), ref.numpy())
+    e = torch.tensor(rng.normal(-5.4, 0.2, size=(3, 4, B)))
+    ww = torch.tensor(rng.uniform(0.5, 1.5, size=(3, 4, B)))
+    np.testing.assert_allclose(float(aiqmc_b200.estimate_energy(e.cuda(), ww.cuda())), np.average(e.numpy(), weights=ww.numpy()), rtol=1e-13)
+    np.testing.assert_allclose(float(aiqmc_b200.trial_energy(-5.4, w.cuda(), 1.0)), -5.4 - math.log(float(w.mean())), rtol=1e-13)
