@@ -113,6 +113,7 @@ struct DerivSplit {
           }
       }
     }
+    keep_alive(&pr); keep_alive(Mi);      // see grad_reverse: forbid stack-slot sharing of live arrays
   }
 
   // tangent (first / second derivative along ONE coordinate) of a 4-vector
@@ -307,6 +308,7 @@ struct DerivSplit {
         for (int l = 0; l < N; ++l) trxx += X[k * N + l].re * X[l * N + k].re - X[k * N + l].im * X[l * N + k].im;
       lap_out = l2 - trxx;
     }
+    keep_alive(cr); keep_alive(cc); keep_alive(hd); keep_alive(hs); keep_alive(h0e); keep_alive(ye);
   }
 
   // tangent of one-electron layer l, row k (one_layer of psi_core.cuh with cached tanh outputs).
@@ -364,6 +366,190 @@ struct DerivSplit {
       const double ws = LAP ? g * (zs[m] - 2.0 * t * zd[m] * zd[m]) : 0.0;
       hd[m] = (DIN == 4) ? (ind + wd) * kInvSqrt2 : wd;
       hs[m] = LAP ? ((DIN == 4) ? (ins + ws) * kInvSqrt2 : ws) : 0.0;
+    }
+  }
+
+  // ---- gradient of log|psi| by ONE reverse (adjoint) sweep, fused with the forward pass in the same thread.
+  //      3N forward tangents cost ~23 k FP64 instructions per configuration at N=4 (and grow like N); the adjoint
+  //      costs ~7 k whatever N: every cached tanh output is used once, every weight twice.
+  //        (1) d log|det| = Re tr(M^-1 dM) gives the adjoints of h_3, of the envelopes and of the Ynlm outputs;
+  //        (2) the three one-electron layers are walked backwards (adjoints of the per-row inputs, of the block
+  //            means and of the pair block sums G_l);
+  //        (3) every ordered pair chain is walked backwards from its three levels to the inter-electron vector;
+  //        (4) each electron's local part (features, Ynlm stream, envelope, e-n Jastrow) is contracted with its
+  //            adjoints through a 3-direction jet (one transcendental evaluation per electron).
+  static AQ_HD void grad_reverse(const AiqmcSystem& sys, const double* __restrict__ P, const double* __restrict__ x,
+                                 double& phase, double& logabs, double* __restrict__ grad) {
+    constexpr LayoutC<NE, NA> L{};
+    typename PS::Primal pr;
+    cplx Mi[N * N];
+    double hp[3 * N * N * 4];                 // pair chains, all levels: hp[((l*N + i)*N + j)*4 + c]
+    double t1[3 * N * QM];                    // first-stage tanh outputs of the one-electron layers
+    PS::forward(sys, P, x, pr, Mi, hp, 1, t1, 1);
+    double ld;
+    PS::gj_inverse(Mi, ld, phase);
+    logabs = ld + pr.jastrow;
+    const double inv_n[2] = {1.0 / sys.n_up, 1.0 / sys.n_dn};
+
+    // (1) determinant
+    double h_bar[N][4], y_bar[N][6], env_bar[N];
+    for (int k = 0; k < N; ++k) {
+      env_bar[k] = 0.0;
+      for (int c = 0; c < 4; ++c) h_bar[k][c] = 0.0;
+      for (int m = 0; m < 6; ++m) y_bar[k][m] = 0.0;
+    }
+    for (int k = 0; k < N; ++k) {
+      const int s = k < sys.n_up_rows ? 0 : 1;
+      const double* W = P + L.orb_w[s];
+      const double* Bv = P + L.orb_b[s];
+      const int e = sys.sigma[k];
+      for (int j = 0; j < N; ++j) {
+        double yo = 0.0;
+        for (int m = 0; m < 6; ++m) yo += pr.y[k][m] * P[L.y_w + m * N + j];
+        double pre = Bv[2 * j], pim = Bv[2 * j + 1];
+        for (int c = 0; c < 4; ++c) { pre += pr.h[3][e][c] * W[c * 2 * N + 2 * j]; pim += pr.h[3][e][c] * W[c * 2 * N + 2 * j + 1]; }
+        const cplx mi = Mi[j * N + k];
+        const double ev = pr.env[k] * yo;
+        const double pre_bar = mi.re * ev, pim_bar = -mi.im * ev;
+        const double ev_bar = mi.re * pre - mi.im * pim;
+        for (int c = 0; c < 4; ++c) h_bar[e][c] += pre_bar * W[c * 2 * N + 2 * j] + pim_bar * W[c * 2 * N + 2 * j + 1];
+        env_bar[k] += ev_bar * yo;
+        const double yo_bar = ev_bar * pr.env[k];
+        for (int m = 0; m < 6; ++m) y_bar[k][m] += yo_bar * P[L.y_w + m * N + j];
+      }
+    }
+
+    // (2) one-electron layers, backwards
+    double G_bar[3][2][N][4];
+    double h0_bar[N][4 * A];
+    for (int l = 2; l >= 0; --l) {
+      if (l == 0) layer_reverse<4 * A>(sys, P, 0, pr, t1, inv_n, h_bar, G_bar[0], h0_bar);
+      else layer_reverse<4>(sys, P, l, pr, t1, inv_n, h_bar, G_bar[l], h_bar);
+    }
+
+    // (3) pair chains, backwards
+    for (int q = 0; q < 3 * N; ++q) grad[q] = 0.0;
+    for (int i = 0; i < N; ++i) {
+      const int s = i < sys.n_up ? 0 : 1;
+      for (int j = 0; j < N; ++j) {
+        if (i == j) continue;
+        const double* a0 = hp + ((0 * N + i) * N + j) * 4;
+        const double* a1 = hp + ((1 * N + i) * N + j) * 4;
+        const double* a2 = hp + ((2 * N + i) * N + j) * 4;
+        double b1[4], b0[4];
+        chain_reverse(P + L.dbl_w[1], a1, a2, G_bar[2][s][j], G_bar[1][s][j], b1);
+        chain_reverse(P + L.dbl_w[0], a0, a1, b1, G_bar[0][s][j], b0);
+        const double r = a0[0];
+        double r_bar = b0[0];
+        if (i < j) {                                            // e-e Pade term (Jastrow.py:23-41)
+          const double q = s_inv(1.0 + P[L.jas_alpha + i * N + j] * r);
+          r_bar += P[L.jas_cusp + i * N + j] * q * q;
+        }
+        const double rs = r_bar * s_inv(r);
+        for (int c = 0; c < 3; ++c) {
+          const double db = b0[1 + c] + rs * a0[1 + c];           // d = x_j - x_i
+          grad[3 * j + c] += db;
+          grad[3 * i + c] -= db;
+        }
+      }
+    }
+
+    // (4) electron-local parts through a 3-direction jet
+    using J = Jet<false, 3>;
+    using Op = ScalarOps<J>;
+    for (int e = 0; e < N; ++e) {
+      J xj[3];
+      for (int c = 0; c < 3; ++c) { xj[c] = Op::cst(x[3 * e + c]); xj[c].d[c] = 1.0; }
+      J h0e[4 * A], ye[6], enve, jaee;
+      PS::template electron_local<J>(P, e, xj, h0e, ye, enve, jaee);
+      for (int c = 0; c < 3; ++c) {
+        double g = jaee.d[c] + env_bar[e] * enve.d[c];
+        for (int q = 0; q < 4 * A; ++q) g += h0_bar[e][q] * h0e[q].d[c];
+        for (int m = 0; m < 6; ++m) g += y_bar[e][m] * ye[m].d[c];
+        grad[3 * e + c] += g;
+      }
+    }
+    // nvcc 12.9's stack colouring has overlapped live local arrays in this code base three times (DESIGN.md,
+    // toolchain notes); keeping every tape / adjoint array observably alive to the end of the function forbids it.
+    keep_alive(&pr); keep_alive(Mi); keep_alive(hp); keep_alive(t1); keep_alive(h_bar); keep_alive(y_bar);
+    keep_alive(env_bar); keep_alive(G_bar); keep_alive(h0_bar);
+  }
+
+  static AQ_HD void keep_alive(const void* p) {
+#ifdef __CUDA_ARCH__
+    asm volatile("" ::"l"(p) : "memory");
+#else
+    (void)p;
+#endif
+  }
+
+  // adjoint of out = (in + tanh(in . W + b)) / sqrt2 ; t recovered from the cached levels: t = sqrt2 out - in.
+  // in_bar = extra + [out_bar + W (g o out_bar)] / sqrt2
+  static AQ_HD void chain_reverse(const double* __restrict__ W, const double* __restrict__ in, const double* __restrict__ out,
+                                  const double* __restrict__ out_bar, const double* __restrict__ extra,
+                                  double* __restrict__ in_bar) {
+    double zb[4];
+    for (int m = 0; m < 4; ++m) {
+      const double t = kSqrt2 * out[m] - in[m];
+      zb[m] = out_bar[m] * kInvSqrt2 * (1.0 - t * t);
+    }
+    for (int q = 0; q < 4; ++q) {
+      double v = out_bar[q] * kInvSqrt2 + extra[q];
+      for (int m = 0; m < 4; ++m) v += W[q * 4 + m] * zb[m];
+      in_bar[q] = v;
+    }
+  }
+
+  // adjoint of one-electron layer l for all rows.  In: h_bar = adjoint of h_{l+1}.  Out: G_bar_l[s][k][c] = adjoint
+  // of the pair block sums G_l[s][k][c]; hin_bar = adjoint of the layer's per-row input (h_l, or h0 for l == 0).
+  // h_bar and hin_bar may alias (they do for l >= 1).
+  template <int DIN>
+  static AQ_HD void layer_reverse(const AiqmcSystem& sys, const double* __restrict__ P, int l,
+                                  const typename PS::Primal& pr, const double* __restrict__ t1, const double inv_n[2],
+                                  const double (*h_bar)[4], double (*G_bar_l)[N][4], double (*hin_bar)[DIN]) {
+    constexpr LayoutC<NE, NA> L{};
+    constexpr int DTOT = 3 * DIN + 8, Q = DTOT / 4;
+    const double* sw = P + L.sing_w[l];
+    double gup_bar[DIN], gdn_bar[DIN];
+    for (int q = 0; q < DIN; ++q) { gup_bar[q] = 0.0; gdn_bar[q] = 0.0; }
+    double own[N][DIN];                                   // adjoint reaching row k's own input directly
+    for (int k = 0; k < N; ++k) {
+      const double* cw = P + L.conv_w[l] + k * DTOT;
+      double zb[4];
+      for (int m = 0; m < 4; ++m) {
+        const double hn = pr.h[l + 1][k][m];
+        double t, ob;
+        if (DIN == 4) {                                   // residual layer (quirk Q5)
+          const double hprev = (l == 0) ? pr.h0[k][m] : pr.h[l][k][m];
+          t = kSqrt2 * hn - hprev;
+          ob = h_bar[k][m] * kInvSqrt2;
+        } else {
+          t = hn;
+          ob = h_bar[k][m];
+        }
+        zb[m] = ob * (1.0 - t * t);
+        if (DIN == 4) own[k][m] = ob;
+      }
+      if (DIN != 4) for (int q = 0; q < DIN; ++q) own[k][q] = 0.0;
+      for (int q = 0; q < Q; ++q) {
+        double ob = 0.0;
+        for (int m = 0; m < 4; ++m) ob += zb[m] * sw[q * 4 + m];
+        const double t = t1[(l * N + k) * QM + q];
+        const double pb = ob * (1.0 - t * t) * 0.25;
+        for (int c = 0; c < 4; ++c) {
+          const int idx = 4 * q + c;
+          const double xb = pb * cw[idx];
+          if (idx < DIN) own[k][idx] += xb;
+          else if (idx < 2 * DIN) gup_bar[idx - DIN] += xb;
+          else if (idx < 3 * DIN) gdn_bar[idx - 2 * DIN] += xb;
+          else if (idx < 3 * DIN + 4) G_bar_l[0][k][idx - 3 * DIN] = xb * inv_n[0];
+          else G_bar_l[1][k][idx - 3 * DIN - 4] = xb * inv_n[1];
+        }
+      }
+    }
+    for (int k = 0; k < N; ++k) {
+      const bool up = k < sys.n_up;
+      for (int q = 0; q < DIN; ++q) hin_bar[k][q] = own[k][q] + (up ? gup_bar[q] * inv_n[0] : gdn_bar[q] * inv_n[1]);
     }
   }
 

@@ -209,7 +209,11 @@ k_ecp_pt(AiqmcSystem sys, const double* __restrict__ pos, const double* __restri
 
       // ---- one-electron stream of all N electrons; the pair chains advance with the layers
       double h[N][4];
+#ifndef AIQMC_PT_NO_ROLL   // layers share one copy of the row code (7.8 k instead of 10 k SASS instructions, 3 % faster)
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
       for (int l = 0; l < 3; ++l) {
         // column block sums for electron i: G'_l[s][i] = sum_{k in s, k != i} h'_l[k,i] + [s == s_i] h_l[i,i]
         double su[4], sd[4];

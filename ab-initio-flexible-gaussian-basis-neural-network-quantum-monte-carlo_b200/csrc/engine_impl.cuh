@@ -191,6 +191,58 @@ __global__ void __launch_bounds__(kThreads) k_primal(AiqmcSystem sys, const doub
   logabs[t] = la;
 }
 
+// gradient by the fused forward + reverse (adjoint) sweep: one thread per configuration, nothing cached in HBM.
+// OUT == 0: grad (n_cfg,3N); OUT == 1: configurations are (walker, moved electron i), gnew (n_cfg,3) keeps electron
+// i's components.  Always: block partial of sum g^2 over all 3N components (limdrift's batch-global v2, quirk Q6).
+template <int NE, int NA, int SRC, int OUT>
+__global__ void __launch_bounds__(kThreads) k_grad_reverse(AiqmcSystem sys, const double* __restrict__ params,
+                                                           const double* __restrict__ pos, int64_t n_cfg, MovedSrc ms,
+                                                           double* __restrict__ phase, double* __restrict__ logabs,
+                                                           double* __restrict__ gout, double* __restrict__ partials,
+                                                           int pcol) {
+  extern __shared__ double sP[];
+  __shared__ double red[kThreads / 32];
+  const double* P = stage_params<NE, NA>(params, sP);
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double g2 = 0.0;
+  if (t < n_cfg) {
+    double x[3 * NE], g[3 * NE];
+    int i = 0;
+    if (SRC == 0) {
+      for (int q = 0; q < 3 * NE; ++q) x[q] = pos[t * 3 * NE + q];
+    } else {
+      const int64_t b = t / NE;
+      i = (int)(t - b * NE);
+      const double te = taueff_of(ms.scal[0], ms.tau, ms.acyrus);
+      double xn[3];
+      for (int c = 0; c < 3; ++c) {
+        // g = grad_eff * tstep + gauss ; x2 = x1 + g on electron i only   (VMCmcstep.py:60-78)
+        const double step = (ms.grad[b * 3 * NE + 3 * i + c] * te) * ms.tau + ms.gauss1[b * 3 * NE + 3 * i + c];
+        xn[c] = step + pos[b * 3 * NE + 3 * i + c];
+        ms.xprop[t * 3 + c] = xn[c];
+      }
+      for (int e = 0; e < NE; ++e)      // no dynamically indexed stores into x (nvcc 12.9 miscompiled that pattern)
+        for (int c = 0; c < 3; ++c) x[3 * e + c] = (e == i) ? xn[c] : pos[b * 3 * NE + 3 * e + c];
+    }
+    double ph, la;
+    DerivSplit<NE, NA>::grad_reverse(sys, P, x, ph, la, g);
+    if (phase) phase[t] = ph;
+    logabs[t] = la;
+    for (int q = 0; q < 3 * NE; ++q) g2 += g[q] * g[q];
+    if (OUT == 0) {
+      for (int q = 0; q < 3 * NE; ++q) gout[t * 3 * NE + q] = g[q];
+    } else {
+      for (int e = 0; e < NE; ++e)
+        if (e == i)
+          for (int c = 0; c < 3; ++c) gout[t * 3 + c] = g[3 * e + c];
+    }
+  }
+  if (partials) {
+    const double s = block_sum<kThreads>(g2, red);
+    if (threadIdx.x == 0) partials[blockIdx.x * 4 + pcol] = s;
+  }
+}
+
 // tangent pass: one thread per (configuration, electron, direction).  A CTA owns a tile of 32 consecutive
 // configurations and kTanWarps<N> of the 3N (electron, direction) pairs: warp = one pair, lane = one
 // configuration -> coalesced cache reads, no divergence, and the tile's cache lines are fetched from DRAM once
@@ -519,6 +571,7 @@ __global__ void __launch_bounds__(kThreads) k_tmove_prep(AiqmcSystem sys, const 
     Psi<NE, NA>::write_cache(pr, ld + pr.jastrow, ph, mc);
     w.logabs[b] = ld + pr.jastrow;
     w.phase[b] = ph;
+    DerivSplit<NE, NA>::keep_alive(&pr); DerivSplit<NE, NA>::keep_alive(M);
   }
   for (int i = 0; i < NE; ++i)
     for (int a = 0; a < NA; ++a) {
@@ -704,6 +757,28 @@ struct Launch {
          *sys, pos, rot, B, w.cache, w, tm_out, tm_tau), ...);
   }
 
+  static constexpr bool kReverse = (NE <= 16);   // fused reverse-mode gradient (its per-thread tape is 12 N^2 doubles)
+
+  // gradient of n_cfg configurations: fused reverse sweep for N <= 16, the two-pass path beyond
+  template <int SRC, int OUT>
+  static int grad(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_cfg, MovedSrc ms,
+                  double* dcache, double* phase, double* logabs, double* gout, double* partials, int pcol,
+                  int64_t* rows, cudaStream_t st) {
+    if constexpr (kReverse) {
+      AQ_CUDA_OK(prep(k_grad_reverse<NE, NA, SRC, OUT>));
+      const unsigned g = (unsigned)((n_cfg + kThreads - 1) / kThreads);
+      ++g_launch_count;
+      k_grad_reverse<NE, NA, SRC, OUT><<<g, kThreads, kSmem, st>>>(*sys, params, pos, n_cfg, ms, phase, logabs, gout,
+                                                                    partials ? partials + *rows * 4 : nullptr, pcol);
+      if (rows) *rows += g;
+      AQ_CUDA_OK(cudaGetLastError());
+      return AIQMC_OK;
+    } else {
+      return deriv<false, SRC, OUT>(sys, params, pos, n_cfg, ms, dcache, nullptr, phase, logabs, gout, nullptr, 0,
+                                    partials, pcol, rows, st);
+    }
+  }
+
   static int psi(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_cfg, int mode,
                  double* phase, double* logabs, double* grad, double* lap, void* ws, int64_t ws_bytes,
                  cudaStream_t st) {
@@ -720,8 +795,7 @@ struct Launch {
     MovedSrc ms{};
     double* dcache = (double*)ws;
     if (mode == 1)
-      return deriv<false, 0, 0>(sys, params, pos, n_cfg, ms, dcache, nullptr, phase, logabs, grad, nullptr, 0, nullptr, 0,
-                                nullptr, st);
+      return Launch::grad<0, 0>(sys, params, pos, n_cfg, ms, dcache, phase, logabs, grad, nullptr, 0, nullptr, st);
     // Laplacian: the per-coordinate second derivatives of one chunk are summed right after its tangent pass
     double* parts = (double*)((char*)ws + deriv_cache_bytes(NE, NA, true, n_cfg));
     const int64_t chunk = deriv_chunk(NE, NA, true);
@@ -749,15 +823,13 @@ struct Launch {
     MovedSrc ms{w.grad, gauss1, w.scal, w.xprop, tau, acyrus};
     // grad log|psi| at x1 and its batch-global square sum (limdrift, quirk Q6)
     int64_t rows = 0;
-    int rc = deriv<false, 0, 0>(sys, params, pos, B, ms, w.dcache, nullptr, nullptr, w.logabs1, w.grad, nullptr, 0,
-                                w.partials, 0, &rows, st);
+    int rc = grad<0, 0>(sys, params, pos, B, ms, w.dcache, nullptr, w.logabs1, w.grad, w.partials, 0, &rows, st);
     if (rc != AIQMC_OK) return rc;
     ++g_launch_count;
     k_reduce_partials<<<1, kRedThreads, 0, st>>>(w.partials, (int)rows, 0, 1, w.scal, 0);
     // the N single-electron-moved configurations of every walker
     rows = 0;
-    rc = deriv<false, 1, 1>(sys, params, pos, n2, ms, w.dcache, nullptr, nullptr, w.logabs2, w.gnew, nullptr, 0,
-                            w.partials, 1, &rows, st);
+    rc = grad<1, 1>(sys, params, pos, n2, ms, w.dcache, nullptr, w.logabs2, w.gnew, w.partials, 1, &rows, st);
     if (rc != AIQMC_OK) return rc;
     ++g_launch_count;
     k_reduce_partials<<<1, kRedThreads, 0, st>>>(w.partials, (int)rows, 1, 1, w.scal, 1);

@@ -221,9 +221,19 @@ template <bool L, int ND> AQ_HD void s_sqrt_inv(const Jet<L, ND>& r2, Jet<L, ND>
   ri = chain(r2, i, -0.5 * i * i2, 0.75 * i * i2 * i2);
 }
 
+#if defined(AIQMC_TANH_OOL) && defined(__CUDACC__)
+// experiment: one out-of-line body per (NV, ACC) instead of an inlined copy at each of the ~40 call sites
+template <int NV, int ACC>
+static __device__ __noinline__ void tanh_ool(const double* __restrict__ z, double* __restrict__ out) {
+  ftanh_n<NV, ACC>(z, out, g_exp_tab);
+}
+#endif
 // NV tanh at once: doubles go through the interleaved ftanh_n (ILP), jets one by one.
 template <int NV, int ACC>
 AQ_HD void tanhv(const double* __restrict__ z, double* __restrict__ out) {
+#if defined(AIQMC_TANH_OOL) && defined(__CUDA_ARCH__)
+  if constexpr (NV <= 8) { tanh_ool<NV, ACC>(z, out); return; }
+#endif
 #ifdef AIQMC_LIBM
   for (int i = 0; i < NV; ++i) out[i] = tanh(z[i]);
 #else
@@ -608,6 +618,9 @@ struct Psi {
     double ld;
     lu_logdet(M, ld, phase);
     logabs = ld + pr.jastrow;
+#ifdef __CUDA_ARCH__
+    asm volatile("" ::"l"(&pr), "l"(M) : "memory");   // forbid stack-slot sharing of live arrays (DESIGN.md toolchain notes)
+#endif
   }
 
   // ---- value + gradient (+ Laplacian of log|psi| if LAP)

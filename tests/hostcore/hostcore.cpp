@@ -21,6 +21,8 @@ static void run(const AiqmcSystem* sys, const double* P, const double* pos, long
       Psi<NE, NA>::template eval_deriv<false>(*sys, P, x, phase[t], logabs[t], grad + t * 3 * NE, dummy);
     } else if (mode == 2) {
       Psi<NE, NA>::template eval_deriv<true>(*sys, P, x, phase[t], logabs[t], grad + t * 3 * NE, lap[t]);
+    } else if (mode == 5) {      // gradient by the fused reverse sweep (deriv_split.cuh)
+      DerivSplit<NE, NA>::grad_reverse(*sys, P, x, phase[t], logabs[t], grad + t * 3 * NE);
     } else {      // 3 / 4: gradient / gradient + Laplacian through the two-pass path (deriv_split.cuh)
       std::vector<double> scratch(DerivCache<NE, NA>::SIZE_LAP);
       double dummy;

@@ -44,6 +44,10 @@ def test_value_grad_laplacian_match_oracle(hostlib, name):
     np.testing.assert_allclose(g3, gt.numpy(), rtol=1e-9, atol=1e-10)
     np.testing.assert_allclose(g4, g3, rtol=1e-13, atol=1e-13)
     np.testing.assert_allclose(lp4, dt.sum(-1).numpy(), rtol=1e-9, atol=1e-9)
+    # the fused forward + reverse (adjoint) gradient the sweep kernels use
+    ph5, la5, g5, _ = H.host_psi(hostlib, case.spec().c_struct(), packed, case.pos, 5)
+    np.testing.assert_allclose(la5, la, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(g5, gt.numpy(), rtol=1e-9, atol=1e-10)
 
 
 def test_benzene_sized_system_value(hostlib):
