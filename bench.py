@@ -35,6 +35,7 @@ SEED = 20260101
 TSTEP = 0.05
 WALKERS_PER_GPU = 65536
 METRIC = "VMC walker-steps/s incl. local energy"
+WORKLOAD = "C atom ccECP (N=4, A=1): VMC sweep + ccECP local energy, BASELINE configs[1]"
 UNIT = "walker-steps/s"
 
 
@@ -171,9 +172,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C atom ccECP (N=4, A=1) VMC sweep + local energy", "walkers_per_step": nwalk,
-                       "tstep": TSTEP, "note": "oracle port of AIQMCrelease3 (torch CPU, float32/complex64); "
-                       "JAX is not installable here so the genuine reference cannot run"},
+            "config": {"workload": WORKLOAD, "walkers_per_gpu": args.walkers, "global_walkers": args.walkers * args.gpus,
+                       "tstep": TSTEP, "nsteps_per_step": 1, "params": "random-init (reference init scales)",
+                       "sample_walkers_per_step": nwalk,
+                       "note": "oracle port of AIQMCrelease3 (torch CPU, float32/complex64) on a bounded sample of "
+                               "the same workload; JAX is not installable here so the genuine reference cannot run"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                              "sample": f"{nwalk} walkers x {args.steps} steps of the same workload"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -346,7 +349,7 @@ def run_gpu(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_time / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C atom ccECP (N=4, A=1): VMC sweep + ccECP local energy, BASELINE configs[1]",
+            "config": {"workload": WORKLOAD,
                        "walkers_per_gpu": B, "global_walkers": B * world, "tstep": TSTEP, "nsteps_per_step": 1,
                        "params": "random-init (reference init scales)", "parallelism": f"walker-sharded x{world}",
                        "l2": "256 MiB flush write between timed iterations (untimed)",
