@@ -120,7 +120,17 @@ __device__ __forceinline__ void orbital_row(const double* __restrict__ P, const 
 #else
 #define AIQMC_PT_BOUNDS __launch_bounds__((pt_threads<NE, NA, WPC, IFIX>()), AIQMC_PT_MINB)
 #endif
-template <int NE, int NA, int WPC, int IFIX>
+// LAYOUT >= 0: the spin layout is compile-time too: symmetric-feature blocks [0,NUP) / [NUP,N) with NUP = ceil(N/2)
+// and orbital rows either in electron order (LAYOUT 0: spins up-first, sigma = identity) or up-spins-then-down-spins
+// of an alternating spin list (LAYOUT 1: sigma = 0,2,4,..,1,3,5,.. -- the reference's examples, e.g.
+// example/single_atom_C: spins = [1,-1,1,-1]).  The ~650 FSELs per point that pick spin blocks disappear.  The
+// launcher checks the system against these layouts and falls back to LAYOUT = -1 (run-time layout) otherwise.
+template <int NE, int LAYOUT>
+__host__ __device__ constexpr int pt_sigma(int k) {
+  constexpr int NUP = (NE + 1) / 2;
+  return LAYOUT == 0 ? k : (k < NUP ? 2 * k : 2 * (k - NUP) + 1);
+}
+template <int NE, int NA, int WPC, int IFIX, int LAYOUT>
 __global__ void AIQMC_PT_BOUNDS
 k_ecp_pt(AiqmcSystem sys, const double* __restrict__ pos, const double* __restrict__ rot, int64_t B,
          const double* __restrict__ cache_all, EnergyWs w, double* __restrict__ tm_out, double tm_tau) {
@@ -168,8 +178,11 @@ k_ecp_pt(AiqmcSystem sys, const double* __restrict__ pos, const double* __restri
     const double v0 = vl[0], v1 = vl[1], v2 = vl[2], v3 = vl[3];
     double out_re = 0.0, out_im = 0.0;
     if (tm_out || !(v0 == 0.0 && v1 == 0.0 && v2 == 0.0 && v3 == 0.0)) {   // exact zero channel contributes exactly 0
-      const double inv_n[2] = {1.0 / sys.n_up, 1.0 / sys.n_dn};
-      const int si = i < sys.n_up ? 0 : 1;
+      constexpr int NUP = (N + 1) / 2;
+      const int n_up = LAYOUT >= 0 ? NUP : sys.n_up, n_dn = LAYOUT >= 0 ? N - NUP : sys.n_dn;
+      const int n_up_rows = LAYOUT >= 0 ? NUP : sys.n_up_rows;
+      const double inv_n[2] = {1.0 / n_up, 1.0 / n_dn};
+      const int si = i < n_up ? 0 : 1;
       // ---- rotated point and cos(theta)  (quirks Q13, Q14)
       double ae[3], xn[3];
 #pragma unroll
@@ -225,7 +238,7 @@ k_ecp_pt(AiqmcSystem sys, const double* __restrict__ pos, const double* __restri
 #pragma unroll
           for (int k = 0; k < N; ++k) {
             const double v = (k == i) ? 0.0 : cc[k][c];
-            if (k < sys.n_up) su[c] += v; else sd[c] += v;
+            if (k < n_up) su[c] += v; else sd[c] += v;
           }
         }
         double g0u[4 * A], g0d[4 * A], gm[2][4];
@@ -241,7 +254,7 @@ k_ecp_pt(AiqmcSystem sys, const double* __restrict__ pos, const double* __restri
           for (int c = 0; c < 4; ++c) {
             double u = 0.0, d = 0.0;
 #pragma unroll
-            for (int k = 0; k < N; ++k) { if (k < sys.n_up) u += h[k][c]; else d += h[k][c]; }
+            for (int k = 0; k < N; ++k) { if (k < n_up) u += h[k][c]; else d += h[k][c]; }
             gm[0][c] = u * inv_n[0];
             gm[1][c] = d * inv_n[1];
           }
@@ -298,7 +311,7 @@ k_ecp_pt(AiqmcSystem sys, const double* __restrict__ pos, const double* __restri
 #pragma unroll
       for (int k = 0; k < N; ++k) {
         const bool diag = (k == i);
-        const int e = sys.sigma[k];
+        const int e = LAYOUT >= 0 ? pt_sigma<NE, LAYOUT>(k) : sys.sigma[k];
         double hs[4], yr[6];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -310,7 +323,7 @@ k_ecp_pt(AiqmcSystem sys, const double* __restrict__ pos, const double* __restri
 #pragma unroll
         for (int m = 0; m < 6; ++m) yr[m] = diag ? yn[m] : C[MC::Y + k * 6 + m];
         const double envr = diag ? envn : C[MC::ENV + k];
-        if (k < sys.n_up_rows) orbital_row<NE, NA, 0>(P, hs, yr, envr, M[k]);
+        if (k < n_up_rows) orbital_row<NE, NA, 0>(P, hs, yr, envr, M[k]);
         else orbital_row<NE, NA, 1>(P, hs, yr, envr, M[k]);
       }
       const cplx det = det_small<N>(M);

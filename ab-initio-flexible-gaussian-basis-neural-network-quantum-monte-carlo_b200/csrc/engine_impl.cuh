@@ -748,13 +748,32 @@ struct Launch {
     return AIQMC_OK;
   }
 
+  // spin layouts the quadrature kernel is specialised for (ecp_pt.cuh): 0 = up-first, 1 = alternating; -1 = other
+  static int spin_layout(const AiqmcSystem* sys) {
+    constexpr int NUP = (NE + 1) / 2;
+    if (sys->n_up != NUP || sys->n_dn != NE - NUP || sys->n_up_rows != NUP) return -1;
+    bool l0 = true, l1 = true;
+    for (int k = 0; k < NE; ++k) {
+      l0 = l0 && sys->sigma[k] == pt_sigma<NE, 0>(k);
+      l1 = l1 && sys->sigma[k] == pt_sigma<NE, 1>(k);
+    }
+    return l0 ? 0 : (l1 ? 1 : -1);
+  }
+  template <int LAYOUT, int... I>
+  static void launch_pt_layout(const AiqmcSystem* sys, const double* pos, const double* rot, int64_t B,
+                               const EnergyWs& w, double* tm_out, double tm_tau, cudaStream_t st) {
+    constexpr int WPC = AIQMC_PT_WPCI;
+    (k_ecp_pt<NE, NA, WPC, I, LAYOUT><<<(unsigned)((B + WPC - 1) / WPC), pt_threads<NE, NA, WPC, I>(), 0, st>>>(
+         *sys, pos, rot, B, w.cache, w, tm_out, tm_tau), ...);
+  }
   template <int... I>
   static void launch_pt(const AiqmcSystem* sys, const double* pos, const double* rot, int64_t B, const EnergyWs& w,
                         double* tm_out, double tm_tau, cudaStream_t st, std::integer_sequence<int, I...>) {
-    constexpr int WPC = AIQMC_PT_WPCI;
     g_launch_count += sizeof...(I);
-    (k_ecp_pt<NE, NA, WPC, I><<<(unsigned)((B + WPC - 1) / WPC), pt_threads<NE, NA, WPC, I>(), 0, st>>>(
-         *sys, pos, rot, B, w.cache, w, tm_out, tm_tau), ...);
+    const int layout = spin_layout(sys);
+    if (layout == 0) launch_pt_layout<0, I...>(sys, pos, rot, B, w, tm_out, tm_tau, st);
+    else if (layout == 1) launch_pt_layout<1, I...>(sys, pos, rot, B, w, tm_out, tm_tau, st);
+    else launch_pt_layout<-1, I...>(sys, pos, rot, B, w, tm_out, tm_tau, st);
   }
 
   static constexpr bool kReverse = (NE <= 16);   // fused reverse-mode gradient (its per-thread tape is 12 N^2 doubles)
@@ -883,7 +902,7 @@ struct Launch {
 #ifdef AIQMC_PT_SINGLE_LAUNCH
             constexpr int WPC = AIQMC_PT_WPC;
             ++g_launch_count;
-            k_ecp_pt<NE, NA, WPC, -1><<<(unsigned)((B + WPC - 1) / WPC), pt_threads<NE, NA, WPC, -1>(), 0, st>>>(
+            k_ecp_pt<NE, NA, WPC, -1, -1><<<(unsigned)((B + WPC - 1) / WPC), pt_threads<NE, NA, WPC, -1>(), 0, st>>>(
                 *sys, pos, rot, B, w.cache, w, nullptr, 0.0);
 #else
             launch_pt(sys, pos, rot, B, w, nullptr, 0.0, st, std::make_integer_sequence<int, NE>{});   // one launch per moved electron

@@ -29,6 +29,16 @@
 namespace aiqmc {
 
 constexpr int kExpTab = 16;
+#ifdef __CUDACC__
+// 2^(j/16), filled by every kernel prologue.  Device code indexes this array directly (not through the `tab`
+// pointer argument) so the lookup is one LDS with an immediate base instead of generic-pointer arithmetic.
+__shared__ double g_exp_tab[kExpTab];
+#endif
+#ifdef __CUDA_ARCH__
+#define AQF_TAB(tab, j) g_exp_tab[j]
+#else
+#define AQF_TAB(tab, j) (tab)[j]
+#endif
 
 // Polynomial / reduction constants.  On the device they live in constant memory so that each one is a
 // c[3][imm] operand of the DFMA that uses it (as 64-bit literals every use costs two IMAD.MOVs).
@@ -112,7 +122,7 @@ AQF_HD double fexp(double x, const double* __restrict__ tab) {
   q = fma(r, q, 0.5);
   q = fma(r, q, 1.0);
   q = q * r;                                             // exp(r) - 1
-  const double tj = tab[n & (kExpTab - 1)];
+  const double tj = AQF_TAB(tab, n & (kExpTab - 1));
   const double res = fma(tj, q, tj);
   const int k = n >> 4;
 #ifdef __CUDA_ARCH__
@@ -182,7 +192,7 @@ AQF_HD void ftanh_n(const double* __restrict__ x, double* __restrict__ out, cons
 #pragma unroll
 #endif
   for (int i = 0; i < NV; ++i) {
-    const double tj = tab[n[i] & (kExpTab - 1)];
+    const double tj = AQF_TAB(tab, n[i] & (kExpTab - 1));
     int k = n[i] >> 4;
     k = k < -64 ? -64 : k;                                               // e < 2^-64 no longer changes 1 + e
     d[i] = fma(make_double(hi_word(tj) + (k << 20), lo_word(tj)), p[i], 1.0);   // 1 + exp(-2|x|) in (1, 2]

@@ -86,9 +86,9 @@ __device__ __forceinline__ void shell_out(const AiqmcGtoShell& sh, double dx, do
 __global__ void __launch_bounds__(128) k_gto_eval(const double* __restrict__ points, int64_t n, int nao,
                                                   double* __restrict__ val, double* __restrict__ grad,
                                                   double* __restrict__ lap) {
-  __shared__ double tab[kExpTab];
-  if (threadIdx.x < kExpTab) tab[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / kExpTab));
+  if (threadIdx.x < kExpTab) g_exp_tab[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / kExpTab));
   __syncthreads();
+  const double* tab = g_exp_tab;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const double x = points[3 * t], y = points[3 * t + 1], z = points[3 * t + 2];

@@ -160,9 +160,6 @@ template <bool L, int ND> AQ_HD Jet<L, ND> chain(const Jet<L, ND>& u, double f, 
 
 // exp / tanh: in-house fexp/ftanh (fastmath.cuh) unless AIQMC_LIBM is defined.  On the device the
 // 64-entry 2^(j/64) table lives in shared memory (filled by stage_params in every kernel).
-#ifdef __CUDACC__
-__shared__ double g_exp_tab[kExpTab];
-#endif
 AQ_HD const double* exp_tab() {
 #ifdef __CUDA_ARCH__
   return g_exp_tab;
