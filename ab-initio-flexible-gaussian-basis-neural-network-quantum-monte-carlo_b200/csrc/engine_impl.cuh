@@ -698,6 +698,7 @@ static __global__ void k_energy_final(int64_t B, double* __restrict__ e_l, Energ
 }  // namespace aiqmc
 #include "ecp_coop.cuh"
 #include "ecp_pt.cuh"
+#include "ecp_grp.cuh"
 namespace aiqmc {
 
 // ---------------------------------------------------------------------------------------
@@ -716,6 +717,7 @@ template <int NE, int NA>
 struct Launch {
   static constexpr int kSmem = make_layout(NE, NA).total * 8;
   static constexpr bool kCoop = (NE <= 16 && NA <= 4);   // lane-per-electron quadrature kernel available
+  static constexpr bool kGrp = (NE >= 5 && NE <= 32);    // packed lane-per-electron groups (ecp_grp.cuh)
   static constexpr bool kPt = (NE <= 4 && make_layout(NE, NA).total <= kConstParMax);   // thread-per-point kernel
 
   template <class K>
@@ -774,6 +776,27 @@ struct Launch {
     if (layout == 0) launch_pt_layout<0, I...>(sys, pos, rot, B, w, tm_out, tm_tau, st);
     else if (layout == 1) launch_pt_layout<1, I...>(sys, pos, rot, B, w, tm_out, tm_tau, st);
     else launch_pt_layout<-1, I...>(sys, pos, rot, B, w, tm_out, tm_tau, st);
+  }
+
+  // packed-group quadrature / T-move amplitudes: stage the electron-independent weights in constant memory, launch
+  static int launch_grp(const AiqmcSystem* sys, const double* params, const double* pos, const double* rot, int64_t B,
+                        const EnergyWs& w, double* tm_out, double tm_tau, cudaStream_t st) {
+    if constexpr (kGrp) {
+      using U = UniLayout<NE, NA>;
+      using CF = GrpCfg<NE, NA>;
+      for (int l = 0; l < 3; ++l)
+        AQ_CUDA_OK(cudaMemcpyToSymbolAsync(c_uni, params + U::seg_src(l), U::seg_len(l) * sizeof(double),
+                                           U::seg_dst(l) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      AQ_CUDA_OK(cudaMemcpyToSymbolAsync(c_uni, params + U::K.y_w, 6 * NE * sizeof(double), U::y_w * sizeof(double),
+                                         cudaMemcpyDeviceToDevice, st));
+      AQ_CUDA_OK(cudaFuncSetAttribute(k_ecp_grp<NE, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::kBytes));
+      AQ_CUDA_OK(cudaFuncSetAttribute(k_ecp_grp<NE, NA>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+      ++g_launch_count;
+      k_ecp_grp<NE, NA><<<(unsigned)B, CF::T, CF::kBytes, st>>>(*sys, params, pos, rot, B, w.cache, w, tm_out, tm_tau);
+      AQ_CUDA_OK(cudaGetLastError());
+    }
+    return AIQMC_OK;
   }
 
   static constexpr bool kReverse = (NE <= 16);   // fused reverse-mode gradient (its per-thread tape is 12 N^2 doubles)
@@ -910,6 +933,13 @@ struct Launch {
             done = true;
           }
         }
+        if constexpr (kGrp) {
+          if (!done && !(stages & (8 | 16))) {
+            const int rc = launch_grp(sys, params, pos, rot, B, w, nullptr, 0.0, st);
+            if (rc != AIQMC_OK) return rc;
+            done = true;
+          }
+        }
         if constexpr (kCoop) {
           if (!done && !(stages & 8)) {
             const int T = coop_threads<NE, NA>();
@@ -954,6 +984,9 @@ struct Launch {
       AQ_CUDA_OK(cudaMemcpyToSymbolAsync(c_par, params, make_layout(NE, NA).total * sizeof(double), 0,
                                          cudaMemcpyDeviceToDevice, st));
       launch_pt(sys, pos, rot, B, w, tm, tau, st, std::make_integer_sequence<int, NE>{});
+    } else if constexpr (kGrp) {
+      const int rc = launch_grp(sys, params, pos, rot, B, w, tm, tau, st);
+      if (rc != AIQMC_OK) return rc;
     } else {
       AQ_CUDA_OK(prep(k_ecp_quad<NE, NA>));
       const int64_t nt = B * NE * NA * AIQMC_NQUAD;

@@ -226,6 +226,22 @@ def test_cached_quadrature_kernels_match_full_evaluation_kernel(name, rich):
     assert np.array_equal(e_coop, eng.local_energy(torch.tensor(case.pos), rot, stages=7 | 16).cpu().numpy())
 
 
+def test_packed_group_quadrature_benzene_matches_full_evaluation_kernel():
+    """C6H6 (N=30, A=12, BASELINE configs[4]): the packed lane-per-electron kernel (ecp_grp.cuh, one 30-lane group per
+    warp, rows of the 30x30 complex LU in registers) against the plain full-evaluation kernel (stage bit 8)."""
+    ring = lambda r, n: [[r * math.cos(2 * math.pi * k / n), r * math.sin(2 * math.pi * k / n), 0.0] for k in range(n)]
+    case = Case(n=30, natoms=12, spins=[1.] * 15 + [-1.] * 15, seed=21, atoms=ring(2.640, 6) + ring(4.689, 6),
+                charges=[4.0] * 6 + [1.0] * 6, nwalkers=5, width=0.8)
+    tabs = ecp_tables(case.a, rich=True)
+    eng = engine(case, ecp=aiqmc_b200.make_ecp(case.a, list_l=2, **tabs))
+    rot = torch.tensor(O.random_rotations(case.rng, case.B))
+    e_def = eng.local_energy(torch.tensor(case.pos), rot, stages=7).cpu().numpy()
+    e_ref = eng.local_energy(torch.tensor(case.pos), rot, stages=7 | 8).cpu().numpy()
+    assert np.all(np.isfinite(e_ref))
+    np.testing.assert_allclose(e_def, e_ref, rtol=1e-9, atol=1e-9)
+    assert np.array_equal(e_def, eng.local_energy(torch.tensor(case.pos), rot, stages=7).cpu().numpy())
+
+
 @pytest.mark.parametrize("name,rich,tstep,scale", [("C_ecp", False, 0.05, 1.0), ("C_ecp", True, 1.0, -3.0),
                                                    ("N2_ecp", True, 1.0, -3.0), ("h2like", True, 1.0, -5.0)])
 def test_dmc_tmoves_match_oracle(name, rich, tstep, scale):

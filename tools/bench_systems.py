@@ -37,8 +37,11 @@ for name in (sys.argv[1:] or ["N2", "C_ae", "C6H6"]):
     rot = torch.from_numpy(bench.random_rot(rng, B)).cuda() if with_ecp else None
     pos = torch.from_numpy(case.pos.copy()).cuda()
     out = {}
-    for label, f in (("sweep", lambda: eng.vmc_sweep(pos, r["gauss1"], r["gauss2"], r["rnd"], bench.TSTEP, want_accept=False)),
-                     ("energy", lambda: eng.local_energy(pos, rot))):
+    stages = [("sweep", lambda: eng.vmc_sweep(pos, r["gauss1"], r["gauss2"], r["rnd"], bench.TSTEP, want_accept=False)),
+              ("energy", lambda: eng.local_energy(pos, rot))]
+    if with_ecp and os.environ.get("STAGES"):       # energy split: 1 = kinetic + Coulomb + local channel, 2 = quadrature
+        stages += [("e:base", lambda: eng.local_energy(pos, rot, stages=1)), ("e:quad", lambda: eng.local_energy(pos, rot, stages=2))]
+    for label, f in stages:
         t0 = time.time()
         f(); torch.cuda.synchronize()
         first = time.time() - t0
