@@ -60,13 +60,19 @@ struct StaticFor {
   }
 };
 
+#ifndef AIQMC_GRP_ALIGN
+#define AIQMC_GRP_ALIGN 1
+#endif
+#ifndef AIQMC_GRP_MINB
+#define AIQMC_GRP_MINB 3
+#endif
 #ifndef AIQMC_GRP_WARPS
 #define AIQMC_GRP_WARPS 0      // 0 = pick per system
 #endif
 constexpr int grp_pick_warps(int n, int a) {
   if (AIQMC_GRP_WARPS > 0) return AIQMC_GRP_WARPS;
   const int gpw = 32 / n, pw = a * AIQMC_NQUAD;
-  const int wmax = n > 16 ? 8 : 12;
+  const int wmax = 12;
   int best = 8;
   double beff = 0.0;
   for (int w = wmax; w >= 6; --w) {        // best tail efficiency of the per-electron point loop, larger CTAs first
@@ -93,12 +99,13 @@ struct GrpCfg {
     return pc < NG ? NG : pc;
   }
   static constexpr int PC = pc_raw();                      // points per chunk
-  static constexpr int SCR = (9 * NE + 18 + 8 * NA + 4 * NE + 1) & ~1;   // per-group scratch doubles
+  static constexpr int oPIV = (9 * NE + 18 + 8 * NA + 1) & ~1;            // pivot-row buffers inside the group scratch (16 B aligned)
+  static constexpr int SCR = oPIV + 4 * NE;                               // per-group scratch doubles
   // shared-memory carve-up (doubles)
   static constexpr int D0 = 12 * NA + 8, Q0 = 3 * NA + 2;
   static constexpr int oCW0 = 0, oCW1 = oCW0 + D0 * NE, oCW2 = oCW1 + 20 * NE;
   static constexpr int oCB0 = oCW2 + 20 * NE, oCB1 = oCB0 + Q0 * NE, oCB2 = oCB1 + 5 * NE;
-  static constexpr int oOW = oCB2 + 5 * NE;                // orb_w[0] orb_b[0] orb_w[1] orb_b[1]  (20 N)
+  static constexpr int oOW = (oCB2 + 5 * NE + 1) & ~1;              // orb_w[0] orb_b[0] orb_w[1] orb_b[1]  (20 N)
   static constexpr int oGS = oOW + 20 * NE;                // [3][2][N][4]
   static constexpr int oH0T = oGS + 24 * NE;               // [4A][N]
   static constexpr int oG0M = oH0T + 4 * NA * NE;          // [8A]
@@ -159,8 +166,79 @@ __device__ __forceinline__ void grp_one_layer(const double* __restrict__ cw, con
   for (int m = 0; m < 4; ++m) hout[m] = (DIN == 4) ? (in(m) + tz[m]) * kInvSqrt2 : tz[m];   // residual only if shapes match (Q5)
 }
 
+
+// ---- LU across the lanes of a group: the lane holds its row in registers with the CURRENT column in element 0.
+// One step = pivot search (one REDUX on a key that packs the high word of |a|^2 with the lane index), pivot row
+// broadcast through the double-buffered scratch, multiplier, update of the WD-1 trailing elements written one slot
+// to the left (the shift is free), determinant bookkeeping.  lu_run unrolls the steps for N <= 16; beyond that
+// it runs rolled segments of kLuSeg steps at a fixed width (17 % more FMAs at N = 30, but 1 k instead of 4.6 k
+// instructions: the straight-line triangular nest alone was 70 kB of SASS and the kernel stalled on fetch).
+struct LuState {
+  bool used;
+  unsigned unused;
+  int par, ex, parity_buf;
+  cplx prod;
+};
+constexpr int kLuSeg = 6;
+
+template <int NE, int WD>
+__device__ __forceinline__ void lu_step(LuState& st, double (&rre)[NE], double (&rim)[NE], double2* __restrict__ pivb,
+                                        int k, unsigned mask) {
+  const double m2 = rre[0] * rre[0] + rim[0] * rim[0];
+  // [high word of m2 >> 5, + 1][31 - lane]: monotone in m2 (m2 >= 0), ties go to the lowest lane, 0 = finished row
+  const unsigned key = st.used ? 0u : (((((unsigned)hi_word(m2)) >> 5) + 1u) << 5) | (31u - (unsigned)k);
+  const unsigned kmax = __reduce_max_sync(mask, key);
+  const unsigned best = 31u - (kmax & 31u);
+  double2* pb = pivb + st.parity_buf * NE;
+  st.parity_buf ^= 1;
+  if ((unsigned)k == best) {
+    StaticFor<0, WD>::run([&](auto jc) { constexpr int j = decltype(jc)::value; pb[j] = make_double2(rre[j], rim[j]); });
+    st.used = true;
+  }
+  __syncwarp();
+  const double2 pv2 = pb[0];
+  const cplx pv = {pv2.x, pv2.y};
+  st.par ^= __popc(st.unused & ((1u << best) - 1u));       // Lehmer code of the row permutation
+  st.unused &= ~(1u << best);
+  st.prod = cmul(st.prod, pv);
+  {
+    const double mag = fabs(st.prod.re) + fabs(st.prod.im);
+    int e = ((hi_word(mag) >> 20) & 0x7ff) - 1023;
+    e = e < -1000 ? -1000 : (e > 1000 ? 1000 : e);
+    const double sc = make_double((1023 - e) << 20, 0);
+    st.prod.re *= sc; st.prod.im *= sc;
+    st.ex += e;
+  }
+  const double pn = s_inv(pv.re * pv.re + pv.im * pv.im);
+  const cplx pinv = {pv.re * pn, -pv.im * pn};
+  const cplx f = cmul(cplx{rre[0], rim[0]}, pinv);
+  StaticFor<1, WD>::run([&](auto jc) {                      // finished rows compute garbage nobody reads
+    constexpr int j = decltype(jc)::value;
+    const double2 pj = pb[j];
+    rre[j - 1] = fma(f.im, pj.y, fma(-f.re, pj.x, rre[j]));        // 4 DFMA per complex update
+    rim[j - 1] = fma(-f.im, pj.x, fma(-f.re, pj.y, rim[j]));
+  });
+  rre[WD - 1] = 0.0; rim[WD - 1] = 0.0;
+}
+
+template <int NE, int C0>
+__device__ __forceinline__ void lu_run(LuState& st, double (&rre)[NE], double (&rim)[NE], double2* __restrict__ pivb,
+                                       int k, unsigned mask) {
+  if constexpr (C0 < NE) {
+    if constexpr (NE <= 16) {
+      lu_step<NE, NE - C0>(st, rre, rim, pivb, k, mask);
+      lu_run<NE, C0 + 1>(st, rre, rim, pivb, k, mask);
+    } else {
+      constexpr int WD = NE - C0, ST = WD < kLuSeg ? WD : kLuSeg;
+#pragma unroll 1
+      for (int s = 0; s < ST; ++s) lu_step<NE, WD>(st, rre, rim, pivb, k, mask);
+      lu_run<NE, C0 + ST>(st, rre, rim, pivb, k, mask);
+    }
+  }
+}
+
 template <int NE, int NA>
-__global__ void __launch_bounds__((GrpCfg<NE, NA>::T), (NE <= 16 ? 2 : 1))
+__global__ void __launch_bounds__((GrpCfg<NE, NA>::T), (NE <= 16 ? AIQMC_GRP_MINB : 1))
 k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __restrict__ pos,
           const double* __restrict__ rot, int64_t B, const double* __restrict__ cache_all, EnergyWs w,
           double* __restrict__ tm_out, double tm_tau) {
@@ -169,7 +247,8 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
   using U = UniLayout<NE, NA>;
   constexpr int N = NE, A = NA, GPW = CF::GPW, NG = CF::NG, PW = CF::PW, PC = CF::PC, LSTR = CF::LSTR;
   constexpr LayoutC<NE, NA> L{};
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem_grp[];
+  double* const smem = smem_grp;
   const int tid = threadIdx.x;
   const int64_t b = blockIdx.x;
   const double* cache = cache_all + b * MC::SIZE;
@@ -213,7 +292,7 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
   double* red_in = scr;                                    // [N][9]
   double* red_out = scr + 9 * N;                           // [18]: up sums (9), down sums (9)
   double* g0 = red_out + 18;                               // [8A]
-  cplx* pivb = reinterpret_cast<cplx*>(g0 + 8 * A);        // [2][N]
+  double2* pivb = reinterpret_cast<double2*>(scr + CF::oPIV);   // [2][N] (re, im)
   __syncthreads();
   const double xk[3] = {smem[CF::oX + 3 * kk], smem[CF::oX + 3 * kk + 1], smem[CF::oX + 3 * kk + 2]};
   const double den_r = smem[CF::oMISC + 1], den_i = smem[CF::oMISC + 2];
@@ -271,7 +350,14 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
 #pragma unroll 1
       for (int it = 0;; ++it) {
         const int t0 = warp * GPW + it * NG;
+#if AIQMC_GRP_ALIGN
+        // all warps of the CTA walk the (large, straight-line) loop body together so that they share instruction
+        // fetches; warps past the end of the chunk run a dummy pass instead of leaving early
+        if (it * NG >= npt) break;                                      // CTA-uniform
+        __syncthreads();
+#else
         if (t0 >= npt) break;                                           // warp-uniform
+#endif
         const bool valid = t0 + g < npt;
         const int t = valid ? t0 + g : npt - 1;
         const double* Lp = smem + CF::oL + t * LSTR;
@@ -314,8 +400,12 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
             for (int col = k; col < (l == 0 ? kCols : 8); col += N) {
               if (l == 0 && col >= 4 && col < 8) continue;               // no h sums before the first layer
               double u = 0.0, dsum = 0.0;
-              for (int q = 0; q < n_up; ++q) u += red_in[q * 9 + col];
-              for (int q = n_up; q < N; ++q) dsum += red_in[q * 9 + col];
+#pragma unroll
+              for (int q = 0; q < N; ++q) {                               // fixed order: deterministic
+                const double v = red_in[q * 9 + col];
+                u += q < n_up ? v : 0.0;
+                dsum += q < n_up ? 0.0 : v;
+              }
               red_out[col] = u;
               red_out[9 + col] = dsum;
             }
@@ -389,9 +479,11 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
           const double* Bv = Wt + 8 * N;
           StaticFor<0, N>::run([&](auto jc) {
             constexpr int j = decltype(jc)::value;
-            double pre = Bv[2 * j], pim = Bv[2 * j + 1];
+            const double2* W2 = reinterpret_cast<const double2*>(Wt);        // (re, im) pairs: one LDS.128 each
+            const double2 b2 = reinterpret_cast<const double2*>(Bv)[j];
+            double pre = b2.x, pim = b2.y;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { pre += hs[c] * Wt[c * 2 * N + 2 * j]; pim += hs[c] * Wt[c * 2 * N + 2 * j + 1]; }
+            for (int c = 0; c < 4; ++c) { const double2 w2 = W2[c * N + j]; pre += hs[c] * w2.x; pim += hs[c] * w2.y; }
             double yo = 0.0;
 #pragma unroll
             for (int m = 0; m < 6; ++m) yo += yr[m] * c_uni[U::y_w + m * N + j];
@@ -400,45 +492,15 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
           });
         }
 
-        // ---- complex LU across the group's lanes with partial pivoting
-        bool used = !act;
-        unsigned unused = N >= 32 ? 0xffffffffu : ((1u << N) - 1u);
-        int par = 0, ex = 0;
-        cplx prod = {1.0, 0.0};
-        StaticFor<0, N>::run([&](auto cc_) {
-          constexpr int c = decltype(cc_)::value;
-          const double m2 = rre[c] * rre[c] + rim[c] * rim[c];
-          const unsigned key = used ? 0u : (unsigned)hi_word(m2) + 1u;   // exponent + 20 mantissa bits: monotone for m2 >= 0
-          const unsigned kmax = __reduce_max_sync(gmask, key);
-          const unsigned best = __reduce_min_sync(gmask, key == kmax ? (unsigned)k : 255u);
-          cplx* pb = pivb + (c & 1) * N;
-          if ((unsigned)k == best) {
-            StaticFor<c, N>::run([&](auto jc) { constexpr int j = decltype(jc)::value; pb[j] = {rre[j], rim[j]}; });
-            used = true;
-          }
-          __syncwarp();
-          const cplx pv = pb[c];
-          par ^= __popc(unused & ((1u << best) - 1u));
-          unused &= ~(1u << best);
-          prod = cmul(prod, pv);
-          {
-            const double mag = fabs(prod.re) + fabs(prod.im);
-            int e = ((hi_word(mag) >> 20) & 0x7ff) - 1023;
-            e = e < -1000 ? -1000 : (e > 1000 ? 1000 : e);
-            const double sc = make_double((1023 - e) << 20, 0);
-            prod.re *= sc; prod.im *= sc;
-            ex += e;
-          }
-          const double pn = s_inv(pv.re * pv.re + pv.im * pv.im);
-          const cplx pinv = {pv.re * pn, -pv.im * pn};
-          const cplx f = cmul(cplx{rre[c], rim[c]}, pinv);
-          StaticFor<c + 1, N>::run([&](auto jc) {                        // finished rows compute garbage nobody reads
-            constexpr int j = decltype(jc)::value;
-            const cplx pj = pb[j];
-            rre[j] -= f.re * pj.re - f.im * pj.im;
-            rim[j] -= f.re * pj.im + f.im * pj.re;
-          });
-        });
+        // ---- complex LU across the group's lanes with partial pivoting (lu_step / lu_run above)
+        LuState lu;
+        lu.used = !act;
+        lu.unused = N >= 32 ? 0xffffffffu : ((1u << N) - 1u);
+        lu.par = 0; lu.ex = 0; lu.parity_buf = 0;
+        lu.prod = {1.0, 0.0};
+        lu_run<NE, 0>(lu, rre, rim, pivb, k, GPW == 1 ? 0xffffffffu : gmask);
+        int par = lu.par, ex = lu.ex;
+        cplx prod = lu.prod;
         if (valid && act && k == 0) {
           if (par & 1) { prod.re = -prod.re; prod.im = -prod.im; }
           const double la = 0.5 * log(prod.re * prod.re + prod.im * prod.im) + ex * 0.69314718055994530942 +
