@@ -24,7 +24,7 @@ import torch
 
 from . import parallel
 from .engine import WalkerEngine
-from .system import SystemSpec, make_ecp
+from .system import SystemSpec, make_ecp, unpack_param_grad
 
 
 @dataclass
@@ -217,6 +217,86 @@ def total_energy(local_energy_fn, process_group=None):
         mean, variance, _ = parallel.allreduce_energy_stats(stats, process_group)
         return e_l, mean, variance
     return _total
+
+
+# ---- loss: Loss/pploss.py:73-223 ----------------------------------------------
+@dataclass
+class AuxiliaryLossData:
+    """Loss/pploss.py:20-33."""
+    variance: Any
+    local_energy: Any
+    clipped_energy: Any
+    grad_local_energy: Any = None
+    local_energy_mat: Any = None
+
+
+def clip_local_values(local_values: torch.Tensor, mean_local_values, clip_scale: float, clip_from_median: bool,
+                      center_at_clipped_value: bool, complex_output: bool = False, process_group=None):
+    """pploss.py:73-135 on device tensors; the pmean's are all-reduces over `process_group`."""
+    batch_mean = lambda v: parallel.allreduce_mean(torch.mean(v), process_group)
+
+    def clip_at_total_variation(values, center, scale):
+        tv = batch_mean(torch.abs(values - center))
+        return torch.minimum(torch.maximum(values, center - scale * tv), center + scale * tv)
+
+    if clip_from_median:
+        allv = parallel.all_gather_cat(local_values.real.contiguous(), process_group)
+        clip_center = torch.quantile(allv, 0.5, interpolation='midpoint')      # jnp.median
+    else:
+        clip_center = mean_local_values
+    if complex_output:
+        cr = clip_center.real if torch.is_complex(clip_center) else clip_center
+        ci = clip_center.imag if torch.is_complex(clip_center) else torch.zeros_like(cr)
+        clipped = torch.complex(clip_at_total_variation(local_values.real, cr, clip_scale),
+                                clip_at_total_variation(local_values.imag, ci, clip_scale))
+    else:
+        clipped = clip_at_total_variation(local_values, clip_center, clip_scale)
+    diff_center = batch_mean(clipped) if center_at_clipped_value else mean_local_values
+    return diff_center, clipped - diff_center
+
+
+def make_loss(network, local_energy_fn, clip_local_energy: float = 0.0, clip_from_median: bool = True,
+              center_at_clipped_energy: bool = True, complex_output: bool = True, process_group=None):
+    """pploss.py:137-223.  Returns total_energy(params, key, data) -> (loss, AuxiliaryLossData) and, as the stand-in
+    for jax.value_and_grad(total_energy, has_aux=True) through the custom JVP, total_energy.value_and_grad(params,
+    key, data) -> ((loss, aux), grads) with `grads` a pytree shaped like the reference's params, already pmean'ed
+    over `process_group` (Optimizer/adam.py:49-59).  `network` is make_ai_net(...).apply, `local_energy_fn` the
+    closure of aiqmc_b200.local_energy."""
+    def total_energy(params, key, data: AINetData):
+        e_l, e_l_mat = local_energy_fn(params, key, data)
+        eng = local_energy_fn.engine_of(params, data)
+        mean, variance, _ = parallel.allreduce_energy_stats(eng.energy_stats(e_l), process_group)
+        loss = mean if torch.is_complex(e_l) else mean.real
+        return loss, AuxiliaryLossData(variance=variance, local_energy=e_l, clipped_energy=e_l, local_energy_mat=e_l_mat)
+
+    def value_and_grad(params, key, data: AINetData):
+        loss, aux = total_energy(params, key, data)
+        e_l = aux.local_energy
+        if clip_local_energy > 0.0:
+            aux.clipped_energy, diff = clip_local_values(e_l, loss, clip_local_energy, clip_from_median,
+                                                         center_at_clipped_energy, complex_output, process_group)
+        else:
+            diff = e_l - loss
+        eng = _engine_of(network, params, data)
+        B = e_l.shape[0]
+        if complex_output:
+            # (term1 - 2 term2).real / B of pploss.py:208-218 with psi_tangent = d(log|psi| + i phase)
+            ce = aux.clipped_energy if torch.is_complex(aux.clipped_energy) else torch.complex(aux.clipped_energy, torch.zeros_like(aux.clipped_energy))
+            d = diff if torch.is_complex(diff) else torch.complex(diff, torch.zeros_like(diff))
+            ce = ce.expand(B) if ce.ndim == 0 else ce
+            alpha, beta = 2.0 * d.real / B, 2.0 * (d.imag + ce.imag) / B
+            out_loss = loss.real
+        else:
+            alpha, beta = diff.real / B, torch.zeros(B, dtype=torch.float64, device=eng.device)
+            out_loss = loss.real if torch.is_complex(loss) else loss
+        g, _, _ = eng.param_grad(_positions(eng, data), alpha, beta)
+        g = parallel.allreduce_mean(g, process_group)
+        tree = params.tree if isinstance(params, PackedParams) else params
+        grads = unpack_param_grad(eng.layout, g.cpu().numpy(), tree, eng.spec)
+        return (out_loss, aux), grads
+
+    total_energy.value_and_grad = value_and_grad
+    return total_energy
 
 
 # ---- DMC -------------------------------------------------------------------------------

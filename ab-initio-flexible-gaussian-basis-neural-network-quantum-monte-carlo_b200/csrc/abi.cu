@@ -18,6 +18,7 @@ int64_t sweep_ws_bytes_rt(int n, int a, int64_t B);
 int64_t energy_ws_bytes_rt(int n, int a, int64_t B, int with_ecp);
 int64_t psi_ws_bytes_rt(int n, int a, int64_t n_cfg, int with_lap);
 int64_t tmove_ws_bytes_rt(int n, int a, int64_t B);
+int64_t pgrad_ws_bytes_rt(int n, int a, int64_t B);
 }  // namespace aiqmc
 
 #define X(NE, NA) extern "C" const aiqmc::OpsTable* aiqmc_ops_##NE##_##NA();
@@ -265,6 +266,20 @@ int aiqmc_dmc_tmove(const AiqmcSystem* sys, const AiqmcEcp* ecp, const double* p
   if (!ops) return AIQMC_E_UNSUPPORTED;
   return ops->tmove(sys, ecp, params, pos, rot, u, rnd, n_walkers, tstep, pos_out, acceptance, selected, workspace,
                     workspace_bytes, (cudaStream_t)stream);
+}
+int64_t aiqmc_param_grad_workspace_bytes(const AiqmcSystem* sys, int64_t n_walkers) {
+  if (!sys_ok(sys) || n_walkers < 0) return AIQMC_E_BADARG;
+  return aiqmc::pgrad_ws_bytes_rt(sys->n_elec, sys->n_atoms, n_walkers);
+}
+int aiqmc_psi_param_grad(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_walkers,
+                         const double* alpha, const double* beta, double* grad_out, double* phase, double* logabs,
+                         void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!sys_ok(sys) || !params || !grad_out || n_walkers < 0) return AIQMC_E_BADARG;
+  if (n_walkers > 0 && (!pos || !alpha || !beta || !workspace)) return AIQMC_E_BADARG;
+  const aiqmc::OpsTable* ops = find_ops(sys->n_elec, sys->n_atoms);
+  if (!ops) return AIQMC_E_UNSUPPORTED;
+  return ops->param_grad(sys, params, pos, n_walkers, alpha, beta, grad_out, phase, logabs, workspace, workspace_bytes,
+                         (cudaStream_t)stream);
 }
 int aiqmc_local_energy_ecp(const AiqmcSystem* sys, const AiqmcEcp* ecp, const double* params, const double* pos,
                            const double* rot, int64_t n_walkers, double* e_l, void* workspace,

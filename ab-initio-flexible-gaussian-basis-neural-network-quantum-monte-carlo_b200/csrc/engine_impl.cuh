@@ -699,7 +699,66 @@ static __global__ void k_energy_final(int64_t B, double* __restrict__ e_l, Energ
 #include "ecp_coop.cuh"
 #include "ecp_pt.cuh"
 #include "ecp_grp.cuh"
+#include "param_grad.cuh"
 namespace aiqmc {
+
+// ---------------------------------------------------------------------------------------
+// parameter gradient of sum_w (alpha_w log|psi_w| + beta_w phase_w)  (Loss/pploss.py:186-223, param_grad.cuh)
+// One warp per CTA, one walker per lane, grid-stride over the batch; every contribution is reduced across the
+// warp in a fixed order and added to the CTA's shared-memory accumulator by lane 0 (deterministic, no atomics);
+// the per-CTA partials are summed by k_reduce_param_partials.
+// ---------------------------------------------------------------------------------------
+struct WarpSink {
+  double* acc;
+  __device__ __forceinline__ void add(int off, double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) acc[off] += v;
+  }
+};
+constexpr int kPgradMaxBlocks = 148 * 16;
+inline int64_t pgrad_blocks(int64_t B) {
+  const int64_t nb = (B + 31) / 32;
+  return nb < 1 ? 1 : (nb > kPgradMaxBlocks ? kPgradMaxBlocks : nb);
+}
+inline int64_t pgrad_ws_bytes(int n, int a, int64_t B) { return align256(pgrad_blocks(B) * make_layout(n, a).total * 8); }
+
+template <int NE, int NA>
+__global__ void __launch_bounds__(32) k_param_grad(AiqmcSystem sys, const double* __restrict__ params,
+                                                   const double* __restrict__ pos, int64_t B,
+                                                   const double* __restrict__ alpha, const double* __restrict__ beta,
+                                                   double* __restrict__ phase, double* __restrict__ logabs,
+                                                   double* __restrict__ partials) {
+  constexpr int total = make_layout(NE, NA).total;
+  extern __shared__ double sP[];
+  const double* P = stage_params<NE, NA>(params, sP);
+  double* acc = sP + total;
+  for (int q = threadIdx.x; q < total; q += 32) acc[q] = 0.0;
+  __syncwarp();
+  WarpSink sink{acc};
+  for (int64_t b0 = (int64_t)blockIdx.x * 32; b0 < B; b0 += (int64_t)gridDim.x * 32) {
+    const int64_t b = b0 + threadIdx.x;
+    const bool valid = b < B;
+    const int64_t bb = valid ? b : B - 1;                // tail lanes redo the last walker with a zero seed
+    double x[3 * NE];
+    for (int q = 0; q < 3 * NE; ++q) x[q] = pos[bb * 3 * NE + q];
+    double ph, la;
+    ParamGrad<NE, NA>::run(sys, P, x, valid ? alpha[b] : 0.0, valid ? beta[b] : 0.0, ph, la, sink);
+    if (valid && phase) phase[b] = ph;
+    if (valid && logabs) logabs[b] = la;
+  }
+  __syncwarp();
+  for (int q = threadIdx.x; q < total; q += 32) partials[(int64_t)blockIdx.x * total + q] = acc[q];
+}
+
+static __global__ void k_reduce_param_partials(const double* __restrict__ partials, int nblk, int total,
+                                               double* __restrict__ out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= total) return;
+  double s = 0.0;
+  for (int k = 0; k < nblk; ++k) s += partials[(int64_t)k * total + q];      // fixed order
+  out[q] = s;
+}
 
 // ---------------------------------------------------------------------------------------
 // launchers
@@ -1001,6 +1060,30 @@ struct Launch {
     return AIQMC_OK;
   }
 
+
+  static constexpr bool kPgrad = (NE <= 16);   // per-thread tape is 12 N^2 doubles of local memory, as for kReverse
+  static int param_grad(const AiqmcSystem* sys, const double* params, const double* pos, int64_t B, const double* alpha,
+                        const double* beta, double* grad_out, double* phase, double* logabs, void* ws, int64_t ws_bytes,
+                        cudaStream_t st) {
+    if constexpr (kPgrad) {
+      constexpr int total = make_layout(NE, NA).total;
+      if (B <= 0) {
+        AQ_CUDA_OK(cudaMemsetAsync(grad_out, 0, total * sizeof(double), st));
+        return AIQMC_OK;
+      }
+      if (!ws || ws_bytes < pgrad_ws_bytes(NE, NA, B)) return AIQMC_E_WORKSPACE;
+      const int nblk = (int)pgrad_blocks(B);
+      AQ_CUDA_OK(cudaFuncSetAttribute(k_param_grad<NE, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kSmem));
+      g_launch_count += 2;
+      k_param_grad<NE, NA><<<nblk, 32, 2 * kSmem, st>>>(*sys, params, pos, B, alpha, beta, phase, logabs, (double*)ws);
+      k_reduce_param_partials<<<(total + 255) / 256, 256, 0, st>>>((const double*)ws, nblk, total, grad_out);
+      AQ_CUDA_OK(cudaGetLastError());
+      return AIQMC_OK;
+    } else {
+      return AIQMC_E_UNSUPPORTED;
+    }
+  }
+
   static cudaError_t upload_ecp(const AiqmcEcp* ecp, cudaStream_t st) {
     static AiqmcEcp h_ecp;                 // last table uploaded to this TU's __constant__ copy
     static bool h_valid = false;
@@ -1014,7 +1097,7 @@ struct Launch {
   }
 
   static const OpsTable* table() {
-    static const OpsTable t = {NE, NA, &Launch::psi, &Launch::sweep, &Launch::energy, &Launch::tmove};
+    static const OpsTable t = {NE, NA, &Launch::psi, &Launch::sweep, &Launch::energy, &Launch::tmove, &Launch::param_grad};
     return &t;
   }
 };

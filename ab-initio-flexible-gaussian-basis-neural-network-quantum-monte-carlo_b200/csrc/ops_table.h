@@ -16,5 +16,7 @@ struct OpsTable {
                 void*, int64_t, int, cudaStream_t);
   int (*tmove)(const AiqmcSystem*, const AiqmcEcp*, const double*, const double*, const double*, const double*,
                const double*, int64_t, double, double*, double*, int32_t*, void*, int64_t, cudaStream_t);
+  int (*param_grad)(const AiqmcSystem*, const double*, const double*, int64_t, const double*, const double*, double*,
+                    double*, double*, void*, int64_t, cudaStream_t);
 };
 }  // namespace aiqmc

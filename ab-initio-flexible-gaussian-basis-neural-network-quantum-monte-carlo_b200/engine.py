@@ -195,6 +195,27 @@ class WalkerEngine:
                                                      _ptr(out), _stream()), "aiqmc_gather_walkers")
         return out
 
+    def param_grad(self, pos, alpha, beta):
+        """sum_w alpha_w d log|psi_w|/d params + beta_w d phase_w/d params in the PACKED layout (device, (P,)), plus
+        (phase, log|psi|) of every walker.  One reverse sweep per walker (csrc/param_grad.cuh); replaces the
+        jax.jvp(batch_network) of Loss/pploss.py:204 as seen through jax.grad."""
+        p = self._pos(pos).reshape(-1, 3 * self.n)
+        B = p.shape[0]
+        cv = lambda a: torch.as_tensor(a).to(device=self.device, dtype=torch.float64).reshape(B).contiguous()
+        al, be = cv(alpha), cv(beta)
+        nbytes = self.lib.aiqmc_param_grad_workspace_bytes(C.byref(self.sys), B)
+        if nbytes < 0:
+            _lib.check(int(nbytes), "aiqmc_param_grad_workspace_bytes")
+        ws = self._workspace("pgrad", nbytes)
+        g = torch.empty(self.layout.total, dtype=torch.float64, device=self.device)
+        ph = torch.empty(B, dtype=torch.float64, device=self.device)
+        la = torch.empty(B, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.aiqmc_psi_param_grad(C.byref(self.sys), _ptr(self.params_dev), _ptr(p), B, _ptr(al),
+                                                     _ptr(be), _ptr(g), _ptr(ph), _ptr(la), _ptr(ws), ws.numel(),
+                                                     _stream()), "aiqmc_psi_param_grad")
+        return g, ph, la
+
     def dmc_tmove(self, pos: torch.Tensor, rot: torch.Tensor, u: torch.Tensor, rnd: torch.Tensor, tstep: float):
         """DMC/Tmoves.py:32-225 for the whole batch: (new positions (B,3N), acceptance (B,N), selected move (B,N))."""
         if self.ecp is None:

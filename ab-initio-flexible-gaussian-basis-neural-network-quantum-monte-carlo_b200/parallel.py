@@ -49,6 +49,26 @@ def allreduce_energy_stats(stats: torch.Tensor, group=None):
     return mean, variance, cnt
 
 
+def allreduce_mean(x: torch.Tensor, group=None) -> torch.Tensor:
+    """constants.pmean (kfac_jax pmean_if_pmap): mean over the ranks of `group`; identity for a single process."""
+    _, world = _world(group)
+    if world > 1:
+        x = x.clone()
+        dist.all_reduce(x, group=group)
+        x = x / world
+    return x
+
+
+def all_gather_cat(x: torch.Tensor, group=None) -> torch.Tensor:
+    """constants.all_gather flattened: every rank's (B,) shard concatenated (clip_from_median, pploss.py:118)."""
+    _, world = _world(group)
+    if world == 1:
+        return x
+    parts = [torch.empty_like(x) for _ in range(world)]
+    dist.all_gather(parts, x.contiguous(), group=group)
+    return torch.cat(parts)
+
+
 def allreduce_min(x: torch.Tensor, group=None) -> torch.Tensor:
     _, world = _world(group)
     if world > 1:

@@ -157,6 +157,54 @@ def pack_params(layout: AiqmcLayout, params: Mapping[str, Any], spec: SystemSpec
     return buf
 
 
+def unpack_param_grad(layout: AiqmcLayout, gpacked, params: Mapping[str, Any], spec: SystemSpec) -> dict:
+    """Transpose of pack_params: a gradient w.r.t. the packed buffer (aiqmc_psi_param_grad) -> a gradient pytree with
+    the structure of the reference's params (nn.py:203-278,370-407).  The three host-side precomputations of
+    pack_params get their chain rule here: row normalisation of params['y'][0]['w'], sigma * xi of the envelope, the
+    scatter of ee_par / ee_anti into the (N,N) pair table.  Leaves the wavefunction does not use come back as zeros."""
+    n, a = spec.nelectrons, spec.natoms
+    g = _np(gpacked).reshape(-1)
+    if g.size != layout.total:
+        raise ValueError(f"packed gradient has {g.size} elements, expected {layout.total}")
+    take = lambda off, shape: g[off:off + int(np.prod(shape))].reshape(shape).copy()
+    d = [12 * a + 8, 20, 20]
+    ky = [4 * a + 2, 6, 6]
+    streams, streams_y = [], []
+    for l in range(3):
+        lp = {'convolutional': {'w': take(layout.conv_w[l], (n, d[l])), 'b': take(layout.conv_b[l], (n, d[l] // 4))},
+              'single': {'w': take(layout.sing_w[l], (d[l] // 4, 4)), 'b': take(layout.sing_b[l], (4,))}}
+        if l < 2:
+            lp['double'] = {'w': take(layout.dbl_w[l], (4, 4)), 'b': take(layout.dbl_b[l], (4,))}
+        streams.append(lp)
+        streams_y.append({'single_Ynlm': {'w': take(layout.yn_w[l], (ky[l], 6)), 'b': take(layout.yn_b[l], (6,))}})
+    out = {'layers': {'input': {}, 'streams': streams, 'streams_y': streams_y}}
+    out['orbitals'] = [{'w': take(layout.orb_w[s], (4, 2 * n)), 'b': take(layout.orb_b[s], (2 * n,))} for s in range(2)]
+    wy = _np(params['y'][0]['w'])
+    nrm = np.linalg.norm(wy, axis=-1, keepdims=True)
+    what, gy = wy / nrm, take(layout.y_w, (6, n))
+    out['y'] = [{'w': (gy - what * np.sum(what * gy, axis=-1, keepdims=True)) / nrm}]
+    ga = take(layout.jas_alpha, (n, n))
+    ee = {}
+    for idx, leaf in ((spec.parallel_indices, 'ee_par'), (spec.antiparallel_indices, 'ee_anti')):
+        idx = np.asarray(idx).reshape(2, -1)
+        ee[leaf] = ga[idx[0], idx[1]].reshape(_np(params['jastrow_ee'][leaf]).shape)
+    out['jastrow_ee'] = ee
+    out['jastrow_ae'] = {'ae': take(layout.jas_beta, (n, a))}
+    gpi, gsx = take(layout.env_pi, (n, a, 3)), take(layout.env_sx, (n, a, 3))
+    gal, gbe = take(layout.env_alpha, (n,)), take(layout.env_beta, (n, a))
+    env = []
+    for e, pe in enumerate(params['envelope']):
+        sigma, xi = _np(pe['sigma']), _np(pe['xi'])
+        leaf = {'pi': gpi[e], 'sigma': gsx[e] * xi, 'xi': np.sum(gsx[e] * sigma).reshape(xi.shape),
+                'alpha': gal[e].reshape(_np(pe['alpha']).shape), 'beta': gbe[e]}
+        for k in pe:
+            if k not in leaf:
+                leaf[k] = np.zeros_like(_np(pe[k]))
+        env.append(leaf)
+    out['envelope'] = env
+    return out
+
+
 def quadrature_table():
     """pseudopotential.py:181-225: the 50 unrotated points (8-digit literals as written in the
     reference) and their per-point weights, order OA, OB, OC, OD."""

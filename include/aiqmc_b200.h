@@ -181,6 +181,21 @@ int aiqmc_dmc_tmove(const AiqmcSystem* sys, const AiqmcEcp* ecp, const double* p
 int aiqmc_energy_stats(const double* e_l, int32_t e_l_stride, int64_t n_walkers, double* stats,
                        void* stream);
 
+/* ---- parameter side of the loss gradient: replaces the `jax.jvp(batch_network, primals, tangents)`
+ * of make_loss.total_energy_jvp (Loss/pploss.py:186-223) as seen through jax.grad.
+ * grad_out (aiqmc_param_layout(...).total doubles, packed layout) = sum over walkers of
+ *     alpha[w] * d log|psi_w| / d params  +  beta[w] * d phase_w / d params,
+ * one reverse (adjoint) sweep per walker.  With diff = clipped E_L - centre (clip_local_values, pploss.py:73-135):
+ * alpha = 2 Re(diff) / B, beta = 2 (Im(diff) + Im(clipped E_L)) / B reproduces tangents_out of :215-218 for complex
+ * outputs, alpha = diff / B, beta = 0 the real branch (:222).  Entries for quantities pack_params derives on the host
+ * (row-normalised y weights, sigma * xi) are gradients w.r.t. the PACKED values; non-trainable slots are 0.
+ * phase / logabs (n_walkers) may be NULL.  Sums are fixed-order (bit reproducible).  Systems with N > 16 return
+ * AIQMC_E_UNSUPPORTED (per-thread tape size). */
+int64_t aiqmc_param_grad_workspace_bytes(const AiqmcSystem* sys, int64_t n_walkers);
+int aiqmc_psi_param_grad(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_walkers,
+                         const double* alpha, const double* beta, double* grad_out, double* phase, double* logabs,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- DMC: replaces DMC/drift_diffusion.py, S_matrix.py, dmc.py:86-92, branch.py ---------- */
 /* Step 1 of comput_S (S_matrix.py:22-23): min over this device's walkers of
  * min(|E_est - Re E_L[b]|, branchcut[b]) -> ecut_min (device scalar).  The reference takes this

@@ -648,6 +648,85 @@ def total_energy(local_energy_fn):
     return _total
 
 
+def clip_local_values(local_values, mean_local_values, clip_scale, clip_from_median, center_at_clipped_value,
+                      complex_output=False):
+    """Loss/pploss.py:73-135 on one device (pmean / all_gather are identities)."""
+    def clip_at_total_variation(values, center, scale):
+        tv = torch.mean(torch.abs(values - center))
+        return torch.clamp(values, min=center - scale * tv, max=center + scale * tv)
+    if clip_from_median:
+        clip_center = torch.as_tensor(np.median(local_values.real.detach().numpy()))      # jnp.median
+    else:
+        clip_center = mean_local_values
+    if complex_output:
+        ci = clip_center.imag if torch.is_complex(clip_center) else torch.zeros(())
+        clipped = torch.complex(clip_at_total_variation(local_values.real, clip_center.real, clip_scale),
+                                clip_at_total_variation(local_values.imag, ci, clip_scale))
+    else:
+        clipped = clip_at_total_variation(local_values, clip_center, clip_scale)
+    diff_center = torch.mean(clipped) if center_at_clipped_value else mean_local_values
+    return diff_center, clipped - diff_center
+
+
+def make_loss(network_apply, local_energy_fn, clip_local_energy=0.0, clip_from_median=True,
+              center_at_clipped_energy=True, complex_output=True):
+    """Loss/pploss.py:137-223.  total_energy(params, key, data) -> (loss, aux dict); value_and_grad restates what
+    jax.value_and_grad sees through total_energy_jvp: the tangent functional (:204-222) is linear in psi_tangent =
+    J t, so its gradient is autograd of the same expression with psi(params) in place of psi_tangent and the local
+    energies held constant."""
+    def total_energy(params, key, data):
+        e_l, _ = local_energy_fn(params, key, data)
+        loss = e_l.mean()
+        diff = e_l - loss
+        variance = (diff * diff.conj()).mean().real
+        return loss, dict(variance=variance, local_energy=e_l, clipped_energy=e_l)
+
+    def value_and_grad(params, key, data):
+        loss, aux = total_energy(params, key, data)             # (the kinetic term differentiates inside: no no_grad)
+        loss = loss.detach()
+        aux = {k: v.detach() for k, v in aux.items()}
+        if clip_local_energy > 0.0:
+            aux['clipped_energy'], diff = clip_local_values(aux['local_energy'], loss, clip_local_energy,
+                                                            clip_from_median, center_at_clipped_energy, complex_output)
+        else:
+            diff = aux['local_energy'] - loss
+        leaves = []
+        def req(t):
+            if isinstance(t, dict):
+                return {k: req(v) for k, v in t.items()}
+            if isinstance(t, (list, tuple)):
+                return [req(v) for v in t]
+            v = t.clone().requires_grad_(True)
+            leaves.append(v)
+            return v
+        p = req(params)
+        phase, logabs = network_apply(p, data.positions, data.spins[0], data.atoms[0], None)
+        B = data.positions.shape[0]
+        if complex_output:
+            psi = torch.complex(logabs, phase)                      # log_network = mag + 1j * phase
+            clipped_el = diff + aux['clipped_energy']
+            term1 = torch.sum(clipped_el * psi.conj()) + torch.sum(clipped_el.conj() * psi)
+            term2 = torch.sum(aux['clipped_energy'] * psi.real)
+            surrogate = (term1 - 2 * term2).real / B
+            out_loss = loss.real
+        else:
+            surrogate = torch.dot(logabs, diff.real) / B
+            out_loss = loss.real if torch.is_complex(loss) else loss
+        grads = torch.autograd.grad(surrogate, leaves, allow_unused=True)
+        it = iter(grads)
+        def rebuild(t):
+            if isinstance(t, dict):
+                return {k: rebuild(v) for k, v in t.items()}
+            if isinstance(t, (list, tuple)):
+                return [rebuild(v) for v in t]
+            g = next(it)
+            return g if g is not None else torch.zeros_like(t)
+        return (out_loss, aux), rebuild(params)
+
+    total_energy.value_and_grad = value_and_grad
+    return total_energy
+
+
 # --------------------------------------------------------------------------
 # DMC  (DMC/drift_diffusion.py, S_matrix.py, branch.py, dmc.py, main_dmc.py)
 # --------------------------------------------------------------------------

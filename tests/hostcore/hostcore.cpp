@@ -3,6 +3,7 @@
 // product package; the product path is the CUDA library and fails loudly without it.
 #include "../../ab-initio-flexible-gaussian-basis-neural-network-quantum-monte-carlo_b200/csrc/psi_core.cuh"
 #include "../../ab-initio-flexible-gaussian-basis-neural-network-quantum-monte-carlo_b200/csrc/deriv_split.cuh"
+#include "../../ab-initio-flexible-gaussian-basis-neural-network-quantum-monte-carlo_b200/csrc/param_grad.cuh"
 #include "../../ab-initio-flexible-gaussian-basis-neural-network-quantum-monte-carlo_b200/csrc/dispatch.h"
 #include <vector>
 
@@ -54,4 +55,29 @@ extern "C" void hc_fastmath(int which, const double* x, long n, double* out) {
   }
   for (long i = 0; i < n; ++i)
     out[i] = which == 0 ? fexp(x[i], tab) : which == 1 ? ftanh(x[i], tab) : which == 2 ? frcp(x[i]) : frsqrt(x[i]);
+}
+
+// per-walker d(alpha log|psi| + beta phase)/d(packed params) through csrc/param_grad.cuh; out (n, layout.total)
+struct HostSink {
+  double* acc;
+  void add(int off, double v) { acc[off] += v; }
+};
+template <int NE, int NA>
+static void run_pgrad(const AiqmcSystem* sys, const double* P, const double* pos, long n, const double* alpha,
+                      const double* beta, double* out) {
+  const int total = make_layout(NE, NA).total;
+#pragma omp parallel for schedule(dynamic, 4)
+  for (long t = 0; t < n; ++t) {
+    HostSink sink{out + t * total};
+    double ph, la;
+    ParamGrad<NE, NA>::run(*sys, P, pos + t * 3 * NE, alpha[t], beta[t], ph, la, sink);
+  }
+}
+extern "C" int hc_param_grad(const AiqmcSystem* sys, const double* P, const double* pos, long n, const double* alpha,
+                             const double* beta, double* out) {
+#define X(NE, NA) \
+  if (sys->n_elec == NE && sys->n_atoms == NA) { run_pgrad<NE, NA>(sys, P, pos, n, alpha, beta, out); return 0; }
+  AIQMC_FOR_EACH_SYSTEM(X)
+#undef X
+  return -1;
 }

@@ -8,12 +8,12 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "hostcore", "hostcore.cpp")
 LIB = os.path.join(HERE, "hostcore", "libhostcore.so")
-CORE = os.path.join(os.path.dirname(HERE), "ab-initio-flexible-gaussian-basis-neural-network-quantum-monte-carlo_b200",
-                    "csrc", "psi_core.cuh")
+CSRC = os.path.join(os.path.dirname(HERE), "ab-initio-flexible-gaussian-basis-neural-network-quantum-monte-carlo_b200", "csrc")
+CORE = os.path.join(CSRC, "psi_core.cuh")
 
 
 def build(force=False):
-    newest = max(os.path.getmtime(p) for p in (SRC, CORE))
+    newest = max(os.path.getmtime(p) for p in [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))])
     if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
         subprocess.check_call(["g++", "-O2", "-fopenmp", "-std=c++17", "-shared", "-fPIC", "-o", LIB, SRC])
     return LIB
@@ -38,3 +38,16 @@ def host_psi(lib, sys_struct, packed, pos, mode):
                     dptr(logabs), dptr(grad), dptr(lap))
     assert rc == 0, "no host instantiation for this (N, A)"
     return phase, logabs, grad, lap
+
+
+def host_param_grad(lib, sys_struct, packed, pos, alpha, beta):
+    """Per-walker d(alpha log|psi| + beta phase)/d(packed params), shape (ncfg, len(packed))."""
+    n = sys_struct.n_elec
+    pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3 * n)
+    ncfg = pos.shape[0]
+    out = np.zeros((ncfg, packed.size))
+    rc = lib.hc_param_grad(C.byref(sys_struct), dptr(packed), dptr(pos), C.c_long(ncfg),
+                           dptr(np.ascontiguousarray(alpha, dtype=np.float64)),
+                           dptr(np.ascontiguousarray(beta, dtype=np.float64)), dptr(out))
+    assert rc == 0, "no host instantiation for this (N, A)"
+    return out
