@@ -51,6 +51,16 @@ def _worker(rank, world, port, B, out):
         assert np.array_equal(src.numpy(), inds_ref.numpy()[lo:hi])
         np.testing.assert_array_equal(newp.numpy(), p_all.numpy()[inds_ref.numpy()[lo:hi]])
         assert imported == int(((inds_ref[lo:hi] < lo) | (inds_ref[lo:hi] >= hi)).sum())
+        # loss side (pploss.py:73-135 across ranks): pmean'ed clipping statistics, all-gathered median, pmean(grad)
+        g_local = torch.tensor(rng.normal(size=5)) * (rank + 1)
+        np.testing.assert_allclose(parallel.allreduce_mean(g_local).numpy(),
+                                   sum(g_local.numpy() / (rank + 1) * (r + 1) for r in range(world)) / world, rtol=1e-14)
+        assert torch.equal(parallel.all_gather_cat(e.real.contiguous()), e_all.real)
+        for median in (True, False):
+            centre, diff = aiqmc_b200.clip_local_values(e, e_all.mean(), 1.5, median, True, complex_output=True)
+            centre_ref, diff_ref = O.clip_local_values(e_all, e_all.mean(), 1.5, median, True, complex_output=True)
+            np.testing.assert_allclose(complex(centre), complex(centre_ref), rtol=1e-12)
+            np.testing.assert_allclose(diff.numpy(), diff_ref.numpy()[lo:hi], rtol=1e-12, atol=1e-14)
         out[rank] = 1
     finally:
         dist.destroy_process_group()

@@ -35,7 +35,10 @@ ops = {
     "quad": lambda: eng.local_energy(pos, rot, stages=2, out=e_l),
     "quad_coop": lambda: eng.local_energy(pos, rot, stages=2 | 16, out=e_l),
     "final": lambda: eng.local_energy(pos, rot, stages=4, out=e_l),
+    "pgrad": lambda: eng.param_grad(pos, seed_a, seed_b),          # loss-gradient side, not part of a walker step
 }
+seed_a = torch.randn(B, dtype=torch.float64, device="cuda")
+seed_b = torch.randn(B, dtype=torch.float64, device="cuda")
 ops["base"]()          # fills the workspace the quadrature stage reads (v_l tables, move cache)
 tot = 0.0
 for name in args.stages.split(","):
