@@ -144,11 +144,15 @@ AQF_HD void ftanh_n(const double* __restrict__ x, double* __restrict__ out, cons
   const FmK& K = fmk();
   double u[NV], t[NV], r[NV], p[NV], d[NV], y[NV];
   int n[NV];
+  uint32_t sg[NV];               // sign of x, taken first so that x itself is dead once u exists (one register, not two)
 #ifdef __CUDACC__
 #pragma unroll
 #endif
-  for (int i = 0; i < NV; ++i)   // u = -2|x| by integer ops (exponent + 1, sign set); x = 0 gives a harmless |u| <= 2^-1021
-    u[i] = make_double((int32_t)((((uint32_t)hi_word(x[i]) & 0x7fffffffu) + 0x00100000u) | 0x80000000u), lo_word(x[i]));
+  for (int i = 0; i < NV; ++i) { // u = -2|x| by integer ops (exponent + 1, sign set); x = 0 gives a harmless |u| <= 2^-1021
+    const uint32_t hx = (uint32_t)hi_word(x[i]);
+    sg[i] = hx & 0x80000000u;
+    u[i] = make_double((int32_t)(((hx & 0x7fffffffu) + 0x00100000u) | 0x80000000u), lo_word(x[i]));
+  }
 #ifdef __CUDACC__
 #pragma unroll
 #endif
@@ -226,7 +230,7 @@ AQF_HD void ftanh_n(const double* __restrict__ x, double* __restrict__ out, cons
 #endif
   for (int i = 0; i < NV; ++i) {
     const double th = fma(2.0, y[i], -1.0);
-    out[i] = make_double((int32_t)((uint32_t)hi_word(th) | ((uint32_t)hi_word(x[i]) & 0x80000000u)), lo_word(th));
+    out[i] = make_double((int32_t)((uint32_t)hi_word(th) | sg[i]), lo_word(th));
   }
 }
 
