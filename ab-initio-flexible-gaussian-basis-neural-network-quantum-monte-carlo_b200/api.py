@@ -299,6 +299,52 @@ def make_loss(network, local_energy_fn, clip_local_energy: float = 0.0, clip_fro
     return total_energy
 
 
+# ---- all-electron Metropolis-Hastings: AIQMCrelease2/MonteCarloSample/mcstep.py -------------
+def make_mcmc_step(batch_network, batch_per_device: int, steps: int = 10, atoms=None, ndim: int = 3, blocks: int = 1,
+                   process_group=None):
+    """mcstep.py:71-104 -> mcmc_step(params, data, key, width) -> (new_data, pmove).  `batch_network` is the `apply`
+    of make_ai_net; key = dict(noise (steps,B,3N) ~ N(0,1), u (steps,B) ~ U(0,1)) in parity mode (the draws of
+    :49-56 and :28-29) or an int seed; pmove is pmean'ed over `process_group` as at :101."""
+    if ndim != 3 or blocks != 1:
+        raise NotImplementedError("the reference only ever uses ndim=3, blocks=1 (mcstep.py:47)")
+    nsteps = steps * blocks
+
+    def mcmc_step(params, data: AINetData, key, width):
+        eng = _engine_of(batch_network, params, data)
+        pos = _positions(eng, data).clone()
+        B = pos.shape[0]
+        _, la = eng.psi(pos, mode=0)
+        lp = (2.0 * la).contiguous()
+        count = torch.zeros((), dtype=torch.int64, device=eng.device)
+        gen = None
+        if isinstance(key, (int, np.integer)):
+            gen = torch.Generator(device=eng.device)
+            gen.manual_seed(int(key))
+        for s in range(nsteps):
+            if gen is None:
+                noise, u = key['noise'][s], key['u'][s]
+            else:
+                noise = torch.randn((B, 3 * eng.n), dtype=torch.float64, device=eng.device, generator=gen)
+                u = torch.rand((B,), dtype=torch.float64, device=eng.device, generator=gen)
+            eng.mh_step(pos, lp, noise, u, float(width), count)
+        pmove = count.to(torch.float64) / (nsteps * batch_per_device)
+        return replace(data, positions=pos), parallel.allreduce_mean(pmove, process_group)
+    return mcmc_step
+
+
+def update_mcmc_width(t: int, width, adapt_frequency: int, pmove, pmoves: np.ndarray, pmove_max: float = 0.55,
+                      pmove_min: float = 0.5):
+    """mcstep.py:107-124 verbatim semantics (host side)."""
+    t_since = t % adapt_frequency
+    pmoves[t_since] = float(torch.as_tensor(pmove).reshape(-1)[0])
+    if t > 0 and t_since == 0:
+        if np.mean(pmoves) > pmove_max:
+            width = width * 1.1
+        elif np.mean(pmoves) < pmove_min:
+            width = width / 1.1
+    return width, pmoves
+
+
 # ---- DMC -------------------------------------------------------------------------------
 def propose_drift_diffusion(f, tstep: float, ndim: int, nelectrons: int, batch_size: int):
     """DMC/drift_diffusion.py:25-107 -> (new_data, tdamp, grad_eff_old, grad_new_eff_s).

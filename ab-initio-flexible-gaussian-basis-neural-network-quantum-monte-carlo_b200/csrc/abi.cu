@@ -116,6 +116,60 @@ __global__ void k_dmc_weights(double* __restrict__ w, const double* __restrict__
   if (b < B) w[b] = exp(tau * tdamp * (0.5 * sn[b] + 0.5 * so[b])) * w[b];   // dmc.py:91-92
 }
 
+// ---- FermiNet-style all-electron Metropolis-Hastings (AIQMCrelease2/MonteCarloSample/mcstep.py:12-68) ----
+// proposal: 1 thread = (walker, electron): harmonic-mean distance to the nuclei before / after, the move and this
+// electron's part of log q(x1|x2) - log q(x2|x1)  (_harmonic_mean :12-16, _log_prob_gaussian :19-23)
+__global__ void k_mh_propose(int n, int a, const double* __restrict__ atoms, const double* __restrict__ pos,
+                             const double* __restrict__ noise, int64_t B, double stddev, double* __restrict__ x2,
+                             double* __restrict__ dlq) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * n) return;
+  double x[3], y[3];
+  for (int c = 0; c < 3; ++c) x[c] = pos[t * 3 + c];
+  double s1 = 0.0;
+  for (int k = 0; k < a; ++k) {
+    const double d0 = x[0] - atoms[3 * k], d1 = x[1] - atoms[3 * k + 1], d2 = x[2] - atoms[3 * k + 2];
+    s1 += 1.0 / sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+  }
+  const double sig1 = stddev * ((double)a / s1);
+  double sq = 0.0;
+  for (int c = 0; c < 3; ++c) {
+    y[c] = x[c] + sig1 * noise[t * 3 + c];
+    x2[t * 3 + c] = y[c];
+    sq += (y[c] - x[c]) * (y[c] - x[c]);
+  }
+  double s2 = 0.0;
+  for (int k = 0; k < a; ++k) {
+    const double d0 = y[0] - atoms[3 * k], d1 = y[1] - atoms[3 * k + 1], d2 = y[2] - atoms[3 * k + 2];
+    s2 += 1.0 / sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+  }
+  const double sig2 = stddev * ((double)a / s2);
+  const double lq1 = -0.5 * sq / (sig1 * sig1) - 3.0 * log(sig1);     // log q(x1 | x2 centre, sigma(x1))  (:61)
+  const double lq2 = -0.5 * sq / (sig2 * sig2) - 3.0 * log(sig2);     // log q(x2 | x1 centre, sigma(x2))  (:62)
+  dlq[t] = lq2 - lq1;
+}
+// accept (mh_accept :26-34): 1 thread = walker; ratio = lp_2 + lq_2 - lp_1 - lq_1 > log(u)
+__global__ void k_mh_accept(int n, double* __restrict__ pos, const double* __restrict__ x2, double* __restrict__ lp,
+                            const double* __restrict__ logabs2, const double* __restrict__ dlq,
+                            const double* __restrict__ u, int64_t B, uint8_t* __restrict__ accept,
+                            unsigned long long* __restrict__ num_accepts) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool ok = false;
+  if (b < B) {
+    double d = 0.0;
+    for (int e = 0; e < n; ++e) d += dlq[b * n + e];               // fixed order
+    const double lp2 = 2.0 * logabs2[b];
+    ok = (lp2 + d - lp[b]) > log(u[b]);
+    if (ok) {
+      for (int q = 0; q < 3 * n; ++q) pos[b * 3 * n + q] = x2[b * 3 * n + q];
+      lp[b] = lp2;
+    }
+    if (accept) accept[b] = ok ? 1 : 0;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, ok);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(num_accepts, (unsigned long long)__popc(m));   // integer: order-independent
+}
+
 // inclusive cumsum by one CTA: per-thread contiguous chunks + scan of chunk totals
 __global__ void __launch_bounds__(kBig) k_cumsum(const double* __restrict__ w, int64_t B, double* __restrict__ cum) {
   __shared__ double tot[kBig];
@@ -323,6 +377,36 @@ int aiqmc_dmc_weights(double* weights, const double* s_old, const double* s_new,
   ++g_launch_count;
   k_dmc_weights<<<(unsigned)((n_walkers + 255) / 256), 256, 0, (cudaStream_t)stream>>>(weights, s_old, s_new,
                                                                                        n_walkers, tau, tdamp);
+  AQ_CUDA_OK(cudaGetLastError());
+  return AIQMC_OK;
+}
+
+int64_t aiqmc_mh_workspace_bytes(const AiqmcSystem* sys, int64_t n_walkers) {
+  if (!sys_ok(sys) || n_walkers < 0) return AIQMC_E_BADARG;
+  return (n_walkers * 3 * sys->n_elec + n_walkers * sys->n_elec + 2 * n_walkers + 64) * 8;
+}
+int aiqmc_mh_step(const AiqmcSystem* sys, const double* params, double* pos, double* lp, const double* noise,
+                  const double* u, int64_t n_walkers, double stddev, uint8_t* accept, uint64_t* num_accepts,
+                  void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!sys_ok(sys) || !params || n_walkers < 0 || !(stddev > 0.0) || !num_accepts) return AIQMC_E_BADARG;
+  if (n_walkers == 0) return AIQMC_OK;
+  if (!pos || !lp || !noise || !u || !workspace) return AIQMC_E_BADARG;
+  if (workspace_bytes < aiqmc_mh_workspace_bytes(sys, n_walkers)) return AIQMC_E_WORKSPACE;
+  const int n = sys->n_elec, a = sys->n_atoms;
+  const int64_t B = n_walkers;
+  double* x2 = (double*)workspace;
+  double* dlq = x2 + B * 3 * n;
+  double* la2 = dlq + B * n;
+  double* ph2 = la2 + B;
+  const AiqmcLayout lay = aiqmc::make_layout(n, a);
+  cudaStream_t st = (cudaStream_t)stream;
+  ++g_launch_count;
+  k_mh_propose<<<(unsigned)((B * n + 255) / 256), 256, 0, st>>>(n, a, params + lay.atoms, pos, noise, B, stddev, x2, dlq);
+  const int rc = aiqmc_psi_fwd(sys, params, x2, B, ph2, la2, stream);
+  if (rc != AIQMC_OK) return rc;
+  ++g_launch_count;
+  k_mh_accept<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(n, pos, x2, lp, la2, dlq, u, B, accept,
+                                                           (unsigned long long*)num_accepts);
   AQ_CUDA_OK(cudaGetLastError());
   return AIQMC_OK;
 }

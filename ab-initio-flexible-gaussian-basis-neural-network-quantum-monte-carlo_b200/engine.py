@@ -216,6 +216,21 @@ class WalkerEngine:
                                                      _stream()), "aiqmc_psi_param_grad")
         return g, ph, la
 
+    def mh_step(self, pos: torch.Tensor, lp: torch.Tensor, noise, u, stddev: float, num_accepts: torch.Tensor,
+                want_accept: bool = False):
+        """One all-electron Metropolis-Hastings move (MonteCarloSample/mcstep.py:37-68), in place on pos (B,3N) and
+        lp (B) = 2 log|psi|; num_accepts: device int64 scalar, incremented.  Returns the accept mask if asked."""
+        B = pos.shape[0]
+        cv = lambda a, shape: torch.as_tensor(a).to(device=self.device, dtype=torch.float64).reshape(shape).contiguous()
+        nz, uu = cv(noise, (B, 3 * self.n)), cv(u, (B,))
+        ws = self._workspace("mh", self.lib.aiqmc_mh_workspace_bytes(C.byref(self.sys), B))
+        acc = torch.empty(B, dtype=torch.uint8, device=self.device) if want_accept else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.aiqmc_mh_step(C.byref(self.sys), _ptr(self.params_dev), _ptr(pos), _ptr(lp), _ptr(nz),
+                                              _ptr(uu), B, float(stddev), _ptr(acc) if acc is not None else None,
+                                              _ptr(num_accepts), _ptr(ws), ws.numel(), _stream()), "aiqmc_mh_step")
+        return acc
+
     def dmc_tmove(self, pos: torch.Tensor, rot: torch.Tensor, u: torch.Tensor, rnd: torch.Tensor, tstep: float):
         """DMC/Tmoves.py:32-225 for the whole batch: (new positions (B,3N), acceptance (B,N), selected move (B,N))."""
         if self.ecp is None:

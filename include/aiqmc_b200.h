@@ -196,6 +196,18 @@ int aiqmc_psi_param_grad(const AiqmcSystem* sys, const double* params, const dou
                          const double* alpha, const double* beta, double* grad_out, double* phase, double* logabs,
                          void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- all-electron Metropolis-Hastings: replaces mh_update / mh_accept of
+ * AIQMCrelease2/MonteCarloSample/mcstep.py:26-68 (= ferminet/mcmc.py:67-150), one all-electron move per call:
+ * x2 = x1 + stddev * hmean(x1) * noise with hmean the per-electron harmonic mean distance to the nuclei (:12-16),
+ * ratio = 2 log|psi(x2)| + log q(x1|x2) - lp - log q(x2|x1) (:59-63), accepted where ratio > log(u) (:29-30).
+ * pos (B,3N) and lp (B) = 2 log|psi(pos)| are updated in place; noise (B,3N) ~ N(0,1) and u (B) ~ U(0,1) are the two
+ * draws of :49-56,:28-29 (parity mode inputs); *num_accepts (device uint64) is incremented by the number of accepted
+ * walkers; accept (B) uint8 may be NULL.  The caller loops `steps` times and adapts the width (update_mcmc_width). */
+int64_t aiqmc_mh_workspace_bytes(const AiqmcSystem* sys, int64_t n_walkers);
+int aiqmc_mh_step(const AiqmcSystem* sys, const double* params, double* pos, double* lp, const double* noise,
+                  const double* u, int64_t n_walkers, double stddev, uint8_t* accept, uint64_t* num_accepts,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- DMC: replaces DMC/drift_diffusion.py, S_matrix.py, dmc.py:86-92, branch.py ---------- */
 /* Step 1 of comput_S (S_matrix.py:22-23): min over this device's walkers of
  * min(|E_est - Re E_L[b]|, branchcut[b]) -> ecut_min (device scalar).  The reference takes this

@@ -728,6 +728,67 @@ def make_loss(network_apply, local_energy_fn, clip_local_energy=0.0, clip_from_m
 
 
 # --------------------------------------------------------------------------
+# all-electron Metropolis-Hastings (AIQMCrelease2/MonteCarloSample/mcstep.py:12-124 = ferminet/mcmc.py:67-150)
+# --------------------------------------------------------------------------
+def _harmonic_mean(x, atoms):
+    """mcstep.py:12-16; x (B,N,1,3), atoms (A,3) -> (B,N,1,1)."""
+    ae = x - atoms[None, ...]
+    r_ae = torch.linalg.norm(ae, dim=-1, keepdim=True)
+    return 1.0 / torch.mean(1.0 / r_ae, dim=-2, keepdim=True)
+
+
+def _log_prob_gaussian(x, mu, sigma):
+    """mcstep.py:19-23."""
+    numer = torch.sum(-0.5 * ((x - mu) ** 2) / (sigma ** 2), dim=[1, 2, 3])
+    denom = x.shape[-1] * torch.sum(torch.log(sigma), dim=[1, 2, 3])
+    return numer - denom
+
+
+def mh_update(params, f, data: AINetData, rand, lp_1, num_accepts, stddev=0.02, atoms=None, ndim=3):
+    """mcstep.py:37-68 with the two draws explicit: rand = dict(noise (B,N,1,3), u (B,))."""
+    x1 = data.positions
+    n = x1.shape[0]
+    x1 = x1.reshape(n, -1, 1, ndim)
+    hmean1 = _harmonic_mean(x1, atoms)
+    x2 = x1 + stddev * hmean1 * rand['noise'].reshape(x1.shape)
+    lp_2 = 2.0 * f(params, x2.reshape(n, -1), data.spins, data.atoms, data.charges)
+    hmean2 = _harmonic_mean(x2, atoms)
+    lq_1 = _log_prob_gaussian(x1, x2, stddev * hmean1)
+    lq_2 = _log_prob_gaussian(x2, x1, stddev * hmean2)
+    ratio = lp_2 + lq_2 - lp_1 - lq_1
+    cond = ratio > torch.log(rand['u'])                                    # mh_accept :26-34
+    x_new = torch.where(cond[..., None], x2.reshape(n, -1), x1.reshape(n, -1))
+    lp_new = torch.where(cond, lp_2, lp_1)
+    return replace(data, positions=x_new), lp_new, num_accepts + cond.sum(), cond
+
+
+def make_mcmc_step(batch_network, batch_per_device, steps=10, atoms=None, ndim=3, blocks=1):
+    """mcstep.py:71-104; rand = dict(noise (steps,B,3N), u (steps,B))."""
+    def mcmc_step(params, data: AINetData, rand, width):
+        lp = 2.0 * batch_network(params, data.positions, data.spins, data.atoms, data.charges)
+        acc = torch.zeros((), dtype=torch.float64)
+        masks = []
+        for s in range(steps * blocks):
+            data, lp, acc, cond = mh_update(params, batch_network, data, dict(noise=rand['noise'][s], u=rand['u'][s]), lp,
+                                            acc, stddev=width, atoms=atoms, ndim=ndim)
+            masks.append(cond)
+        return data, acc / (steps * blocks * batch_per_device), torch.stack(masks), lp
+    return mcmc_step
+
+
+def update_mcmc_width(t, width, adapt_frequency, pmove, pmoves, pmove_max=0.55, pmove_min=0.5):
+    """mcstep.py:107-124."""
+    t_since = t % adapt_frequency
+    pmoves[t_since] = float(pmove)
+    if t > 0 and t_since == 0:
+        if np.mean(pmoves) > pmove_max:
+            width *= 1.1
+        elif np.mean(pmoves) < pmove_min:
+            width /= 1.1
+    return width, pmoves
+
+
+# --------------------------------------------------------------------------
 # DMC  (DMC/drift_diffusion.py, S_matrix.py, branch.py, dmc.py, main_dmc.py)
 # --------------------------------------------------------------------------
 def propose_drift_diffusion(logabs_f, tstep, ndim, nelectrons, batch_size):
