@@ -345,6 +345,90 @@ def update_mcmc_width(t: int, width, adapt_frequency: int, pmove, pmoves: np.nda
     return width, pmoves
 
 
+# ---- correlated sampling (correlatedsamples/*.py) and the ccECP file reader ------------------
+def _corr_call(fn_name, atoms, new_atoms, pos, out_cols):
+    from . import lib as _lib
+    from .engine import _ptr, _stream
+    import ctypes as C
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise _lib.AiqmcError("correlated sampling needs a CUDA device (no CPU fallback)")
+    at = np.ascontiguousarray(np.asarray(atoms, dtype=np.float64).reshape(-1, 3))
+    nat = np.ascontiguousarray(np.asarray(new_atoms, dtype=np.float64).reshape(-1, 3))
+    if at.shape != nat.shape:
+        raise ValueError("atoms and new_atoms must have the same shape")
+    p = torch.as_tensor(pos).to(device="cuda", dtype=torch.float64)
+    lead = p.shape[:-1]
+    p2 = p.reshape(-1, p.shape[-1]).contiguous()
+    B, n = p2.shape[0], p2.shape[1] // 3
+    out = torch.empty((B, 3 * n) if out_cols else (B,), dtype=torch.float64, device="cuda")
+    rc = getattr(lib, fn_name)(at.ctypes.data_as(C.c_void_p), nat.ctypes.data_as(C.c_void_p), at.shape[0], _ptr(p2), B, n,
+                               _ptr(out), _stream())
+    _lib.check(rc, fn_name)
+    return out.reshape(*lead, 3 * n) if out_cols else out.reshape(lead)
+
+
+def correlated_samples(atoms, new_atoms, pos):
+    """corrsamples.py:23-47, natively batched: pos (..., 3N) -> space-warped positions for the displaced nuclei."""
+    return _corr_call("aiqmc_correlated_samples", atoms, new_atoms, pos, True)
+
+
+def weights_jacobian(pos, atoms, new_atoms):
+    """jacobianWeights.py:22-51, natively batched: pos (..., 3N) -> the reference's Jacobian weight per walker."""
+    return _corr_call("aiqmc_weights_jacobian", atoms, new_atoms, pos, False)
+
+
+def read_ecp_nwchem(text: str, symbols: Sequence[str], n_channels: int = 3, n_gauss: int = 2) -> Dict[str, np.ndarray]:
+    """What pseudopotential/readpp.py:1-47 set out to do (it stops half way): an NWChem-format ccECP block
+    (`X nelec k`, `X ul` + rows `n exponent coefficient`, then `X S`, `X P`, ...) -> the tables the reference
+    hard-codes (example/single_atom_C/single_atom_C.py:13-23): Rn_local / Local_exps / Local_coes (A, K_loc) and
+    Rn_non_local / Non_local_exps / Non_local_coes (A, n_channels, n_gauss) zero padded, one row per atom of `symbols`,
+    plus nelec_core (A,) and list_l = n_channels - 1.  Keys follow aiqmc_b200.make_ecp / local_energy."""
+    blocks: Dict[str, Dict[str, list]] = {}
+    core: Dict[str, int] = {}
+    elem, chan = None, None
+    for raw in text.splitlines():
+        tok = raw.split('#')[0].split()
+        if not tok or tok[0].upper() in ("ECP", "END"):
+            continue
+        if len(tok) == 3 and tok[1].lower() == "nelec":
+            core[tok[0]] = int(tok[2])
+        elif len(tok) == 2 and not tok[0][0].isdigit():
+            elem, chan = tok[0], tok[1].lower()
+            blocks.setdefault(elem, {})[chan] = []
+        elif len(tok) == 3 and elem is not None:
+            blocks[elem][chan].append((float(tok[0]), float(tok[1]), float(tok[2])))
+        else:
+            raise ValueError(f"cannot parse ECP line: {raw!r}")
+    order = ["s", "p", "d", "f", "g"][:n_channels]
+    for sname in symbols:
+        if sname not in blocks or "ul" not in blocks[sname]:
+            raise ValueError(f"no ECP block for element {sname}")
+    k_loc = max(len(blocks[s]["ul"]) for s in symbols)
+    A = len(symbols)
+    out = {"rn_local": np.zeros((A, k_loc)), "local_exps": np.zeros((A, k_loc)), "local_coes": np.zeros((A, k_loc)),
+           "rn_non_local": np.zeros((A, n_channels, n_gauss)), "non_local_exps": np.zeros((A, n_channels, n_gauss)),
+           "non_local_coes": np.zeros((A, n_channels, n_gauss)), "nelec_core": np.zeros(A, dtype=np.int64),
+           "list_l": n_channels - 1}
+    out["rn_non_local"][:] = 2.0          # padding convention of the reference's tables (single_atom_C.py:15)
+    for ia, s in enumerate(symbols):
+        if s not in blocks or "ul" not in blocks[s]:
+            raise ValueError(f"no ECP block for element {s}")
+        out["nelec_core"][ia] = core.get(s, 0)
+        for k, (nn, ex, co) in enumerate(blocks[s]["ul"]):
+            out["rn_local"][ia, k], out["local_exps"][ia, k], out["local_coes"][ia, k] = nn, ex, co
+        for l, name in enumerate(order):
+            rows = blocks[s].get(name, [])
+            if len(rows) > n_gauss:
+                raise ValueError(f"{s} {name.upper()} channel has {len(rows)} gaussians, table holds {n_gauss}")
+            for k, (nn, ex, co) in enumerate(rows):
+                out["rn_non_local"][ia, l, k], out["non_local_exps"][ia, l, k], out["non_local_coes"][ia, l, k] = nn, ex, co
+        extra = [c for c in blocks[s] if c != "ul" and c not in order]
+        if extra:
+            raise ValueError(f"{s}: channels {extra} do not fit n_channels={n_channels}")
+    return out
+
+
 # ---- DMC -------------------------------------------------------------------------------
 def propose_drift_diffusion(f, tstep: float, ndim: int, nelectrons: int, batch_size: int):
     """DMC/drift_diffusion.py:25-107 -> (new_data, tdamp, grad_eff_old, grad_new_eff_s).

@@ -170,6 +170,53 @@ __global__ void k_mh_accept(int n, double* __restrict__ pos, const double* __res
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(num_accepts, (unsigned long long)__popc(m));   // integer: order-independent
 }
 
+// ---- correlated sampling under a nuclear displacement: correlatedsamples/corrsamples.py:23-47,
+//      jacobianWeights.py:22-51.  Atom tables travel by value (<= AIQMC_MAX_ATOMS atoms).
+struct AtomPair { double old_[AIQMC_MAX_ATOMS * 3]; double new_[AIQMC_MAX_ATOMS * 3]; };
+// space-warp move: x_i += sum_a w_ia (R'_a - R_a), w_ia = r_ia^-4 / sum_b r_ib^-4; 1 thread = (walker, electron)
+__global__ void k_space_warp(AtomPair at, int a, const double* __restrict__ pos, int64_t ne_total,
+                             double* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ne_total) return;
+  const double x0 = pos[3 * t], x1 = pos[3 * t + 1], x2 = pos[3 * t + 2];
+  double den = 0.0, m0 = 0.0, m1 = 0.0, m2 = 0.0;
+  for (int k = 0; k < a; ++k) {
+    const double d0 = x0 - at.old_[3 * k], d1 = x1 - at.old_[3 * k + 1], d2 = x2 - at.old_[3 * k + 2];
+    const double r2 = d0 * d0 + d1 * d1 + d2 * d2;
+    const double w = 1.0 / (r2 * r2);
+    den += w;
+    m0 += w * (at.new_[3 * k] - at.old_[3 * k]);
+    m1 += w * (at.new_[3 * k + 1] - at.old_[3 * k + 1]);
+    m2 += w * (at.new_[3 * k + 2] - at.old_[3 * k + 2]);
+  }
+  out[3 * t] = x0 + m0 / den;
+  out[3 * t + 1] = x1 + m1 / den;
+  out[3 * t + 2] = x2 + m2 / den;
+}
+// the reference's Jacobian weight, as written (jacobianWeights.py:30-50): per direction d and electron i
+//   T1 = sum_a -4 |ae_iad|^-5 (1 - R_ad),  T3 = sum_a dR_a0 * (-4 |ae_iad|^-5 (1 - R_ad)) / T1 + 1   (dR_a0 for ALL d)
+// and jacobian = prod_i T3x T3y T3z; 1 thread = walker
+__global__ void k_warp_jacobian(AtomPair at, int a, int n, const double* __restrict__ pos, int64_t B,
+                                double* __restrict__ jac) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double prod = 1.0;
+  for (int i = 0; i < n; ++i) {
+    double e = 1.0;
+    for (int d = 0; d < 3; ++d) {
+      const double x = pos[(b * n + i) * 3 + d];
+      double t1 = 0.0;
+      for (int k = 0; k < a; ++k) t1 += -4.0 * pow(fabs(x - at.old_[3 * k + d]), -5.0) * (1.0 - at.old_[3 * k + d]);
+      double t3 = 0.0;
+      for (int k = 0; k < a; ++k)
+        t3 += (at.new_[3 * k] - at.old_[3 * k]) * (-4.0 * pow(fabs(x - at.old_[3 * k + d]), -5.0) * (1.0 - at.old_[3 * k + d])) / t1;
+      e *= t3 + 1.0;
+    }
+    prod *= e;
+  }
+  jac[b] = prod;
+}
+
 // inclusive cumsum by one CTA: per-thread contiguous chunks + scan of chunk totals
 __global__ void __launch_bounds__(kBig) k_cumsum(const double* __restrict__ w, int64_t B, double* __restrict__ cum) {
   __shared__ double tot[kBig];
@@ -407,6 +454,38 @@ int aiqmc_mh_step(const AiqmcSystem* sys, const double* params, double* pos, dou
   ++g_launch_count;
   k_mh_accept<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(n, pos, x2, lp, la2, dlq, u, B, accept,
                                                            (unsigned long long*)num_accepts);
+  AQ_CUDA_OK(cudaGetLastError());
+  return AIQMC_OK;
+}
+
+static bool fill_atoms(AtomPair& at, const double* atoms, const double* new_atoms, int a) {
+  if (!atoms || !new_atoms || a < 1 || a > AIQMC_MAX_ATOMS) return false;
+  memset(&at, 0, sizeof(at));
+  memcpy(at.old_, atoms, sizeof(double) * 3 * a);
+  memcpy(at.new_, new_atoms, sizeof(double) * 3 * a);
+  return true;
+}
+int aiqmc_correlated_samples(const double* atoms, const double* new_atoms, int32_t n_atoms, const double* pos,
+                             int64_t n_walkers, int32_t n_elec, double* pos_out, void* stream) {
+  AtomPair at;
+  if (!fill_atoms(at, atoms, new_atoms, n_atoms) || n_walkers < 0 || n_elec < 1) return AIQMC_E_BADARG;
+  if (n_walkers == 0) return AIQMC_OK;
+  if (!pos || !pos_out) return AIQMC_E_BADARG;
+  const int64_t ne = n_walkers * n_elec;
+  ++g_launch_count;
+  k_space_warp<<<(unsigned)((ne + 255) / 256), 256, 0, (cudaStream_t)stream>>>(at, n_atoms, pos, ne, pos_out);
+  AQ_CUDA_OK(cudaGetLastError());
+  return AIQMC_OK;
+}
+int aiqmc_weights_jacobian(const double* atoms, const double* new_atoms, int32_t n_atoms, const double* pos,
+                           int64_t n_walkers, int32_t n_elec, double* jacobian, void* stream) {
+  AtomPair at;
+  if (!fill_atoms(at, atoms, new_atoms, n_atoms) || n_walkers < 0 || n_elec < 1) return AIQMC_E_BADARG;
+  if (n_walkers == 0) return AIQMC_OK;
+  if (!pos || !jacobian) return AIQMC_E_BADARG;
+  ++g_launch_count;
+  k_warp_jacobian<<<(unsigned)((n_walkers + 255) / 256), 256, 0, (cudaStream_t)stream>>>(at, n_atoms, n_elec, pos,
+                                                                                       n_walkers, jacobian);
   AQ_CUDA_OK(cudaGetLastError());
   return AIQMC_OK;
 }

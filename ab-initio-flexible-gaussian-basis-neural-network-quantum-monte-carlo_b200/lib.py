@@ -21,7 +21,8 @@ EXPORTS = ["aiqmc_param_layout", "aiqmc_supported", "aiqmc_last_cuda_error", "ai
            "aiqmc_energy_workspace_bytes", "aiqmc_local_energy_ae", "aiqmc_local_energy_ecp", "aiqmc_local_energy_ecp_stages", "aiqmc_energy_stats",
            "aiqmc_dmc_tmove_workspace_bytes", "aiqmc_dmc_tmove", "aiqmc_dmc_ecut_min", "aiqmc_dmc_s", "aiqmc_dmc_weights", "aiqmc_branch_workspace_bytes",
            "aiqmc_branch_comb", "aiqmc_gather_walkers", "aiqmc_bench_dfma", "aiqmc_gto_eval", "aiqmc_param_grad_workspace_bytes",
-           "aiqmc_psi_param_grad", "aiqmc_mh_workspace_bytes", "aiqmc_mh_step"]
+           "aiqmc_psi_param_grad", "aiqmc_mh_workspace_bytes", "aiqmc_mh_step", "aiqmc_correlated_samples",
+           "aiqmc_weights_jacobian"]
 
 _lib = None
 
@@ -63,6 +64,8 @@ def load() -> C.CDLL:
         "aiqmc_psi_param_grad": (C.c_int, [sysp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp]),
         "aiqmc_mh_workspace_bytes": (i64, [sysp, i64]),
         "aiqmc_mh_step": (C.c_int, [sysp, vp, vp, vp, vp, vp, i64, f64, vp, vp, vp, i64, vp]),
+        "aiqmc_correlated_samples": (C.c_int, [vp, vp, i32, vp, i64, i32, vp, vp]),
+        "aiqmc_weights_jacobian": (C.c_int, [vp, vp, i32, vp, i64, i32, vp, vp]),
         "aiqmc_gto_eval": (C.c_int, [vp, i32, vp, i32, vp, i64, i32, vp, vp, vp, vp]),
         "aiqmc_bench_dfma": (C.c_int, [i64, vp, C.POINTER(C.c_double), vp]),
         "aiqmc_energy_stats": (C.c_int, [vp, i32, i64, vp, vp]),

@@ -59,6 +59,50 @@ def build_case(nwalkers, seed=SEED):
     return case, ecp_tables(1)
 
 
+OTHER_SYSTEMS = {   # the other BASELINE.json systems, reported next to the headline as "other_workloads" (not the metric)
+    "N2 ccECP (N=10, A=2), BASELINE configs[2]": dict(n=10, natoms=2, spins=[1.] * 5 + [-1.] * 5,
+                                                       atoms=[[0, 0, -1.034], [0, 0, 1.034]], charges=[5.0, 5.0], B=8192),
+    "C6H6 ccECP (N=30, A=12), BASELINE configs[4]": dict(
+        n=30, natoms=12, spins=[1.] * 15 + [-1.] * 15,
+        atoms=[[r * math.cos(2 * math.pi * k / 6), r * math.sin(2 * math.pi * k / 6), 0.0] for r in (2.640, 4.689) for k in range(6)],
+        charges=[4.0] * 6 + [1.0] * 6, B=296),
+}
+
+
+def time_other_systems(reps=2):
+    """One walker step (sweep + ccECP local energy) of the other named systems at a modest batch, CUDA events on the
+    current stream; a few seconds in total.  walker-steps/s and the same fixed algorithmic-flop rate as the headline."""
+    import aiqmc_b200
+    from common import Case, ecp_tables
+    out = {}
+    for name, spec in OTHER_SYSTEMS.items():
+        spec = dict(spec)
+        B = spec.pop("B")
+        case = Case(seed=SEED, nwalkers=B, width=1.0, **spec)
+        case.params = case.net.init(np.random.default_rng(1), randomize_all=False)
+        eng = aiqmc_b200.WalkerEngine(case.spec(), case.params, ecp=aiqmc_b200.make_ecp(case.a, list_l=2, **ecp_tables(case.a)))
+        rng = np.random.default_rng(5)
+        r = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in make_rand(rng, B, case.n, TSTEP).items()}
+        rot = torch.from_numpy(random_rot(rng, B)).cuda()
+        pos = torch.from_numpy(case.pos.copy()).cuda()
+
+        def one():
+            eng.vmc_sweep(pos, r["gauss1"], r["gauss2"], r["rnd"], TSTEP, want_accept=False)
+            eng.local_energy(pos, rot)
+        one()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(); one(); a1.record(); torch.cuda.synchronize()
+            ts.append(a0.elapsed_time(a1))
+        ms = float(np.median(ts))
+        out[name] = {"walkers": B, "ms_per_step": ms, "walker_steps_per_s": B / ms * 1e3,
+                     "algorithmic_tflops": B / ms * 1e3 * flops_walker_step_ecp(case.n, case.a) / 1e12}
+        del eng
+    return out
+
+
 def make_rand(rng, B, n, tstep):
     return dict(gauss1=(rng.standard_normal((B, 3 * n)) * math.sqrt(tstep)),
                 gauss2=(rng.standard_normal((B, n, 3 * n)) * math.sqrt(tstep)),
@@ -346,6 +390,13 @@ def run_gpu(args):
         cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"{args.cpu_walkers} walkers x 2 steps (oracle port, torch CPU float32, {sps:.2f} s/step)"}
 
+    other = None
+    if world == 1 and not args.no_other_systems:
+        try:
+            other = time_other_systems()
+        except Exception as exc:                      # never lose the headline line to the side measurement
+            other = {"error": repr(exc)}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_time / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -356,7 +407,8 @@ def run_gpu(args):
                        "rng": "per-step gauss/uniform/rotation arrays pre-generated (parity-mode inputs)"},
             "clocks": clocks, "gpu_launches": gpu_launches,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": t_wall, "energy_mean_last_step": e_mean}
+            "roofline": roofline, "cpu_baseline": cpu, "other_workloads": other, "wall_s_timed_region": t_wall,
+            "energy_mean_last_step": e_mean}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -371,6 +423,7 @@ def main():
     ap.add_argument("--walkers", type=int, default=WALKERS_PER_GPU, help="walkers per GPU")
     ap.add_argument("--cpu-walkers", type=int, default=256, help="walkers in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-systems", action="store_true", help="skip the N2 / C6H6 side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

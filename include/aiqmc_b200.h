@@ -208,6 +208,17 @@ int aiqmc_mh_step(const AiqmcSystem* sys, const double* params, double* pos, dou
                   const double* u, int64_t n_walkers, double stddev, uint8_t* accept, uint64_t* num_accepts,
                   void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- correlated sampling under a nuclear displacement -------------------------
+ * aiqmc_correlated_samples replaces correlated_samples (correlatedsamples/corrsamples.py:23-47): the space-warp
+ * move x_i += sum_a w_ia (R'_a - R_a), w_ia = r_ia^-4 / sum_b r_ib^-4, for every electron of every walker.
+ * aiqmc_weights_jacobian replaces weights_jacobian (correlatedsamples/jacobianWeights.py:22-51) as written there
+ * (including the use of the x displacement for all three directions): jacobian (B).
+ * atoms / new_atoms: HOST arrays (n_atoms,3); pos, pos_out, jacobian: device. */
+int aiqmc_correlated_samples(const double* atoms, const double* new_atoms, int32_t n_atoms, const double* pos,
+                             int64_t n_walkers, int32_t n_elec, double* pos_out, void* stream);
+int aiqmc_weights_jacobian(const double* atoms, const double* new_atoms, int32_t n_atoms, const double* pos,
+                           int64_t n_walkers, int32_t n_elec, double* jacobian, void* stream);
+
 /* ---- DMC: replaces DMC/drift_diffusion.py, S_matrix.py, dmc.py:86-92, branch.py ---------- */
 /* Step 1 of comput_S (S_matrix.py:22-23): min over this device's walkers of
  * min(|E_est - Re E_L[b]|, branchcut[b]) -> ecut_min (device scalar).  The reference takes this

@@ -789,6 +789,34 @@ def update_mcmc_width(t, width, adapt_frequency, pmove, pmoves, pmove_max=0.55, 
 
 
 # --------------------------------------------------------------------------
+# correlated sampling (correlatedsamples/corrsamples.py:23-47, jacobianWeights.py:22-51), one walker at a time
+# --------------------------------------------------------------------------
+def correlated_samples(atoms, new_atoms, pos):
+    deltaR = new_atoms - atoms
+    ae, ee, r_ae, r_ee = construct_input_features(pos, atoms, ndim=3)
+    k_r_R = 1 / (r_ae ** 4)                                                       # (N,A,1)
+    denominator = torch.sum(torch.sum(k_r_R, dim=-1), dim=-1, keepdim=True)     # (N,1)
+    output = k_r_R / denominator[:, None, :]                                      # vmap(devided)
+    move = torch.sum(output * deltaR[None, :, :], dim=1)                          # vmap(multiply), sum over atoms
+    return pos + move.reshape(-1)
+
+
+def weights_jacobian(pos, atoms, new_atoms):
+    ae, ee, r_ae, r_ee = construct_input_features(pos, atoms, ndim=3)
+    deltaR = new_atoms - atoms
+
+    def jacobian_element(ae_inner, atoms_inner):
+        temp1 = torch.sum(-4 * torch.abs(ae_inner) ** (-5) * (1 - atoms_inner), dim=-1, keepdim=True)
+        temp2 = deltaR[:, 0] * (-4 * torch.abs(ae_inner) ** (-5) * (1 - atoms_inner))
+        return torch.sum(temp2 / temp1, dim=-1, keepdim=True) + 1
+
+    x = jacobian_element(ae[:, :, 0], atoms[:, 0])
+    y = jacobian_element(ae[:, :, 1], atoms[:, 1])
+    z = jacobian_element(ae[:, :, 2], atoms[:, 2])
+    return torch.prod(x * y * z)
+
+
+# --------------------------------------------------------------------------
 # DMC  (DMC/drift_diffusion.py, S_matrix.py, branch.py, dmc.py, main_dmc.py)
 # --------------------------------------------------------------------------
 def propose_drift_diffusion(logabs_f, tstep, ndim, nelectrons, batch_size):
