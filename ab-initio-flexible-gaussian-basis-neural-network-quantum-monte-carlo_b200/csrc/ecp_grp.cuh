@@ -502,25 +502,36 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
         int par = lu.par, ex = lu.ex;
         cplx prod = lu.prod;
         if (valid && act && k == 0) {
-          if (par & 1) { prod.re = -prod.re; prod.im = -prod.im; }
-          const double la = 0.5 * log(prod.re * prod.re + prod.im * prod.im) + ex * 0.69314718055994530942 +
-                            smem[CF::oMISC + 0] + (jee_tot - smem[CF::oJEE + i]) + (Lp[9] - smem[CF::oJAE + i]);
-          const double pha = atan2(prod.im, prod.re);
-          // ratio = log psi(x') / log psi(x) * weight with complex logs (quirk Q12)
-          const int e = c0 + t, a = e / AIQMC_NQUAD, p = e - a * AIQMC_NQUAD;
-          const double wq = c_ecp.quad_wts[p] * den_inv;
-          const double rr = (la * den_r + pha * den_i) * wq, ri = (pha * den_r - la * den_i) * wq;
-          const double v0 = Lp[4], v1 = Lp[5], v2 = Lp[6], v3 = Lp[7], cs = Lp[3];
-          const double k4 = 0.07957747154594767;   // 1/(4 pi)
-          const double f = v0 * k4 + v1 * (3.0 * k4 * cs) + v2 * (2.5 * k4 * (3.0 * cs * cs - 1.0)) +
-                           v3 * (3.5 * k4 * (5.0 * cs * cs * cs - 3.0 * cs));
-          smem[CF::oACC + 2 * t] = f * rr;
-          smem[CF::oACC + 2 * t + 1] = f * ri;
-          if (tm_out) tmove_point_out(tm_out + (((b * N + i) * A + a) * AIQMC_NQUAD + p) * 4, v0, v1, v2, v3, cs, rr, ri, tm_tau);
+          // leave the determinant (mantissa product, exponent, parity) and the Jastrow change in the point's record;
+          // the log / atan2 / quadrature weight are applied by the thread-per-point epilogue below (one lane per
+          // point instead of a whole warp walking through libm for GPW results)
+          double* Lw = smem + CF::oL + t * LSTR;
+          Lw[0] = (par & 1) ? -prod.re : prod.re;
+          Lw[1] = (par & 1) ? -prod.im : prod.im;
+          Lw[2] = (double)ex;
+          Lw[10] = (jee_tot - smem[CF::oJEE + i]) + (Lp[9] - smem[CF::oJAE + i]);
         }
         __syncwarp();
       }
       __syncthreads();
+      // ---- epilogue: thread per point -- log|det|, phase, the ratio of complex logs (quirk Q12), angular weights
+      for (int t = tid; t < npt; t += CF::T) {
+        const double* Lp = smem + CF::oL + t * LSTR;
+        const double pr = Lp[0], pi = Lp[1];
+        const double la = 0.5 * log(pr * pr + pi * pi) + Lp[2] * 0.69314718055994530942 + smem[CF::oMISC + 0] + Lp[10];
+        const double pha = atan2(pi, pr);
+        const int e = c0 + t, a = e / AIQMC_NQUAD, p = e - a * AIQMC_NQUAD;
+        const double wq = c_ecp.quad_wts[p] * den_inv;
+        const double rr = (la * den_r + pha * den_i) * wq, ri = (pha * den_r - la * den_i) * wq;
+        const double v0 = Lp[4], v1 = Lp[5], v2 = Lp[6], v3 = Lp[7], cs = Lp[3];
+        const double k4 = 0.07957747154594767;   // 1/(4 pi)
+        const double f = v0 * k4 + v1 * (3.0 * k4 * cs) + v2 * (2.5 * k4 * (3.0 * cs * cs - 1.0)) +
+                         v3 * (3.5 * k4 * (5.0 * cs * cs * cs - 3.0 * cs));
+        smem[CF::oACC + 2 * t] = f * rr;
+        smem[CF::oACC + 2 * t + 1] = f * ri;
+        if (tm_out) tmove_point_out(tm_out + (((b * N + i) * A + a) * AIQMC_NQUAD + p) * 4, v0, v1, v2, v3, cs, rr, ri, tm_tau);
+      }
+      __syncthreads();                                   // the records are rewritten by the next chunk's phase 0
       if (warp == 0 && !tm_out)
         for (int q = lane; q < npt; q += 32) { acc_re += smem[CF::oACC + 2 * q]; acc_im += smem[CF::oACC + 2 * q + 1]; }
     }

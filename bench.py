@@ -321,21 +321,40 @@ def run_gpu(args):
     h2d = sum(v.numel() * v.element_size() for v in host_sets[0].values()) + pos_host.numel() * 8
     d2h = pos_host.numel() * 8 + 32
 
-    def e2e_step(s):
-        p = pos_host.to(dev, non_blocking=True)
-        sd = {k: v.to(dev, non_blocking=True) for k, v in s.items()}
-        st = step(p, sd)
-        pos_host.copy_(p, non_blocking=True)
-        stats_host.copy_(st, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    # Every step copies its inputs host -> device and its results device -> host inside the timed region.  The
+    # walker positions make a round trip through host memory each step (they serialise the steps); the step's random
+    # arrays (38 of the 44.5 MB) do not depend on the previous step, so their copy for step k+1 is issued on a second
+    # stream while step k computes (CUDA streams + events, pinned buffers) -- the same bytes, overlapped.
+    copy_stream = torch.cuda.Stream(device=dev)
 
-    for w in range(min(args.warmup, 3)):
-        e2e_step(host_sets[w])
+    def prefetch(s):
+        with torch.cuda.stream(copy_stream):
+            sd = {k: v.to(dev, non_blocking=True) for k, v in s.items()}
+            done = torch.cuda.Event()
+            done.record(copy_stream)
+        return sd, done
+
+    def e2e_run(sets):
+        nxt = prefetch(sets[0])
+        for k in range(len(sets)):
+            sd, done = nxt
+            if k + 1 < len(sets):
+                nxt = prefetch(sets[k + 1])
+            cur = torch.cuda.current_stream()
+            cur.wait_event(done)
+            for v in sd.values():
+                v.record_stream(cur)
+            p = pos_host.to(dev, non_blocking=True)
+            st = step(p, sd)
+            pos_host.copy_(p, non_blocking=True)
+            stats_host.copy_(st, non_blocking=True)
+            cur.synchronize()                               # the host reads positions + statistics of this step
+
+    e2e_run(host_sets[:min(args.warmup, 3)])
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for k in range(args.steps):
-        e2e_step(host_sets[args.warmup + k])
+    e2e_run(host_sets[args.warmup:args.warmup + args.steps])
     ev1.record()
     barrier()
     t_e2e = torch.tensor([ev0.elapsed_time(ev1) / 1e3], dtype=torch.float64, device=dev)
