@@ -100,6 +100,57 @@ def time_other_systems(reps=2):
         out[name] = {"walkers": B, "ms_per_step": ms, "walker_steps_per_s": B / ms * 1e3,
                      "algorithmic_tflops": B / ms * 1e3 * flops_walker_step_ecp(case.n, case.a) / 1e12}
         del eng
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(); fn(); a1.record(); torch.cuda.synchronize()
+            ts.append(a0.elapsed_time(a1))
+        return float(np.median(ts))
+
+    # configs[0]: carbon all-electron, 4096 walkers (sweep + all-electron local energy)
+    B = 4096
+    case = Case(n=6, natoms=1, spins=[1.] * 3 + [-1.] * 3, seed=SEED, atoms=[[0., 0., 0.]], charges=[6.0], nwalkers=B, width=1.0)
+    case.params = case.net.init(np.random.default_rng(1), randomize_all=False)
+    eng = aiqmc_b200.WalkerEngine(case.spec(), case.params)
+    rng = np.random.default_rng(5)
+    r = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in make_rand(rng, B, case.n, TSTEP).items()}
+    pos = torch.from_numpy(case.pos.copy()).cuda()
+    ms = timed(lambda: (eng.vmc_sweep(pos, r["gauss1"], r["gauss2"], r["rnd"], TSTEP, want_accept=False), eng.local_energy(pos)))
+    out["C all-electron (N=6, A=1), BASELINE configs[0]"] = {
+        "walkers": B, "ms_per_step": ms, "walker_steps_per_s": B / ms * 1e3,
+        "algorithmic_tflops": B / ms * 1e3 * (6 * case.n + 5) * flops_psi(case.n, case.a) / 1e12}
+
+    # configs[3]: carbon ccECP fixed-node DMC -- one dmc_propagate_run (T-move, drift-diffusion, two local energies,
+    # S, weights) + the comb and gather of branch / reconfigure, per walker; A_DMC = (150NA + 9N + 11) F
+    B = 65536
+    case, tabs = build_case(B)
+    net = aiqmc_b200.make_ai_net(**case.kw)
+    run = aiqmc_b200.dmc_propagate(net.apply, net.apply, TSTEP, case.n, 1, 3, B, case.charges, **tabs)
+    packed = net.pack(case.params, torch.tensor(case.atoms))
+    eng = packed.engine
+    rng = np.random.default_rng(6)
+    cu = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    key = dict(tmove=dict(rot=cu(random_rot(rng, B)), u=cu(rng.uniform(size=B)), rnd=cu(rng.uniform(size=(B, case.n)))),
+               sweep={k: cu(v) for k, v in make_rand(rng, B, case.n, TSTEP).items()}, rot=cu(random_rot(rng, B)))
+    data = aiqmc_b200.AINetData(positions=cu(case.pos), spins=torch.tensor(case.spins), atoms=torch.tensor(case.atoms),
+                                charges=torch.tensor(case.charges))
+    weights = torch.ones(B, dtype=torch.float64, device="cuda")
+    branchcut = torch.full((B,), 3.0, dtype=torch.float64, device="cuda")
+    noise = torch.zeros((B, 3 * case.n), dtype=torch.float64, device="cuda")
+
+    def dmc_step():
+        e_new, w, new_data = run(packed, key, data, weights, branchcut, -5.39, -5.41)
+        neww, inds = aiqmc_b200.branch(eng, w, 0.37)
+        aiqmc_b200.reconfigure(eng, new_data.positions, inds, noise)
+    ms = timed(dmc_step)
+    n_, a_ = case.n, case.a
+    out["C ccECP fixed-node DMC step + branch (N=4, A=1), BASELINE configs[3]"] = {
+        "walkers": B, "ms_per_step": ms, "walker_steps_per_s": B / ms * 1e3,
+        "algorithmic_tflops": B / ms * 1e3 * (150 * n_ * a_ + 9 * n_ + 11) * flops_psi(n_, a_) / 1e12}
     return out
 
 
