@@ -140,14 +140,33 @@ k_ecp_pt(AiqmcSystem sys, const double* __restrict__ pos, const double* __restri
   constexpr LayoutC<NE, NA> L{};
   constexpr int kCachePad = (MC::SIZE + 1) & ~1;
   constexpr int kWalk = 3 * N + 9 + 4 + 2;                 // positions, rotation, group norms, denominator
-  __shared__ double sC[WPC][kCachePad];
+  __shared__ __align__(16) double sC[WPC][kCachePad];
   __shared__ double sX[WPC][(kWalk + 1) & ~1];
   __shared__ double sAcc[WPC][E][2];
   const int tid = threadIdx.x;
   const int64_t b0 = (int64_t)blockIdx.x * WPC;
-  for (int q = tid; q < WPC * MC::SIZE; q += blockDim.x) {
-    const int wl = q / MC::SIZE, o = q - wl * MC::SIZE;
-    if (b0 + wl < B) sC[wl][o] = cache_all[(b0 + wl) * MC::SIZE + o];
+  // The CTA's WPC MoveCaches are one contiguous block of HBM (array-of-structs, consecutive walkers): when the
+  // record size keeps 16-byte alignment it is staged by ONE TMA bulk copy (cp.async.bulk, SASS UBLKCP) signalled on an
+  // mbarrier, issued by thread 0 while the other threads load positions / rotations / norms; otherwise by a loop.
+  constexpr bool kBulk = (MC::SIZE % 2 == 0) && (kCachePad == MC::SIZE);
+  __shared__ __align__(8) unsigned long long sBar;
+  if (kBulk) {
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&sBar);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      const int64_t nw = (B - b0 < WPC) ? (B - b0) : WPC;
+      const unsigned bytes = (unsigned)(nw * MC::SIZE * sizeof(double));
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(&sC[0][0]);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst), "l"(cache_all + b0 * MC::SIZE), "r"(bytes), "r"(bar) : "memory");
+    }
+  } else {
+    for (int q = tid; q < WPC * MC::SIZE; q += blockDim.x) {
+      const int wl = q / MC::SIZE, o = q - wl * MC::SIZE;
+      if (b0 + wl < B) sC[wl][o] = cache_all[(b0 + wl) * MC::SIZE + o];
+    }
   }
   for (int q = tid; q < WPC * kWalk; q += blockDim.x) {
     const int wl = q / kWalk, o = q - wl * kWalk;
@@ -162,7 +181,19 @@ k_ecp_pt(AiqmcSystem sys, const double* __restrict__ pos, const double* __restri
     }
   }
   if (tid < kExpTab) g_exp_tab[tid] = exp2((double)tid * (1.0 / kExpTab));
-  __syncthreads();
+  __syncthreads();                       // also publishes the mbarrier initialisation to the waiting threads
+  if (kBulk) {
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&sBar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "AQ_WAIT_CACHE:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra AQ_CACHE_READY;\n"
+        "bra AQ_WAIT_CACHE;\n"
+        "AQ_CACHE_READY:\n"
+        "}\n" ::"r"(bar) : "memory");
+  }
 
   const double* P = c_par;
   const int wl = tid / E;
