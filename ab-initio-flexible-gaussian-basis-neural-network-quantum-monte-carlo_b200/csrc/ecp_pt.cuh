@@ -138,19 +138,17 @@ k_ecp_pt(AiqmcSystem sys, const double* __restrict__ pos, const double* __restri
   constexpr int E = pt_points<NE, NA, WPC, IFIX>();
   using MC = MoveCache<NE, NA>;
   constexpr LayoutC<NE, NA> L{};
-  constexpr int kCachePad = (MC::SIZE + 1) & ~1;
-  constexpr int kWalk = 3 * N + 9 + 4 + 2;                 // positions, rotation, group norms, denominator
-  __shared__ __align__(16) double sC[WPC][kCachePad];
-  __shared__ double sX[WPC][(kWalk + 1) & ~1];
+  static_assert(MC::SIZE % 2 == 0, "MoveCache records must keep 16-byte alignment");
+  __shared__ __align__(16) double sC[WPC][MC::SIZE];
   __shared__ double sAcc[WPC][E][2];
+  __shared__ __align__(8) unsigned long long sBar;
   const int tid = threadIdx.x;
   const int64_t b0 = (int64_t)blockIdx.x * WPC;
-  // The CTA's WPC MoveCaches are one contiguous block of HBM (array-of-structs, consecutive walkers): when the
-  // record size keeps 16-byte alignment it is staged by ONE TMA bulk copy (cp.async.bulk, SASS UBLKCP) signalled on an
-  // mbarrier, issued by thread 0 while the other threads load positions / rotations / norms; otherwise by a loop.
-  constexpr bool kBulk = (MC::SIZE % 2 == 0) && (kCachePad == MC::SIZE);
-  __shared__ __align__(8) unsigned long long sBar;
-  if (kBulk) {
+  // The CTA's WPC MoveCache records -- network intermediates AND the walker's positions / rotation / norms /
+  // denominator / v_l tables (MoveCache::QR) -- are one contiguous, 16-byte aligned block of HBM (array-of-structs,
+  // consecutive walkers): it is staged by ONE TMA bulk copy (cp.async.bulk, SASS UBLKCP) signalled on an mbarrier;
+  // no thread issues a global load in this kernel.
+  {
     const unsigned bar = (unsigned)__cvta_generic_to_shared(&sBar);
     if (tid == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
@@ -162,28 +160,8 @@ k_ecp_pt(AiqmcSystem sys, const double* __restrict__ pos, const double* __restri
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                    ::"r"(dst), "l"(cache_all + b0 * MC::SIZE), "r"(bytes), "r"(bar) : "memory");
     }
-  } else {
-    for (int q = tid; q < WPC * MC::SIZE; q += blockDim.x) {
-      const int wl = q / MC::SIZE, o = q - wl * MC::SIZE;
-      if (b0 + wl < B) sC[wl][o] = cache_all[(b0 + wl) * MC::SIZE + o];
-    }
-  }
-  for (int q = tid; q < WPC * kWalk; q += blockDim.x) {
-    const int wl = q / kWalk, o = q - wl * kWalk;
-    const int64_t b = b0 + wl;
-    if (b < B) {
-      double v;
-      if (o < 3 * N) v = pos[b * 3 * N + o];
-      else if (o < 3 * N + 9) v = rot[b * 9 + (o - 3 * N)];
-      else if (o < 3 * N + 13) v = w.gnorm[4 * b + (o - 3 * N - 9)];
-      else v = (o == 3 * N + 13) ? w.logabs[b] : w.phase[b];
-      sX[wl][o] = v;
-    }
-  }
-  if (tid < kExpTab) g_exp_tab[tid] = exp2((double)tid * (1.0 / kExpTab));
-  __syncthreads();                       // also publishes the mbarrier initialisation to the waiting threads
-  if (kBulk) {
-    const unsigned bar = (unsigned)__cvta_generic_to_shared(&sBar);
+    if (tid < kExpTab) g_exp_tab[tid] = exp2((double)tid * (1.0 / kExpTab));
+    __syncthreads();                     // publishes the mbarrier initialisation to the waiting threads
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -201,11 +179,11 @@ k_ecp_pt(AiqmcSystem sys, const double* __restrict__ pos, const double* __restri
   const int64_t b = b0 + wl;
   if (wl < WPC && b < B) {
     const double* C = sC[wl];
-    const double* X = sX[wl];
+    const double* X = C + MC::QR;
     const int i = IFIX >= 0 ? IFIX : ev / (A * AIQMC_NQUAD);
     const int a = (IFIX >= 0 ? ev : ev - i * A * AIQMC_NQUAD) / AIQMC_NQUAD;
     const int p = (IFIX >= 0 ? ev : ev - i * A * AIQMC_NQUAD) - a * AIQMC_NQUAD;
-    const double* vl = w.vl + ((b * N + i) * A + a) * 4;
+    const double* vl = C + MC::QR_VL + (i * A + a) * 4;
     const double v0 = vl[0], v1 = vl[1], v2 = vl[2], v3 = vl[3];
     double out_re = 0.0, out_im = 0.0;
     if (tm_out || !(v0 == 0.0 && v1 == 0.0 && v2 == 0.0 && v3 == 0.0)) {   // exact zero channel contributes exactly 0
@@ -388,7 +366,11 @@ k_ecp_pt(AiqmcSystem sys, const double* __restrict__ pos, const double* __restri
     }
     if (lane == 0) {
       if (IFIX <= 0) { w.epp[2 * (b0 + wv)] = sr; w.epp[2 * (b0 + wv) + 1] = si2; }
-      else { w.epp[2 * (b0 + wv)] += sr; w.epp[2 * (b0 + wv) + 1] += si2; }     // launches are stream-ordered: fixed order
+      else {   // one add per walker per launch, launches stream-ordered: the sum order is fixed; RED (no return value)
+               // lets the CTA retire without waiting for a load of the accumulator
+        atomicAdd(&w.epp[2 * (b0 + wv)], sr);
+        atomicAdd(&w.epp[2 * (b0 + wv) + 1], si2);
+      }
     }
   }
 }

@@ -379,7 +379,9 @@ struct EnergyWs {
   double* dcache;    // (DerivCache::SIZE_LAP, B) structure-of-arrays derivative cache
 };
 
-inline int64_t move_cache_doubles(int n, int a) { return 12 * n * n + 24 * n + 4 * a * n + 8 * a + 9 * n + 4; }
+inline int64_t move_cache_doubles(int n, int a) {     // == MoveCache<n, a>::SIZE (psi_core.cuh)
+  return (12 * n * n + 24 * n + 4 * a * n + 8 * a + 9 * n + 4 + 4 + 3 * n + 15 + 4 * n * a + 1) & ~(int64_t)1;
+}
 
 inline int64_t energy_ws_bytes(int n, int a, int64_t B, int with_ecp) {
   int64_t s = align256(B * 8) + 2 * align256(B * 8) + 2 * align256(B * 3 * n * 8) + deriv_cache_bytes(n, a, true, B);
@@ -414,6 +416,20 @@ inline EnergyWs carve_energy_ws(void* ws, int n, int a, int64_t B, int with_ecp)
 static __constant__ AiqmcEcp c_ecp;   // one ECP table per translation unit (per system instantiation)
 
 __device__ __forceinline__ int quad_group(int p) { return p < 6 ? 0 : p < 18 ? 1 : p < 26 ? 2 : 3; }
+
+// the quadrature record at the tail of a walker's MoveCache (psi_core.cuh: MoveCache::QR)
+template <int NE, int NA>
+__device__ __forceinline__ void write_quad_record(double* __restrict__ mc, const double* __restrict__ x,
+                                                  const double* __restrict__ rot9, const double* __restrict__ gnorm4,
+                                                  double logabs, double phase, const double* __restrict__ vl) {
+  using MC = MoveCache<NE, NA>;
+  for (int q = 0; q < 3 * NE; ++q) mc[MC::QR + q] = x[q];
+  for (int q = 0; q < 9; ++q) mc[MC::QR + 3 * NE + q] = rot9[q];
+  for (int q = 0; q < 4; ++q) mc[MC::QR + 3 * NE + 9 + q] = gnorm4[q];
+  mc[MC::QR + 3 * NE + 13] = logabs;
+  mc[MC::QR + 3 * NE + 14] = phase;
+  for (int q = 0; q < 4 * NE * NA; ++q) mc[MC::QR_VL + q] = vl[q];
+}
 
 // everything of E_L except the non-local quadrature, from the two derivative passes' outputs:
 // one thread per walker
@@ -480,7 +496,9 @@ __global__ void __launch_bounds__(kThreads) k_energy_rest(AiqmcSystem sys, const
       }
       acc[quad_group(p)] += n2;
     }
-    for (int q = 0; q < 4; ++q) w.gnorm[4 * b + q] = sqrt(acc[q]);
+    for (int q = 0; q < 4; ++q) { acc[q] = sqrt(acc[q]); w.gnorm[4 * b + q] = acc[q]; }
+    write_quad_record<NE, NA>(w.cache + b * MoveCache<NE, NA>::SIZE, x, rot + b * 9, acc, w.logabs[b], w.phase[b],
+                              w.vl + b * NE * NA * 4);
   } else {
     e_out[b] = e;
   }
@@ -597,7 +615,9 @@ __global__ void __launch_bounds__(kThreads) k_tmove_prep(AiqmcSystem sys, const 
     }
     acc[quad_group(p)] += n2;
   }
-  for (int q = 0; q < 4; ++q) w.gnorm[4 * b + q] = sqrt(acc[q]);
+  for (int q = 0; q < 4; ++q) { acc[q] = sqrt(acc[q]); w.gnorm[4 * b + q] = acc[q]; }
+  write_quad_record<NE, NA>(w.cache + b * MoveCache<NE, NA>::SIZE, x, rot + b * 9, acc, w.logabs[b], w.phase[b],
+                            w.vl + b * NE * NA * 4);
 }
 
 // T-move selection (DMC/Tmoves.py:114-222), one thread per (walker, electron).  tm (B,N,A,50,4) holds

@@ -270,7 +270,11 @@ struct MoveCache {
   static constexpr int JAE = ENV + NE;                    // [N]
   static constexpr int JEE = JAE + NE;                    // [N]           sum_{k != i} u_ee(r_ik)
   static constexpr int MISC = JEE + NE;                   // [4] total Jastrow, log|psi|, phase, 0
-  static constexpr int SIZE = MISC + 4;
+  // "quadrature record": the walker-local inputs of the quadrature kernels, appended so that ONE bulk copy of the
+  // record brings everything a CTA needs (written by k_energy_rest / k_tmove_prep)
+  static constexpr int QR = MISC + 4;                     // [3N] positions [9] rotation [4] group norms [2] log|psi|, phase
+  static constexpr int QR_VL = QR + 3 * NE + 15;          // [N][A][4] v_l(r_ia)
+  static constexpr int SIZE = (QR_VL + 4 * NE * NA + 1) & ~1;   // even: records stay 16-byte aligned
 };
 
 // ---------------------------------------------------------------------------------------
