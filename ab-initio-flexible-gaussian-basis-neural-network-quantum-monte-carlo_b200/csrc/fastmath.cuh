@@ -8,8 +8,8 @@
 //              divergent lookups are conflict-free by construction (a 64-entry table measured 4-6
 //              wavefronts per LDS).  10 FP64 ops.  Relative error < 1e-15.
 //   ftanh(x):  2/(1+e) - 1 with e = exp(-2|x|) (degree-5 polynomial, single-constant reduction),
-//              reciprocal from the MUFU.RCP64H seed + one cubic step.  13 FP64 ops, sign and |x| by
-//              integer ops on the high word.  ABSOLUTE error < 2e-13 (relative accuracy is lost for
+//              reciprocal from the MUFU.RCP64H seed + one cubic step.  13 FP64 ops + one DMUL for -2|x| (the |.| is
+//              an operand modifier; the integer-op form cost three more issue slots), sign by integer ops on the high word.  ABSOLUTE error < 2e-13 (relative accuracy is lost for
 //              |x| < 1e-8 by design: only absolute accuracy enters log|psi| and E_L).
 //   ftanh_n<NV, ACC>: NV of them with interleaved steps (ILP); ACC = 1 is an 11-op variant (< 5e-11).
 //   frcp(d), frsqrt(x): MUFU.RCP64H / MUFU.RSQ64H seed + one cubic step (3 / 5 FP64 ops), ~1 ulp.
@@ -148,10 +148,15 @@ AQF_HD void ftanh_n(const double* __restrict__ x, double* __restrict__ out, cons
 #ifdef __CUDACC__
 #pragma unroll
 #endif
-  for (int i = 0; i < NV; ++i) { // u = -2|x| by integer ops (exponent + 1, sign set); x = 0 gives a harmless |u| <= 2^-1021
+  for (int i = 0; i < NV; ++i) {
     const uint32_t hx = (uint32_t)hi_word(x[i]);
     sg[i] = hx & 0x80000000u;
+#if !defined(AIQMC_TANH_INTABS) && defined(__CUDA_ARCH__)
+    u[i] = -2.0 * fabs(x[i]);    // one DMUL with the |.| operand modifier instead of three integer ops and a move
+#else
+    // u = -2|x| by integer ops (exponent + 1, sign set); x = 0 gives a harmless |u| <= 2^-1021
     u[i] = make_double((int32_t)(((hx & 0x7fffffffu) + 0x00100000u) | 0x80000000u), lo_word(x[i]));
+#endif
   }
 #ifdef __CUDACC__
 #pragma unroll
