@@ -194,8 +194,11 @@ __global__ void __launch_bounds__(kThreads) k_primal(AiqmcSystem sys, const doub
 // gradient by the fused forward + reverse (adjoint) sweep: one thread per configuration, nothing cached in HBM.
 // OUT == 0: grad (n_cfg,3N); OUT == 1: configurations are (walker, moved electron i), gnew (n_cfg,3) keeps electron
 // i's components.  Always: block partial of sum g^2 over all 3N components (limdrift's batch-global v2, quirk Q6).
+#ifndef AIQMC_GR_MINB
+#define AIQMC_GR_MINB 1
+#endif
 template <int NE, int NA, int SRC, int OUT>
-__global__ void __launch_bounds__(kThreads) k_grad_reverse(AiqmcSystem sys, const double* __restrict__ params,
+__global__ void __launch_bounds__(kThreads, AIQMC_GR_MINB) k_grad_reverse(AiqmcSystem sys, const double* __restrict__ params,
                                                            const double* __restrict__ pos, int64_t n_cfg, MovedSrc ms,
                                                            double* __restrict__ phase, double* __restrict__ logabs,
                                                            double* __restrict__ gout, double* __restrict__ partials,
