@@ -94,11 +94,20 @@ inline int64_t deriv_cache_doubles(int n, int a, bool lap) {
   return 3 * n + 12 * n * n + 24 * n + 4 * a * n + 8 * a + 12 * n + 16 + 3 * n * qm + 2 * n * n + 8 * n +
          (lap ? 8 * n * n : 0);
 }
-// The derivative cache is filled and consumed in chunks of configurations so that it never exceeds
-// kDerivCacheBudget bytes, whatever the batch (C6H6: 152 kB per configuration).
-constexpr int64_t kDerivCacheBudget = int64_t(1) << 30;
+// The derivative cache is filled and consumed in chunks of configurations so that it stays bounded whatever the
+// batch.  A chunk is also the grid of the one-thread-per-configuration primal pass, so it must be large enough to
+// fill 148 SMs: the budget is 1 GiB for small systems and grows with the per-configuration record (C6H6: 152 kB)
+// up to 16 GiB of the 180 GB -- with the former flat 1 GiB a C6H6 chunk was 7 040 threads (55 CTAs) and the sweep
+// took 394 instead of 262 ms at 2 368 walkers.
+#ifndef AIQMC_DERIV_CACHE_MAX_GIB
+#define AIQMC_DERIV_CACHE_MAX_GIB 16
+#endif
 inline int64_t deriv_chunk(int n, int a, bool lap) {
-  int64_t c = kDerivCacheBudget / (deriv_cache_doubles(n, a, lap) * 8);
+  const int64_t per_cfg = deriv_cache_doubles(n, a, lap) * 8;
+  int64_t budget = per_cfg * 131072;
+  if (budget < (int64_t(1) << 30)) budget = int64_t(1) << 30;
+  if (budget > (int64_t(AIQMC_DERIV_CACHE_MAX_GIB) << 30)) budget = int64_t(AIQMC_DERIV_CACHE_MAX_GIB) << 30;
+  int64_t c = budget / per_cfg;
   c &= ~int64_t(127);
   return c < 128 ? 128 : c;
 }
