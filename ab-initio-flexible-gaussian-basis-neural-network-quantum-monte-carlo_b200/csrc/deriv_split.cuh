@@ -34,7 +34,9 @@ struct DerivCache {
   static constexpr int T1 = GM + 2 * 2 * 4;                 // [3][N][QM]      first-stage tanh outputs
   static constexpr int MI = T1 + 3 * NE * QM;               // [N][N][2]       M^-1
   static constexpr int GMAT = MI + NE * NE * 2;             // [N][4][2]       Gm[k][c] = sum_j W[c,j] E[k,j] Minv[j,k]
-  static constexpr int SIZE_GRAD = GMAT + NE * 4 * 2;
+  static constexpr int YV = GMAT + NE * 4 * 2;              // [N][6]          Ynlm stream outputs
+  static constexpr int ENVV = YV + NE * 6;                  // [N]             envelopes
+  static constexpr int SIZE_GRAD = ENVV + NE;
   static constexpr int TT = SIZE_GRAD;                      // [N][4][N][2]    T[k][c][l] (Laplacian only)
   static constexpr int SIZE_LAP = TT + NE * 4 * NE * 2;
   static constexpr int size(bool lap) { return lap ? SIZE_LAP : SIZE_GRAD; }
@@ -82,6 +84,10 @@ struct DerivSplit {
     for (int q = 0; q < N * N; ++q) {
       dc[(int64_t)(DC::MI + 2 * q) * stride] = Mi[q].re;
       dc[(int64_t)(DC::MI + 2 * q + 1) * stride] = Mi[q].im;
+    }
+    for (int k = 0; k < N; ++k) {
+      for (int m = 0; m < 6; ++m) dc[(int64_t)(DC::YV + k * 6 + m) * stride] = pr.y[k][m];
+      dc[(int64_t)(DC::ENVV + k) * stride] = pr.env[k];
     }
     // Gm[k,c] = sum_j W[c,j] E[k,j] Minv[j,k];  T[k,c,l] likewise for every column l (Laplacian only)
     for (int k = 0; k < N; ++k) {
@@ -473,6 +479,158 @@ struct DerivSplit {
     // toolchain notes); keeping every tape / adjoint array observably alive to the end of the function forbids it.
     keep_alive(&pr); keep_alive(Mi); keep_alive(hp); keep_alive(t1); keep_alive(h_bar); keep_alive(y_bar);
     keep_alive(env_bar); keep_alive(G_bar); keep_alive(h0_bar);
+  }
+
+  // ---- the same reverse sweep, reading the primal quantities from the SoA derivative cache that primal<false>
+  //      wrote (N > 16: the per-thread tape of grad_reverse would be 12 N^2 doubles; the 3N forward tangents of the
+  //      two-pass path read the whole cache record 3N times -- 14 MB per C6H6 configuration, L2-bandwidth bound).
+  //      One thread per configuration; its own state is the adjoints only (~20 kB at N = 30).
+  static AQ_HD void grad_reverse_cached(const AiqmcSystem& sys, const double* __restrict__ P, const double* __restrict__ dc,
+                                        int64_t stride, double* __restrict__ grad) {
+    constexpr LayoutC<NE, NA> L{};
+    auto ld = [&](int slot) -> double { return dc[(int64_t)slot * stride]; };
+    const double inv_n[2] = {1.0 / sys.n_up, 1.0 / sys.n_dn};
+    double x[3 * N];
+    for (int q = 0; q < 3 * N; ++q) x[q] = ld(DC::X + q);
+
+    // (1) determinant
+    double h_bar[N][4], y_bar[N][6], env_bar[N];
+    for (int k = 0; k < N; ++k) {
+      env_bar[k] = 0.0;
+      for (int c = 0; c < 4; ++c) h_bar[k][c] = 0.0;
+      for (int m = 0; m < 6; ++m) y_bar[k][m] = 0.0;
+    }
+    for (int k = 0; k < N; ++k) {
+      const int s = k < sys.n_up_rows ? 0 : 1;
+      const double* W = P + L.orb_w[s];
+      const double* Bv = P + L.orb_b[s];
+      const int e = sys.sigma[k];
+      double h3[4], yk[6];
+      for (int c = 0; c < 4; ++c) h3[c] = ld(DC::H + (2 * N + e) * 4 + c);
+      for (int m = 0; m < 6; ++m) yk[m] = ld(DC::YV + k * 6 + m);
+      const double envk = ld(DC::ENVV + k);
+      for (int j = 0; j < N; ++j) {
+        double yo = 0.0;
+        for (int m = 0; m < 6; ++m) yo += yk[m] * P[L.y_w + m * N + j];
+        double pre = Bv[2 * j], pim = Bv[2 * j + 1];
+        for (int c = 0; c < 4; ++c) { pre += h3[c] * W[c * 2 * N + 2 * j]; pim += h3[c] * W[c * 2 * N + 2 * j + 1]; }
+        const double mre = ld(DC::MI + 2 * (j * N + k)), mim = ld(DC::MI + 2 * (j * N + k) + 1);
+        const double ev = envk * yo;
+        const double pre_bar = mre * ev, pim_bar = -mim * ev;
+        const double ev_bar = mre * pre - mim * pim;
+        for (int c = 0; c < 4; ++c) h_bar[e][c] += pre_bar * W[c * 2 * N + 2 * j] + pim_bar * W[c * 2 * N + 2 * j + 1];
+        env_bar[k] += ev_bar * yo;
+        const double yo_bar = ev_bar * envk;
+        for (int m = 0; m < 6; ++m) y_bar[k][m] += yo_bar * P[L.y_w + m * N + j];
+      }
+    }
+
+    // (2) one-electron layers, backwards (adjoints of the per-row inputs accumulate in place)
+    double G_bar[3][2][N][4];
+    double h0_bar[N][4 * A];
+    for (int l = 2; l >= 0; --l) {
+      if (l == 0) layer_reverse_cached<4 * A>(sys, P, 0, dc, stride, inv_n, h_bar, G_bar[0], h0_bar);
+      else layer_reverse_cached<4>(sys, P, l, dc, stride, inv_n, h_bar, G_bar[l], h_bar);
+    }
+
+    // (3) pair chains, backwards
+    for (int q = 0; q < 3 * N; ++q) grad[q] = 0.0;
+    for (int i = 0; i < N; ++i) {
+      const int s = i < sys.n_up ? 0 : 1;
+      for (int j = 0; j < N; ++j) {
+        if (i == j) continue;
+        double a0[4], a1[4], a2[4];
+        for (int c = 0; c < 4; ++c) {
+          a0[c] = ld(DC::HP + ((0 * N + i) * N + j) * 4 + c);
+          a1[c] = ld(DC::HP + ((1 * N + i) * N + j) * 4 + c);
+          a2[c] = ld(DC::HP + ((2 * N + i) * N + j) * 4 + c);
+        }
+        double b1[4], b0[4];
+        chain_reverse(P + L.dbl_w[1], a1, a2, G_bar[2][s][j], G_bar[1][s][j], b1);
+        chain_reverse(P + L.dbl_w[0], a0, a1, b1, G_bar[0][s][j], b0);
+        const double r = a0[0];
+        double r_bar = b0[0];
+        if (i < j) {                                            // e-e Pade term (Jastrow.py:23-41)
+          const double q = s_inv(1.0 + P[L.jas_alpha + i * N + j] * r);
+          r_bar += P[L.jas_cusp + i * N + j] * q * q;
+        }
+        const double rs = r_bar * s_inv(r);
+        for (int c = 0; c < 3; ++c) {
+          const double db = b0[1 + c] + rs * a0[1 + c];           // d = x_j - x_i
+          grad[3 * j + c] += db;
+          grad[3 * i + c] -= db;
+        }
+      }
+    }
+
+    // (4) electron-local parts through a 3-direction jet
+    using J = Jet<false, 3>;
+    using Op = ScalarOps<J>;
+    for (int e = 0; e < N; ++e) {
+      J xj[3];
+      for (int c = 0; c < 3; ++c) { xj[c] = Op::cst(x[3 * e + c]); xj[c].d[c] = 1.0; }
+      J h0e[4 * A], ye[6], enve, jaee;
+      PS::template electron_local<J>(P, e, xj, h0e, ye, enve, jaee);
+      for (int c = 0; c < 3; ++c) {
+        double g = jaee.d[c] + env_bar[e] * enve.d[c];
+        for (int q = 0; q < 4 * A; ++q) g += h0_bar[e][q] * h0e[q].d[c];
+        for (int m = 0; m < 6; ++m) g += y_bar[e][m] * ye[m].d[c];
+        grad[3 * e + c] += g;
+      }
+    }
+    keep_alive(x); keep_alive(h_bar); keep_alive(y_bar); keep_alive(env_bar); keep_alive(G_bar); keep_alive(h0_bar);
+  }
+
+  // layer_reverse on the cache; `hin_bar` doubles as the per-row accumulator (it may alias h_bar for l >= 1: row k's
+  // h_bar is consumed before row k's hin_bar is written)
+  template <int DIN>
+  static AQ_HD void layer_reverse_cached(const AiqmcSystem& sys, const double* __restrict__ P, int l,
+                                         const double* __restrict__ dc, int64_t stride, const double inv_n[2],
+                                         const double (*h_bar)[4], double (*G_bar_l)[N][4], double (*hin_bar)[DIN]) {
+    constexpr LayoutC<NE, NA> L{};
+    constexpr int DTOT = 3 * DIN + 8, Q = DTOT / 4;
+    auto ld = [&](int slot) -> double { return dc[(int64_t)slot * stride]; };
+    const double* sw = P + L.sing_w[l];
+    double gup_bar[DIN], gdn_bar[DIN];
+    for (int q = 0; q < DIN; ++q) { gup_bar[q] = 0.0; gdn_bar[q] = 0.0; }
+    for (int k = 0; k < N; ++k) {
+      const double* cw = P + L.conv_w[l] + k * DTOT;
+      double zb[4], ob4[4];
+      for (int m = 0; m < 4; ++m) {
+        const double hn = ld(DC::H + (l * N + k) * 4 + m);           // h_{l+1}[k][m]
+        double t, ob;
+        if (DIN == 4) {                                               // residual layer (quirk Q5)
+          const double hprev = (l == 0) ? ld(DC::H0 + k * 4 * A + m) : ld(DC::H + ((l - 1) * N + k) * 4 + m);
+          t = kSqrt2 * hn - hprev;
+          ob = h_bar[k][m] * kInvSqrt2;
+        } else {
+          t = hn;
+          ob = h_bar[k][m];
+        }
+        zb[m] = ob * (1.0 - t * t);
+        ob4[m] = ob;
+      }
+      for (int q = 0; q < DIN; ++q) hin_bar[k][q] = (DIN == 4) ? ob4[q < 4 ? q : 0] : 0.0;
+      for (int q = 0; q < Q; ++q) {
+        double ob = 0.0;
+        for (int m = 0; m < 4; ++m) ob += zb[m] * sw[q * 4 + m];
+        const double t = ld(DC::T1 + (l * N + k) * QM + q);
+        const double pb = ob * (1.0 - t * t) * 0.25;
+        for (int c = 0; c < 4; ++c) {
+          const int idx = 4 * q + c;
+          const double xb = pb * cw[idx];
+          if (idx < DIN) hin_bar[k][idx] += xb;
+          else if (idx < 2 * DIN) gup_bar[idx - DIN] += xb;
+          else if (idx < 3 * DIN) gdn_bar[idx - 2 * DIN] += xb;
+          else if (idx < 3 * DIN + 4) G_bar_l[0][k][idx - 3 * DIN] = xb * inv_n[0];
+          else G_bar_l[1][k][idx - 3 * DIN - 4] = xb * inv_n[1];
+        }
+      }
+    }
+    for (int k = 0; k < N; ++k) {
+      const bool up = k < sys.n_up;
+      for (int q = 0; q < DIN; ++q) hin_bar[k][q] += (up ? gup_bar[q] * inv_n[0] : gdn_bar[q] * inv_n[1]);
+    }
   }
 
   static AQ_HD void keep_alive(const void* p) {

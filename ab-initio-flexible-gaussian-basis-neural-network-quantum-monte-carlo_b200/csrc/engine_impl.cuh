@@ -91,7 +91,7 @@ __host__ __device__ inline int64_t align256(int64_t v) { return (v + 255) & ~int
 
 inline int64_t deriv_cache_doubles(int n, int a, bool lap) {
   const int qm = (3 * a + 2) > 5 ? (3 * a + 2) : 5;
-  return 3 * n + 12 * n * n + 24 * n + 4 * a * n + 8 * a + 12 * n + 16 + 3 * n * qm + 2 * n * n + 8 * n +
+  return 3 * n + 12 * n * n + 24 * n + 4 * a * n + 8 * a + 12 * n + 16 + 3 * n * qm + 2 * n * n + 8 * n + 7 * n +
          (lap ? 8 * n * n : 0);
 }
 // The derivative cache is filled and consumed in chunks of configurations so that it stays bounded whatever the
@@ -244,6 +244,38 @@ __global__ void __launch_bounds__(kThreads, AIQMC_GR_MINB) k_grad_reverse(AiqmcS
     if (OUT == 0) {
       for (int q = 0; q < 3 * NE; ++q) gout[t * 3 * NE + q] = g[q];
     } else {
+      for (int e = 0; e < NE; ++e)
+        if (e == i)
+          for (int c = 0; c < 3; ++c) gout[t * 3 + c] = g[3 * e + c];
+    }
+  }
+  if (partials) {
+    const double s = block_sum<kThreads>(g2, red);
+    if (threadIdx.x == 0) partials[blockIdx.x * 4 + pcol] = s;
+  }
+}
+
+// reverse sweep on the derivative cache (deriv_split.cuh: grad_reverse_cached): one thread per configuration of the
+// chunk; outputs and block partials as k_grad_reverse
+template <int NE, int NA, int OUT>
+__global__ void __launch_bounds__(kThreads) k_reverse_cached(AiqmcSystem sys, const double* __restrict__ params,
+                                                             const double* __restrict__ dc, int64_t cfg0, int64_t n_cfg,
+                                                             double* __restrict__ gout, double* __restrict__ partials,
+                                                             int pcol) {
+  extern __shared__ double sP[];
+  __shared__ double red[kThreads / 32];
+  const double* P = stage_params<NE, NA>(params, sP);
+  const int64_t tl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double g2 = 0.0;
+  if (tl < n_cfg) {
+    double g[3 * NE];
+    DerivSplit<NE, NA>::grad_reverse_cached(sys, P, dc + tl, n_cfg, g);
+    for (int q = 0; q < 3 * NE; ++q) g2 += g[q] * g[q];
+    const int64_t t = cfg0 + tl;
+    if (OUT == 0) {
+      for (int q = 0; q < 3 * NE; ++q) gout[t * 3 * NE + q] = g[q];
+    } else {
+      const int i = (int)(t % NE);
       for (int e = 0; e < NE; ++e)
         if (e == i)
           for (int c = 0; c < 3; ++c) gout[t * 3 + c] = g[3 * e + c];
@@ -833,6 +865,15 @@ struct Launch {
       ++g_launch_count;
       k_primal<NE, NA, LAP, SRC><<<gp, kThreads, kSmem, st>>>(*sys, params, pos, c0, nc, ms, dcache, mc, phase, logabs);
       ++g_launch_count;
+#ifndef AIQMC_NO_REVERSE_CACHED
+      if constexpr (!LAP) {     // gradient only: ONE reverse sweep per configuration instead of 3N forward tangents
+        AQ_CUDA_OK(prep(k_reverse_cached<NE, NA, OUT>));
+        k_reverse_cached<NE, NA, OUT><<<gp, kThreads, kSmem, st>>>(*sys, params, dcache, c0, nc, gout,
+                                                                  partials ? partials + *rows * 4 : nullptr, pcol);
+        if (rows) *rows += gp;
+        continue;
+      }
+#endif
       k_tangent<NE, NA, LAP, OUT><<<gt, 32 * tan_warps<NE>(), kSmem, st>>>(*sys, params, dcache, c0, nc, gout, lap_parts, lap_stride,
                                                               partials ? partials + *rows * 4 : nullptr, pcol);
       if (rows) *rows += gt;

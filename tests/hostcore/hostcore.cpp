@@ -24,6 +24,10 @@ static void run(const AiqmcSystem* sys, const double* P, const double* pos, long
       Psi<NE, NA>::template eval_deriv<true>(*sys, P, x, phase[t], logabs[t], grad + t * 3 * NE, lap[t]);
     } else if (mode == 5) {      // gradient by the fused reverse sweep (deriv_split.cuh)
       DerivSplit<NE, NA>::grad_reverse(*sys, P, x, phase[t], logabs[t], grad + t * 3 * NE);
+    } else if (mode == 6) {      // primal pass into the cache + reverse sweep ON the cache (the N > 16 sweep path)
+      std::vector<double> scratch(DerivCache<NE, NA>::SIZE_GRAD);
+      DerivSplit<NE, NA>::template primal<false>(*sys, P, x, scratch.data(), 1, nullptr, phase[t], logabs[t]);
+      DerivSplit<NE, NA>::grad_reverse_cached(*sys, P, scratch.data(), 1, grad + t * 3 * NE);
     } else {      // 3 / 4: gradient / gradient + Laplacian through the two-pass path (deriv_split.cuh)
       std::vector<double> scratch(DerivCache<NE, NA>::SIZE_LAP);
       double dummy;

@@ -242,6 +242,29 @@ def test_packed_group_quadrature_benzene_matches_full_evaluation_kernel():
     assert np.array_equal(e_def, eng.local_energy(torch.tensor(case.pos), rot, stages=7).cpu().numpy())
 
 
+def test_benzene_gradient_and_sweep_use_the_cached_reverse_pass():
+    """N = 30 > 16: gradients come from the primal pass + ONE reverse sweep on the derivative cache
+    (deriv_split.cuh: grad_reverse_cached).  Gradient vs torch autograd on the oracle; the sweep's accept mask vs
+    the oracle's walkers_update, bit for bit."""
+    ring = lambda r, n: [[r * math.cos(2 * math.pi * k / n), r * math.sin(2 * math.pi * k / n), 0.0] for k in range(n)]
+    case = Case(n=30, natoms=12, spins=[1.] * 15 + [-1.] * 15, seed=21, atoms=ring(2.640, 6) + ring(4.689, 6),
+                charges=[4.0] * 6 + [1.0] * 6, nwalkers=3, width=0.8)
+    eng = engine(case)
+    ph, la, g = eng.psi(torch.tensor(case.pos), mode=1)[:3]
+    f = lambda x: case.net.apply(case.params, x, case.t_spins, case.t_atoms)[1]
+    lat, gt, _ = O.value_and_grad(f, torch.tensor(case.pos))
+    np.testing.assert_allclose(la.cpu().numpy(), lat.detach().numpy(), rtol=1e-10)
+    np.testing.assert_allclose(g.cpu().numpy(), gt.numpy(), rtol=1e-8, atol=1e-9)
+    tstep = 0.05
+    rand = case.sweep_rand(tstep)
+    pos = torch.tensor(case.pos).cuda()
+    out = eng.vmc_sweep(pos, rand['gauss1'].cuda(), rand['gauss2'].cuda(), rand['rnd'].cuda(), tstep)
+    new_data, aux = O.walkers_update(O.select_output(case.net.apply, 1), case.params, case.oracle_data(), rand, tstep,
+                                     3, case.n, case.B, return_aux=True)
+    assert np.array_equal(out['accept'].cpu().numpy().astype(bool), aux['accept'].numpy())
+    np.testing.assert_allclose(pos.cpu().numpy(), new_data.positions.numpy(), rtol=1e-10, atol=1e-10)
+
+
 @pytest.mark.parametrize("name,rich,tstep,scale", [("C_ecp", False, 0.05, 1.0), ("C_ecp", True, 1.0, -3.0),
                                                    ("N2_ecp", True, 1.0, -3.0), ("h2like", True, 1.0, -5.0)])
 def test_dmc_tmoves_match_oracle(name, rich, tstep, scale):

@@ -48,6 +48,11 @@ def test_value_grad_laplacian_match_oracle(hostlib, name):
     ph5, la5, g5, _ = H.host_psi(hostlib, case.spec().c_struct(), packed, case.pos, 5)
     np.testing.assert_allclose(la5, la, rtol=1e-13, atol=1e-13)
     np.testing.assert_allclose(g5, gt.numpy(), rtol=1e-9, atol=1e-10)
+    # the reverse sweep on the derivative cache (systems with N > 16 in the kernels; any system here)
+    ph6, la6, g6, _ = H.host_psi(hostlib, case.spec().c_struct(), packed, case.pos, 6)
+    np.testing.assert_allclose(la6, la, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(g6, gt.numpy(), rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(g6, g5, rtol=1e-12, atol=1e-12)
 
 
 def test_benzene_sized_system_value(hostlib):
@@ -63,6 +68,9 @@ def test_benzene_sized_system_value(hostlib):
     f = lambda x: case.net.apply(case.params, x, case.t_spins, case.t_atoms)[1]
     _, gt, _ = O.value_and_grad(f, torch.tensor(case.pos))
     np.testing.assert_allclose(g, gt.numpy(), rtol=1e-8, atol=1e-9)
+    _, la6, g6, _ = H.host_psi(hostlib, case.spec().c_struct(), packed, case.pos, 6)     # the path the kernels take at N = 30
+    np.testing.assert_allclose(la6, lat.numpy(), rtol=1e-10)
+    np.testing.assert_allclose(g6, gt.numpy(), rtol=1e-8, atol=1e-9)
 
 
 def test_layout_matches_library_and_is_dense(hostlib):
