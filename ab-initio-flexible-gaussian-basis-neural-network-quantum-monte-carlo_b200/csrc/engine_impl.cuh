@@ -785,7 +785,15 @@ inline int64_t pgrad_blocks(int64_t B) {
   const int64_t nb = (B + 31) / 32;
   return nb < 1 ? 1 : (nb > kPgradMaxBlocks ? kPgradMaxBlocks : nb);
 }
-inline int64_t pgrad_ws_bytes(int n, int a, int64_t B) { return align256(pgrad_blocks(B) * make_layout(n, a).total * 8); }
+constexpr int kPgradCachedBlocks = 148;      // CTAs per chunk of the N > 16 path (parameters + accumulator fill an SM's shared memory)
+inline int64_t pgrad_cached_rows(int n, int a, int64_t B) {
+  const int64_t c = deriv_chunk(n, a, false);
+  return ((B + c - 1) / c) * kPgradCachedBlocks;
+}
+inline int64_t pgrad_ws_bytes(int n, int a, int64_t B) {
+  if (n <= 16) return align256(pgrad_blocks(B) * make_layout(n, a).total * 8);
+  return align256(pgrad_cached_rows(n, a, B) * make_layout(n, a).total * 8) + deriv_cache_bytes(n, a, false, B) + align256(B * 8);
+}
 
 template <int NE, int NA>
 __global__ void __launch_bounds__(32) k_param_grad(AiqmcSystem sys, const double* __restrict__ params,
@@ -810,6 +818,29 @@ __global__ void __launch_bounds__(32) k_param_grad(AiqmcSystem sys, const double
     ParamGrad<NE, NA>::run(sys, P, x, valid ? alpha[b] : 0.0, valid ? beta[b] : 0.0, ph, la, sink);
     if (valid && phase) phase[b] = ph;
     if (valid && logabs) logabs[b] = la;
+  }
+  __syncwarp();
+  for (int q = threadIdx.x; q < total; q += 32) partials[(int64_t)blockIdx.x * total + q] = acc[q];
+}
+
+// N > 16: the same sweep run on the derivative cache of a chunk of walkers (k_primal<false> wrote it)
+template <int NE, int NA>
+__global__ void __launch_bounds__(32) k_param_grad_cached(AiqmcSystem sys, const double* __restrict__ params,
+                                                          const double* __restrict__ dc, int64_t cfg0, int64_t n_cfg,
+                                                          const double* __restrict__ alpha, const double* __restrict__ beta,
+                                                          double* __restrict__ partials) {
+  constexpr int total = make_layout(NE, NA).total;
+  extern __shared__ double sP[];
+  const double* P = stage_params<NE, NA>(params, sP);
+  double* acc = sP + total;
+  for (int q = threadIdx.x; q < total; q += 32) acc[q] = 0.0;
+  __syncwarp();
+  WarpSink sink{acc};
+  for (int64_t b0 = (int64_t)blockIdx.x * 32; b0 < n_cfg; b0 += (int64_t)gridDim.x * 32) {
+    const int64_t tl = b0 + threadIdx.x;
+    const bool valid = tl < n_cfg;
+    const int64_t tt = valid ? tl : n_cfg - 1;            // tail lanes redo the last walker with a zero seed
+    ParamGrad<NE, NA>::run_cached(sys, P, dc + tt, n_cfg, valid ? alpha[cfg0 + tl] : 0.0, valid ? beta[cfg0 + tl] : 0.0, sink);
   }
   __syncwarp();
   for (int q = threadIdx.x; q < total; q += 32) partials[(int64_t)blockIdx.x * total + q] = acc[q];
@@ -1134,7 +1165,7 @@ struct Launch {
   }
 
 
-  static constexpr bool kPgrad = (NE <= 16);   // per-thread tape is 12 N^2 doubles of local memory, as for kReverse
+  static constexpr bool kPgrad = (NE <= 16);   // fused forward + reverse per thread; beyond: primal pass + sweep on the cache
   static int param_grad(const AiqmcSystem* sys, const double* params, const double* pos, int64_t B, const double* alpha,
                         const double* beta, double* grad_out, double* phase, double* logabs, void* ws, int64_t ws_bytes,
                         cudaStream_t st) {
@@ -1153,7 +1184,37 @@ struct Launch {
       AQ_CUDA_OK(cudaGetLastError());
       return AIQMC_OK;
     } else {
-      return AIQMC_E_UNSUPPORTED;
+      // N > 16: primal pass into the derivative cache chunk by chunk, the sweep on the cache, one reduction at the end
+      constexpr int total = make_layout(NE, NA).total;
+      if (B <= 0) {
+        AQ_CUDA_OK(cudaMemsetAsync(grad_out, 0, total * sizeof(double), st));
+        return AIQMC_OK;
+      }
+      if (!ws || ws_bytes < pgrad_ws_bytes(NE, NA, B)) return AIQMC_E_WORKSPACE;
+      double* partials = (double*)ws;
+      double* dcache = (double*)((char*)ws + align256(pgrad_cached_rows(NE, NA, B) * total * 8));
+      double* la_tmp = (double*)((char*)dcache + deriv_cache_bytes(NE, NA, false, B));
+      AQ_CUDA_OK(prep(k_primal<NE, NA, false, 0>));
+      AQ_CUDA_OK(cudaFuncSetAttribute(k_param_grad_cached<NE, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kSmem));
+      const int64_t chunk = deriv_chunk(NE, NA, false);
+      MovedSrc ms{};
+      int rows = 0;
+      for (int64_t c0 = 0; c0 < B; c0 += chunk) {
+        const int64_t nc = (B - c0 < chunk) ? B - c0 : chunk;
+        const unsigned gp = (unsigned)((nc + kThreads - 1) / kThreads);
+        int64_t nb = (nc + 31) / 32;
+        if (nb > kPgradCachedBlocks) nb = kPgradCachedBlocks;
+        g_launch_count += 2;
+        k_primal<NE, NA, false, 0><<<gp, kThreads, kSmem, st>>>(*sys, params, pos, c0, nc, ms, dcache, nullptr, phase,
+                                                                 logabs ? logabs : la_tmp);
+        k_param_grad_cached<NE, NA><<<(unsigned)nb, 32, 2 * kSmem, st>>>(*sys, params, dcache, c0, nc, alpha, beta,
+                                                                          partials + (int64_t)rows * total);
+        rows += (int)nb;
+      }
+      ++g_launch_count;
+      k_reduce_param_partials<<<(total + 255) / 256, 256, 0, st>>>(partials, rows, total, grad_out);
+      AQ_CUDA_OK(cudaGetLastError());
+      return AIQMC_OK;
     }
   }
 

@@ -34,11 +34,45 @@ struct ParamGrad {
 #endif
   }
 
+
+  // Where the primal quantities of the reverse sweep come from: the thread's own forward pass (N <= 16), or the SoA
+  // derivative cache written by DerivSplit::primal<false> (N > 16, where the per-thread tape would be 12 N^2 doubles).
+  struct LocalView {
+    const typename PS::Primal& pr;
+    const cplx* Mi;
+    const double* hp;
+    const double* t1;
+    AQ_HD double y(int k, int m) const { return pr.y[k][m]; }
+    AQ_HD double env(int k) const { return pr.env[k]; }
+    AQ_HD double hin(int l, int k, int q) const { return l == 0 ? pr.h0[k][q] : pr.h[l][k][q]; }
+    AQ_HD double hout(int l, int k, int m) const { return pr.h[l + 1][k][m]; }
+    AQ_HD double gmean(int l, int s, int q) const { return l == 0 ? pr.g0[s][q] : pr.g[l][s][q]; }
+    AQ_HD double G(int l, int s, int k, int c) const { return pr.G[l][s][k][c]; }
+    AQ_HD double t1v(int l, int k, int q) const { return t1[(l * N + k) * QM + q]; }
+    AQ_HD double hpv(int l, int i, int j, int c) const { return hp[((l * N + i) * N + j) * 4 + c]; }
+    AQ_HD cplx mi(int j, int k) const { return Mi[j * N + k]; }
+  };
+  struct CacheView {
+    using DC = DerivCache<NE, NA>;
+    const double* dc;
+    int64_t stride;
+    AQ_HD double ld(int slot) const { return dc[(int64_t)slot * stride]; }
+    AQ_HD double y(int k, int m) const { return ld(DC::YV + k * 6 + m); }
+    AQ_HD double env(int k) const { return ld(DC::ENVV + k); }
+    AQ_HD double hin(int l, int k, int q) const { return l == 0 ? ld(DC::H0 + k * 4 * A + q) : ld(DC::H + ((l - 1) * N + k) * 4 + q); }
+    AQ_HD double hout(int l, int k, int m) const { return ld(DC::H + (l * N + k) * 4 + m); }
+    AQ_HD double gmean(int l, int s, int q) const { return l == 0 ? ld(DC::G0M + s * 4 * A + q) : ld(DC::GM + ((l - 1) * 2 + s) * 4 + q); }
+    AQ_HD double G(int l, int s, int k, int c) const { return ld(DC::GS + ((l * 2 + s) * N + k) * 4 + c); }
+    AQ_HD double t1v(int l, int k, int q) const { return ld(DC::T1 + (l * N + k) * QM + q); }
+    AQ_HD double hpv(int l, int i, int j, int c) const { return ld(DC::HP + ((l * N + i) * N + j) * 4 + c); }
+    AQ_HD cplx mi(int j, int k) const { return {ld(DC::MI + 2 * (j * N + k)), ld(DC::MI + 2 * (j * N + k) + 1)}; }
+  };
+
   // adjoint of the one-electron layer l; mirrors DerivSplit::layer_reverse and adds the weight gradients
-  template <int DIN, class Sink>
-  static AQ_HD void layer_reverse(const AiqmcSystem& sys, const double* __restrict__ P, int l,
-                                  const typename PS::Primal& pr, const double* __restrict__ t1, const double inv_n[2],
-                                  const double (*h_bar)[4], double (*G_bar_l)[N][4], double (*hin_bar)[DIN], Sink& sink) {
+  template <int DIN, class View, class Sink>
+  static AQ_HD void layer_reverse(const AiqmcSystem& sys, const double* __restrict__ P, int l, const View& v,
+                                  const double inv_n[2], const double (*h_bar)[4], double (*G_bar_l)[N][4],
+                                  double (*hin_bar)[DIN], Sink& sink) {
     constexpr LayoutC<NE, NA> L{};
     constexpr int DTOT = 3 * DIN + 8, Q = DTOT / 4;
     const double* sw = P + L.sing_w[l];
@@ -51,15 +85,12 @@ struct ParamGrad {
       for (int m = 0; m < 4; ++m) sw_bar[q][m] = 0.0;
     for (int k = 0; k < N; ++k) {
       const double* cw = P + L.conv_w[l] + k * DTOT;
-      const double* hin = (l == 0) ? pr.h0[k] : pr.h[l][k];
-      const double* gup = (l == 0) ? pr.g0[0] : pr.g[l][0];
-      const double* gdn = (l == 0) ? pr.g0[1] : pr.g[l][1];
       double zb[4];
       for (int m = 0; m < 4; ++m) {
-        const double hn = pr.h[l + 1][k][m];
+        const double hn = v.hout(l, k, m);
         double t, ob;
         if (DIN == 4) {                                   // residual layer (quirk Q5)
-          t = kSqrt2 * hn - hin[m];
+          t = kSqrt2 * hn - v.hin(l, k, m);
           ob = h_bar[k][m] * kInvSqrt2;
         } else {
           t = hn;
@@ -73,16 +104,17 @@ struct ParamGrad {
       for (int q = 0; q < Q; ++q) {
         double ob = 0.0;
         for (int m = 0; m < 4; ++m) ob += zb[m] * sw[q * 4 + m];
-        const double t = t1[(l * N + k) * QM + q];
+        const double t = v.t1v(l, k, q);
         for (int m = 0; m < 4; ++m) sw_bar[q][m] += t * zb[m];
         const double pre_bar = ob * (1.0 - t * t);
         sink.add(L.conv_b[l] + k * Q + q, pre_bar);
         const double pb = pre_bar * 0.25;
         for (int c = 0; c < 4; ++c) {
           const int idx = 4 * q + c;
-          const double xin = idx < DIN ? hin[idx] : idx < 2 * DIN ? gup[idx - DIN] : idx < 3 * DIN ? gdn[idx - 2 * DIN]
-                             : idx < 3 * DIN + 4 ? pr.G[l][0][k][idx - 3 * DIN] * inv_n[0]
-                                                 : pr.G[l][1][k][idx - 3 * DIN - 4] * inv_n[1];
+          const double xin = idx < DIN ? v.hin(l, k, idx) : idx < 2 * DIN ? v.gmean(l, 0, idx - DIN)
+                             : idx < 3 * DIN ? v.gmean(l, 1, idx - 2 * DIN)
+                             : idx < 3 * DIN + 4 ? v.G(l, 0, k, idx - 3 * DIN) * inv_n[0]
+                                                 : v.G(l, 1, k, idx - 3 * DIN - 4) * inv_n[1];
           sink.add(L.conv_w[l] + k * DTOT + idx, pb * xin);
           const double xb = pb * cw[idx];
           if (idx < DIN) own[k][idx] += xb;
@@ -126,7 +158,6 @@ struct ParamGrad {
   template <class Sink>
   static AQ_HD void run(const AiqmcSystem& sys, const double* __restrict__ P, const double* __restrict__ x, double alpha,
                         double beta, double& phase, double& logabs, Sink& sink) {
-    constexpr LayoutC<NE, NA> L{};
     typename PS::Primal pr;
     cplx Mi[N * N];
     double hp[3 * N * N * 4];
@@ -135,6 +166,26 @@ struct ParamGrad {
     double ld;
     PS::gj_inverse(Mi, ld, phase);
     logabs = ld + pr.jastrow;
+    const LocalView v{pr, Mi, hp, t1};
+    run_impl(sys, P, x, v, alpha, beta, sink);
+    keep_alive(&pr); keep_alive(Mi); keep_alive(hp); keep_alive(t1);
+  }
+
+  // the sweep on the derivative cache of one configuration (written by DerivSplit::primal<false>)
+  template <class Sink>
+  static AQ_HD void run_cached(const AiqmcSystem& sys, const double* __restrict__ P, const double* __restrict__ dc,
+                               int64_t stride, double alpha, double beta, Sink& sink) {
+    double x[3 * N];
+    for (int q = 0; q < 3 * N; ++q) x[q] = dc[(int64_t)(DerivCache<NE, NA>::X + q) * stride];
+    const CacheView v{dc, stride};
+    run_impl(sys, P, x, v, alpha, beta, sink);
+    keep_alive(x);
+  }
+
+  template <class View, class Sink>
+  static AQ_HD void run_impl(const AiqmcSystem& sys, const double* __restrict__ P, const double* __restrict__ x,
+                             const View& v, double alpha, double beta, Sink& sink) {
+    constexpr LayoutC<NE, NA> L{};
     const double inv_n[2] = {1.0 / sys.n_up, 1.0 / sys.n_dn};
 
     // (1) determinant, column by column
@@ -157,23 +208,26 @@ struct ParamGrad {
         const double* Bv = P + L.orb_b[s];
         const int e = sys.sigma[k];
         double yo = 0.0;
-        for (int m = 0; m < 6; ++m) yo += pr.y[k][m] * P[L.y_w + m * N + j];
+        for (int m = 0; m < 6; ++m) yo += v.y(k, m) * P[L.y_w + m * N + j];
         double pre = Bv[2 * j], pim = Bv[2 * j + 1];
-        for (int c = 0; c < 4; ++c) { pre += pr.h[3][e][c] * W[c * 2 * N + 2 * j]; pim += pr.h[3][e][c] * W[c * 2 * N + 2 * j + 1]; }
-        const cplx mi = Mi[j * N + k];
+        double h3[4];
+        for (int c = 0; c < 4; ++c) h3[c] = v.hout(2, e, c);
+        for (int c = 0; c < 4; ++c) { pre += h3[c] * W[c * 2 * N + 2 * j]; pim += h3[c] * W[c * 2 * N + 2 * j + 1]; }
+        const cplx mi = v.mi(j, k);
         const double cre = alpha * mi.re + beta * mi.im, cim = alpha * mi.im - beta * mi.re;   // (alpha - i beta) M^-1[j,k]
-        const double ev = pr.env[k] * yo;
+        const double envk = v.env(k);
+        const double ev = envk * yo;
         const double pre_bar = cre * ev, pim_bar = -cim * ev;
         const double ev_bar = cre * pre - cim * pim;
         ob[s][0] += pre_bar; ob[s][1] += pim_bar;
         for (int c = 0; c < 4; ++c) {
-          ow[s][c][0] += pr.h[3][e][c] * pre_bar;
-          ow[s][c][1] += pr.h[3][e][c] * pim_bar;
+          ow[s][c][0] += h3[c] * pre_bar;
+          ow[s][c][1] += h3[c] * pim_bar;
           h_bar[e][c] += pre_bar * W[c * 2 * N + 2 * j] + pim_bar * W[c * 2 * N + 2 * j + 1];
         }
         env_bar[k] += ev_bar * yo;
-        const double yo_bar = ev_bar * pr.env[k];
-        for (int m = 0; m < 6; ++m) { y_bar[k][m] += yo_bar * P[L.y_w + m * N + j]; yw[m] += yo_bar * pr.y[k][m]; }
+        const double yo_bar = ev_bar * envk;
+        for (int m = 0; m < 6; ++m) { y_bar[k][m] += yo_bar * P[L.y_w + m * N + j]; yw[m] += yo_bar * v.y(k, m); }
       }
       for (int s = 0; s < 2; ++s) {
         sink.add(L.orb_b[s] + 2 * j, ob[s][0]);
@@ -190,8 +244,8 @@ struct ParamGrad {
     double G_bar[3][2][N][4];
     double h0_bar[N][4 * A];
     for (int l = 2; l >= 0; --l) {
-      if (l == 0) layer_reverse<4 * A>(sys, P, 0, pr, t1, inv_n, h_bar, G_bar[0], h0_bar, sink);
-      else layer_reverse<4>(sys, P, l, pr, t1, inv_n, h_bar, G_bar[l], h_bar, sink);
+      if (l == 0) layer_reverse<4 * A>(sys, P, 0, v, inv_n, h_bar, G_bar[0], h0_bar, sink);
+      else layer_reverse<4>(sys, P, l, v, inv_n, h_bar, G_bar[l], h_bar, sink);
     }
 
     // (3) pair chains, backwards (all ordered pairs, diagonal included); e-e Pade parameters
@@ -203,9 +257,8 @@ struct ParamGrad {
     for (int i = 0; i < N; ++i) {
       const int s = i < sys.n_up ? 0 : 1;
       for (int j = 0; j < N; ++j) {
-        const double* a0 = hp + ((0 * N + i) * N + j) * 4;
-        const double* a1 = hp + ((1 * N + i) * N + j) * 4;
-        const double* a2 = hp + ((2 * N + i) * N + j) * 4;
+        double a0[4], a1[4], a2[4];
+        for (int c = 0; c < 4; ++c) { a0[c] = v.hpv(0, i, j, c); a1[c] = v.hpv(1, i, j, c); a2[c] = v.hpv(2, i, j, c); }
         double b1[4];
         chain_reverse(P + L.dbl_w[1], a1, a2, G_bar[2][s][j], G_bar[1][s][j], b1, wb[1], bb[1]);
         chain_reverse(P + L.dbl_w[0], a0, a1, b1, nullptr, nullptr, wb[0], bb[0]);
@@ -320,7 +373,7 @@ struct ParamGrad {
     for (int l = 0; l < 3; ++l)
       for (int m = 0; m < 6; ++m) sink.add(L.yn_b[l] + m, ybb[l][m]);
 
-    keep_alive(&pr); keep_alive(Mi); keep_alive(hp); keep_alive(t1); keep_alive(h_bar); keep_alive(y_bar);
+    keep_alive(h_bar); keep_alive(y_bar);
     keep_alive(env_bar); keep_alive(G_bar); keep_alive(h0_bar); keep_alive(wb); keep_alive(bb); keep_alive(ywb);
     keep_alive(ybb); keep_alive(yw0b);
   }

@@ -189,8 +189,9 @@ int aiqmc_energy_stats(const double* e_l, int32_t e_l_stride, int64_t n_walkers,
  * alpha = 2 Re(diff) / B, beta = 2 (Im(diff) + Im(clipped E_L)) / B reproduces tangents_out of :215-218 for complex
  * outputs, alpha = diff / B, beta = 0 the real branch (:222).  Entries for quantities pack_params derives on the host
  * (row-normalised y weights, sigma * xi) are gradients w.r.t. the PACKED values; non-trainable slots are 0.
- * phase / logabs (n_walkers) may be NULL.  Sums are fixed-order (bit reproducible).  Systems with N > 16 return
- * AIQMC_E_UNSUPPORTED (per-thread tape size). */
+ * phase / logabs (n_walkers) may be NULL.  Sums are fixed-order (bit reproducible).  N <= 16: one fused forward +
+ * reverse pass per walker; N > 16: the primal pass fills the derivative cache (part of the workspace) and the sweep
+ * runs on it. */
 int64_t aiqmc_param_grad_workspace_bytes(const AiqmcSystem* sys, int64_t n_walkers);
 int aiqmc_psi_param_grad(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_walkers,
                          const double* alpha, const double* beta, double* grad_out, double* phase, double* logabs,

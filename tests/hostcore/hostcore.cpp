@@ -68,19 +68,25 @@ struct HostSink {
 };
 template <int NE, int NA>
 static void run_pgrad(const AiqmcSystem* sys, const double* P, const double* pos, long n, const double* alpha,
-                      const double* beta, double* out) {
+                      const double* beta, double* out, int cached) {
   const int total = make_layout(NE, NA).total;
 #pragma omp parallel for schedule(dynamic, 4)
   for (long t = 0; t < n; ++t) {
     HostSink sink{out + t * total};
     double ph, la;
-    ParamGrad<NE, NA>::run(*sys, P, pos + t * 3 * NE, alpha[t], beta[t], ph, la, sink);
+    if (!cached) {
+      ParamGrad<NE, NA>::run(*sys, P, pos + t * 3 * NE, alpha[t], beta[t], ph, la, sink);
+    } else {     // primal pass into the derivative cache, then the sweep ON the cache (the N > 16 kernel path)
+      std::vector<double> scratch(DerivCache<NE, NA>::SIZE_GRAD);
+      DerivSplit<NE, NA>::template primal<false>(*sys, P, pos + t * 3 * NE, scratch.data(), 1, nullptr, ph, la);
+      ParamGrad<NE, NA>::run_cached(*sys, P, scratch.data(), 1, alpha[t], beta[t], sink);
+    }
   }
 }
 extern "C" int hc_param_grad(const AiqmcSystem* sys, const double* P, const double* pos, long n, const double* alpha,
-                             const double* beta, double* out) {
+                             const double* beta, double* out, int cached) {
 #define X(NE, NA) \
-  if (sys->n_elec == NE && sys->n_atoms == NA) { run_pgrad<NE, NA>(sys, P, pos, n, alpha, beta, out); return 0; }
+  if (sys->n_elec == NE && sys->n_atoms == NA) { run_pgrad<NE, NA>(sys, P, pos, n, alpha, beta, out, cached); return 0; }
   AIQMC_FOR_EACH_SYSTEM(X)
 #undef X
   return -1;

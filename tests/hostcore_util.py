@@ -40,7 +40,7 @@ def host_psi(lib, sys_struct, packed, pos, mode):
     return phase, logabs, grad, lap
 
 
-def host_param_grad(lib, sys_struct, packed, pos, alpha, beta):
+def host_param_grad(lib, sys_struct, packed, pos, alpha, beta, cached=False):
     """Per-walker d(alpha log|psi| + beta phase)/d(packed params), shape (ncfg, len(packed))."""
     n = sys_struct.n_elec
     pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3 * n)
@@ -48,6 +48,6 @@ def host_param_grad(lib, sys_struct, packed, pos, alpha, beta):
     out = np.zeros((ncfg, packed.size))
     rc = lib.hc_param_grad(C.byref(sys_struct), dptr(packed), dptr(pos), C.c_long(ncfg),
                            dptr(np.ascontiguousarray(alpha, dtype=np.float64)),
-                           dptr(np.ascontiguousarray(beta, dtype=np.float64)), dptr(out))
+                           dptr(np.ascontiguousarray(beta, dtype=np.float64)), dptr(out), C.c_int(1 if cached else 0))
     assert rc == 0, "no host instantiation for this (N, A)"
     return out

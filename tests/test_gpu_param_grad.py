@@ -56,11 +56,24 @@ def test_param_gradient_large_batch_linearity_and_empty():
     assert ge.shape == (eng.layout.total,) and float(ge.abs().max()) == 0.0
 
 
-def test_unsupported_large_system_fails_loudly():
-    case = Case(n=30, natoms=12, spins=[1.] * 15 + [-1.] * 15, seed=21, nwalkers=2, charges=[4.0] * 6 + [1.0] * 6)
+def test_benzene_param_gradient_runs_on_the_derivative_cache():
+    """N = 30 > 16 (BASELINE configs[4]): primal pass into the derivative cache + the sweep on the cache; every leaf
+    against torch autograd, and bit-reproducible."""
+    case = Case(n=30, natoms=12, spins=[1.] * 15 + [-1.] * 15, seed=21, nwalkers=35, charges=[4.0] * 6 + [1.0] * 6)
     eng = aiqmc_b200.WalkerEngine(case.spec(), case.params)
-    with pytest.raises(aiqmc_b200.lib.AiqmcError):
-        eng.param_grad(torch.tensor(case.pos), np.ones(2), np.zeros(2))
+    rng = np.random.default_rng(2)
+    alpha, beta = rng.normal(size=case.B), rng.normal(size=case.B)
+    g, ph, la = eng.param_grad(torch.tensor(case.pos), alpha, beta)
+    g2, _, _ = eng.param_grad(torch.tensor(case.pos), alpha, beta)
+    assert torch.equal(g, g2)
+    _, lat = case.net.apply(case.params, torch.tensor(case.pos), case.t_spins, case.t_atoms)
+    np.testing.assert_allclose(la.cpu().numpy(), lat.numpy(), rtol=1e-10)
+    got = dict(tree_leaves(aiqmc_b200.unpack_param_grad(eng.layout, g.cpu().numpy(), case.params, case.spec())))
+    ref = oracle_param_grad(case, case.pos, alpha, beta)
+    for key, r in ref.items():
+        if r.size:
+            np.testing.assert_allclose(np.asarray(got[key]).reshape(r.shape), r, rtol=1e-7,
+                                       atol=1e-8 * max(1.0, float(np.abs(r).max())), err_msg=key)
 
 
 @pytest.mark.parametrize("clip,median", [(0.0, True), (1.0, True), (1.0, False)])

@@ -68,6 +68,9 @@ def test_param_gradient_matches_autograd(hostlib, name):
             continue
         scale = max(1.0, float(np.abs(r).max()))
         np.testing.assert_allclose(g, r, rtol=1e-8, atol=1e-9 * scale, err_msg=key)
+    # the same sweep run ON the derivative cache (the kernels' path for N > 16): identical to rounding
+    pw_cached = H.host_param_grad(hostlib, case.spec().c_struct(), packed, case.pos, alpha, beta, cached=True)
+    np.testing.assert_allclose(pw_cached, per_walker, rtol=1e-11, atol=1e-12 * max(1.0, float(np.abs(per_walker).max())))
     # the phase has a branch cut but a smooth gradient: a pure-phase seed must work on its own
     pw_phase = H.host_param_grad(hostlib, case.spec().c_struct(), packed, case.pos, np.zeros(case.B), np.ones(case.B))
     ref_phase = oracle_param_grad(case, case.pos, np.zeros(case.B), np.ones(case.B))
@@ -77,3 +80,20 @@ def test_param_gradient_matches_autograd(hostlib, name):
             continue
         np.testing.assert_allclose(np.asarray(got_phase[key]).reshape(r.shape), r, rtol=1e-8,
                                    atol=1e-9 * max(1.0, float(np.abs(r).max())), err_msg=key)
+
+
+def test_benzene_param_gradient_on_the_cache_matches_autograd(hostlib):
+    """N = 30, A = 12 (BASELINE configs[4]): the cached sweep against torch autograd, every leaf."""
+    case = Case(n=30, natoms=12, spins=[1.] * 15 + [-1.] * 15, seed=21, nwalkers=2, charges=[4.0] * 6 + [1.0] * 6)
+    lay = aiqmc_b200.system.AiqmcLayout()
+    hostlib.hc_layout(30, 12, C.byref(lay))
+    packed = aiqmc_b200.pack_params(lay, case.params, case.spec())
+    alpha, beta = np.array([0.7, -1.3]), np.array([0.4, 0.9])
+    pw = H.host_param_grad(hostlib, case.spec().c_struct(), packed, case.pos, alpha, beta, cached=True)
+    got = dict(tree_leaves(aiqmc_b200.unpack_param_grad(lay, pw.sum(0), case.params, case.spec())))
+    ref = oracle_param_grad(case, case.pos, alpha, beta)
+    assert set(got) == set(ref)
+    for key, r in ref.items():
+        if r.size:
+            np.testing.assert_allclose(np.asarray(got[key]).reshape(r.shape), r, rtol=1e-7,
+                                       atol=1e-8 * max(1.0, float(np.abs(r).max())), err_msg=key)
