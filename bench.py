@@ -169,16 +169,47 @@ def random_rot(rng, B):
 # clocks sampling (B200_PROFILING.md recipe)
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region: an in-process NVML thread polling every 5 ms (the timed
+    region of the default run is ~0.1 s: `nvidia-smi -lms` starts too slowly to land a sample in it); nvidia-smi is
+    the fallback when pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.rows = []
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v for v in vis.split(",") if v.strip().isdigit()]
+        self.gpu = int(ids[gpu_index]) if gpu_index < len(ids) else gpu_index
+        self.rows = []          # (sm_mhz, max_mhz, set(reasons))
         self.proc = None
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _nvml_loop(self, nv, h):
+        masks = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.rows.append((sm, mx, {k for k, m in masks.items() if bits & m}))
+            except Exception:
+                pass
+            self._stop.wait(0.005)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self._thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self._thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -188,27 +219,28 @@ class ClockSampler:
             self.proc = None
 
     def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
             try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for k, name in enumerate(names):
-                    if r[5 + k].lower().startswith("active"):
-                        reasons.add(name)
+                self.rows.append((float(r[1]), float(r[2]),
+                                  {name for k, name in enumerate(names) if r[5 + k].lower().startswith("active")}))
             except Exception:
                 pass
-        if not sm:
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=1.0)
+        if self.proc is not None:
+            self.proc.terminate()
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        reasons = set()
+        for r in self.rows:
+            reasons |= r[2]
+        return {"sm_mhz": float(np.median([r[0] for r in self.rows])), "sm_max_mhz": float(max(r[1] for r in self.rows)),
+                "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
 # ------------------------------------------------------------------------------------------
