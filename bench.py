@@ -419,18 +419,18 @@ def run_gpu(args):
 
     def e2e_run(sets):
         nxt = prefetch(sets[0])
+        cur = torch.cuda.current_stream()
         for k in range(len(sets)):
             sd, done = nxt
-            if k + 1 < len(sets):
-                nxt = prefetch(sets[k + 1])
-            cur = torch.cuda.current_stream()
             cur.wait_event(done)
-            for v in sd.values():
-                v.record_stream(cur)
             p = pos_host.to(dev, non_blocking=True)
-            st = step(p, sd)
+            st = step(p, sd)                                # asynchronous launches
             pos_host.copy_(p, non_blocking=True)
             stats_host.copy_(st, non_blocking=True)
+            for v in sd.values():
+                v.record_stream(cur)
+            if k + 1 < len(sets):
+                nxt = prefetch(sets[k + 1])                 # host work and the copy overlap this step's kernels
             cur.synchronize()                               # the host reads positions + statistics of this step
 
     e2e_run(host_sets[:min(args.warmup, 3)])
