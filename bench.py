@@ -346,8 +346,10 @@ def run_gpu(args):
 
     e_l = torch.empty((B, 2), dtype=torch.float64, device=dev)
 
-    def step(pos, s, timed_quad=None):
+    def step(pos, s, timed_quad=None, after_sweep=None):
         eng.vmc_sweep(pos, s["gauss1"], s["gauss2"], s["rnd"], TSTEP, want_accept=False)
+        if after_sweep is not None:
+            after_sweep(pos)
         if timed_quad is None:
             eng.local_energy(pos, s["rot"], out=e_l)
         else:
@@ -417,6 +419,16 @@ def run_gpu(args):
             done.record(copy_stream)
         return sd, done
 
+    swept = torch.cuda.Event()
+
+    def pos_to_host(p):                  # the sweep is the last writer of the positions: copy them out on the copy
+        cur_ = torch.cuda.current_stream()   # stream while the local-energy kernels run
+        swept.record(cur_)
+        copy_stream.wait_event(swept)
+        with torch.cuda.stream(copy_stream):
+            pos_host.copy_(p, non_blocking=True)
+        p.record_stream(copy_stream)
+
     def e2e_run(sets):
         nxt = prefetch(sets[0])
         cur = torch.cuda.current_stream()
@@ -424,14 +436,14 @@ def run_gpu(args):
             sd, done = nxt
             cur.wait_event(done)
             p = pos_host.to(dev, non_blocking=True)
-            st = step(p, sd)                                # asynchronous launches
-            pos_host.copy_(p, non_blocking=True)
+            st = step(p, sd, after_sweep=pos_to_host)       # asynchronous launches; positions leave during the energy
             stats_host.copy_(st, non_blocking=True)
             for v in sd.values():
                 v.record_stream(cur)
             if k + 1 < len(sets):
                 nxt = prefetch(sets[k + 1])                 # host work and the copy overlap this step's kernels
             cur.synchronize()                               # the host reads positions + statistics of this step
+            copy_stream.synchronize()
 
     e2e_run(host_sets[:min(args.warmup, 3)])
     barrier()
