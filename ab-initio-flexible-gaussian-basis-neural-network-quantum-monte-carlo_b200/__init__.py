@@ -7,11 +7,11 @@ from .api import (AINetData, Network, PackedParams, branch, comput_S, compute_tm
                   make_ai_net, propose_drift_diffusion, random_rotations, total_energy, branch_global, make_loss,
                   clip_local_values, AuxiliaryLossData, make_mcmc_step, update_mcmc_width,
                   correlated_samples, weights_jacobian, read_ecp_nwchem)
-from .engine import WalkerEngine  # noqa: F401
+from .engine import HostStepPipeline, WalkerEngine  # noqa: F401
 from .system import SystemSpec, jastrow_indices_ee, make_ecp, pack_params, spin_indices_h, unpack_param_grad  # noqa: F401
 
 __all__ = ["AINetData", "Network", "PackedParams", "WalkerEngine", "SystemSpec", "make_ai_net", "main_monte_carlo",
            "local_energy", "propose_drift_diffusion", "comput_S", "compute_tmoves", "dmc_propagate", "estimate_energy", "reconfigure", "trial_energy", "branch", "make_ecp", "pack_params",
            "jastrow_indices_ee", "spin_indices_h", "random_rotations", "total_energy", "branch_global", "parallel", "GaussianBasis", "gto", "make_loss", "clip_local_values",
            "AuxiliaryLossData", "unpack_param_grad", "make_mcmc_step", "update_mcmc_width", "checkpoint", "correlated_samples",
-           "weights_jacobian", "read_ecp_nwchem"]
+           "weights_jacobian", "read_ecp_nwchem", "HostStepPipeline"]

@@ -248,3 +248,66 @@ class WalkerEngine:
                                                 _ptr(r), _ptr(uu), _ptr(rr), B, float(tstep), _ptr(out), _ptr(acc),
                                                 _ptr(sel), _ptr(ws), ws.numel(), _stream()), "aiqmc_dmc_tmove")
         return out, acc, sel
+
+
+class HostStepPipeline:
+    """VMC walker steps driven from HOST buffers (the end-to-end path bench.py times as `e2e`): every step copies its
+    inputs host -> device and its results device -> host, with the copies arranged around the kernels:
+      * the step's random arrays (gauss1, gauss2, rnd, rot) do not depend on the previous step: the set of step k+1
+        travels on a copy stream while step k computes, and the host issues that copy after launching step k's kernels
+        so that its own work hides behind them;
+      * the walker positions make a host round trip per step (they serialise the steps); the sweep is their last
+        writer, so they leave for the host while the local-energy kernels run;
+      * one synchronisation per step, when the host reads positions and energy statistics.
+    All host tensors must be pinned.  `reduce_stats`, if given, is applied to the 4-double statistics on the device
+    (e.g. a torch.distributed all-reduce) before they are copied out."""
+
+    def __init__(self, engine: WalkerEngine, tstep: float, reduce_stats=None):
+        self.eng, self.tstep, self.reduce_stats = engine, float(tstep), reduce_stats
+        self.copy_stream = torch.cuda.Stream(device=engine.device)
+        self.swept = torch.cuda.Event()
+        self.e_l = None
+
+    def _prefetch(self, host_set):
+        with torch.cuda.stream(self.copy_stream):
+            dev_set = {k: v.to(self.eng.device, non_blocking=True) for k, v in host_set.items()}
+            done = torch.cuda.Event()
+            done.record(self.copy_stream)
+        return dev_set, done
+
+    def run(self, pos_host: torch.Tensor, host_sets, stats_host: torch.Tensor) -> None:
+        """Runs len(host_sets) steps (sweep + local energy + statistics); pos_host (B,3N) is updated in place after
+        every step, stats_host (4,) holds [sum Re E, sum Im E, sum |E|^2, count] of the last step."""
+        eng, dev = self.eng, self.eng.device
+        B = pos_host.shape[0]
+        if self.e_l is None or self.e_l.shape[0] != B:
+            self.e_l = torch.empty((B, 2), dtype=torch.float64, device=dev)
+        if not host_sets:
+            return
+        cur = torch.cuda.current_stream(dev)
+        nxt = self._prefetch(host_sets[0])
+        for k in range(len(host_sets)):
+            s, done = nxt
+            cur.wait_event(done)
+            p = pos_host.to(dev, non_blocking=True)
+            eng.vmc_sweep(p, s["gauss1"], s["gauss2"], s["rnd"], self.tstep, want_accept=False)
+            self.swept.record(cur)
+            self.copy_stream.wait_event(self.swept)
+            with torch.cuda.stream(self.copy_stream):
+                pos_host.copy_(p, non_blocking=True)
+            p.record_stream(self.copy_stream)
+            if eng.ecp is not None:
+                eng.local_energy(p, s["rot"], out=self.e_l)
+                e = torch.view_as_complex(self.e_l)
+            else:
+                e = eng.local_energy(p)
+            stats = eng.energy_stats(e)
+            if self.reduce_stats is not None:
+                self.reduce_stats(stats)
+            stats_host.copy_(stats, non_blocking=True)
+            for v in s.values():
+                v.record_stream(cur)
+            if k + 1 < len(host_sets):
+                nxt = self._prefetch(host_sets[k + 1])
+            cur.synchronize()
+            self.copy_stream.synchronize()

@@ -346,10 +346,8 @@ def run_gpu(args):
 
     e_l = torch.empty((B, 2), dtype=torch.float64, device=dev)
 
-    def step(pos, s, timed_quad=None, after_sweep=None):
+    def step(pos, s, timed_quad=None):
         eng.vmc_sweep(pos, s["gauss1"], s["gauss2"], s["rnd"], TSTEP, want_accept=False)
-        if after_sweep is not None:
-            after_sweep(pos)
         if timed_quad is None:
             eng.local_energy(pos, s["rot"], out=e_l)
         else:
@@ -406,50 +404,16 @@ def run_gpu(args):
     h2d = sum(v.numel() * v.element_size() for v in host_sets[0].values()) + pos_host.numel() * 8
     d2h = pos_host.numel() * 8 + 32
 
-    # Every step copies its inputs host -> device and its results device -> host inside the timed region.  The
-    # walker positions make a round trip through host memory each step (they serialise the steps); the step's random
-    # arrays (38 of the 44.5 MB) do not depend on the previous step, so their copy for step k+1 is issued on a second
-    # stream while step k computes (CUDA streams + events, pinned buffers) -- the same bytes, overlapped.
-    copy_stream = torch.cuda.Stream(device=dev)
-
-    def prefetch(s):
-        with torch.cuda.stream(copy_stream):
-            sd = {k: v.to(dev, non_blocking=True) for k, v in s.items()}
-            done = torch.cuda.Event()
-            done.record(copy_stream)
-        return sd, done
-
-    swept = torch.cuda.Event()
-
-    def pos_to_host(p):                  # the sweep is the last writer of the positions: copy them out on the copy
-        cur_ = torch.cuda.current_stream()   # stream while the local-energy kernels run
-        swept.record(cur_)
-        copy_stream.wait_event(swept)
-        with torch.cuda.stream(copy_stream):
-            pos_host.copy_(p, non_blocking=True)
-        p.record_stream(copy_stream)
-
-    def e2e_run(sets):
-        nxt = prefetch(sets[0])
-        cur = torch.cuda.current_stream()
-        for k in range(len(sets)):
-            sd, done = nxt
-            cur.wait_event(done)
-            p = pos_host.to(dev, non_blocking=True)
-            st = step(p, sd, after_sweep=pos_to_host)       # asynchronous launches; positions leave during the energy
-            stats_host.copy_(st, non_blocking=True)
-            for v in sd.values():
-                v.record_stream(cur)
-            if k + 1 < len(sets):
-                nxt = prefetch(sets[k + 1])                 # host work and the copy overlap this step's kernels
-            cur.synchronize()                               # the host reads positions + statistics of this step
-            copy_stream.synchronize()
-
-    e2e_run(host_sets[:min(args.warmup, 3)])
+    # Every step copies its inputs host -> device and its results device -> host inside the timed region, through the
+    # package's own host-buffer entry point (aiqmc_b200.HostStepPipeline: the next step's random arrays travel on a
+    # copy stream while this step computes, the positions leave for the host right after the sweep, one
+    # synchronisation per step when the host reads positions + statistics).
+    pipe = aiqmc_b200.HostStepPipeline(eng, TSTEP, reduce_stats=(lambda st: dist.all_reduce(st)) if world > 1 else None)
+    pipe.run(pos_host, host_sets[:min(args.warmup, 3)], stats_host)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    e2e_run(host_sets[args.warmup:args.warmup + args.steps])
+    pipe.run(pos_host, host_sets[args.warmup:args.warmup + args.steps], stats_host)
     ev1.record()
     barrier()
     t_e2e = torch.tensor([ev0.elapsed_time(ev1) / 1e3], dtype=torch.float64, device=dev)

@@ -81,3 +81,28 @@ def test_gradient_and_laplacian_paths_agree_at_full_size(setup):
     np.testing.assert_allclose(g1.cpu().numpy(), g2.cpu().numpy(), rtol=1e-8, atol=1e-9)
     np.testing.assert_allclose(la1.cpu().numpy(), la2.cpu().numpy(), rtol=1e-13, atol=1e-13)
     np.testing.assert_allclose(la0.cpu().numpy(), la2.cpu().numpy(), rtol=1e-12, atol=1e-12)
+
+
+def test_host_step_pipeline_matches_device_resident_steps():
+    """aiqmc_b200.HostStepPipeline (host buffers in / out every step, copies overlapped with the kernels) gives exactly
+    the positions and statistics of the same steps run on device-resident data."""
+    import bench
+    B, nsteps = 4096, 3
+    case, tabs = bench.build_case(B)
+    eng = aiqmc_b200.WalkerEngine(case.spec(), case.params, ecp=aiqmc_b200.make_ecp(1, list_l=2, **tabs))
+    rng = np.random.default_rng(3)
+    host_sets = []
+    for _ in range(nsteps):
+        r = bench.make_rand(rng, B, case.n, bench.TSTEP)
+        r["rot"] = bench.random_rot(rng, B)
+        host_sets.append({k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in r.items()})
+    pos_host = torch.from_numpy(case.pos.copy()).pin_memory()
+    stats_host = torch.empty(4, dtype=torch.float64).pin_memory()
+    aiqmc_b200.HostStepPipeline(eng, bench.TSTEP).run(pos_host, host_sets, stats_host)
+    pos = torch.from_numpy(case.pos.copy()).cuda()
+    for s in host_sets:
+        d = {k: v.cuda() for k, v in s.items()}
+        eng.vmc_sweep(pos, d["gauss1"], d["gauss2"], d["rnd"], bench.TSTEP, want_accept=False)
+        stats = eng.energy_stats(eng.local_energy(pos, d["rot"]))
+    assert torch.equal(pos.cpu(), pos_host)
+    assert torch.equal(stats.cpu(), stats_host)
