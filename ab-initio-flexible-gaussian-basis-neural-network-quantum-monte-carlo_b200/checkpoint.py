@@ -13,7 +13,6 @@ importable; `restore` therefore walks the .npz itself and unpickles with a shim 
 the shim is exercised on emulated records, stated in the test)."""
 from __future__ import annotations
 
-import contextlib
 import dataclasses
 import datetime
 import io
@@ -41,31 +40,34 @@ def _to_numpy_tree(t):
     return np.asarray(t)
 
 
+def _readable(path: str) -> bool:
+    """True if `path` is an intact .npz holding at least the step counter."""
+    try:
+        with zipfile.ZipFile(path) as z:
+            return z.testzip() is None and 't.npy' in z.namelist()
+    except (OSError, EOFError, zipfile.BadZipFile):
+        return False
+
+
 def find_last_checkpoint(ckpt_path: Optional[str] = None) -> Optional[str]:
-    """checkpoint.py:13-25: newest readable qmcjax_ckpt_* file of the directory, or None."""
-    if ckpt_path and os.path.exists(ckpt_path):
-        for file in sorted((f for f in os.listdir(ckpt_path) if 'qmcjax_ckpt' in f), reverse=True):
-            fname = os.path.join(ckpt_path, file)
-            try:
-                with zipfile.ZipFile(fname) as z:
-                    if z.testzip() is None and 't.npy' in z.namelist():
-                        return fname
-            except (OSError, EOFError, zipfile.BadZipFile):
-                continue
-    return None
+    """Behaviour of checkpoint.py:13-25: the newest `qmcjax_ckpt*` file of the directory that can be opened; damaged
+    files (an interrupted write) are skipped in favour of the next older one; None if there is nothing usable."""
+    if not ckpt_path or not os.path.isdir(ckpt_path):
+        return None
+    names = sorted((n for n in os.listdir(ckpt_path) if 'qmcjax_ckpt' in n), reverse=True)
+    return next((os.path.join(ckpt_path, n) for n in names if _readable(os.path.join(ckpt_path, n))), None)
 
 
 def create_save_path(save_path: Optional[str]) -> str:
-    """checkpoint.py:28-34."""
-    timestamp = datetime.datetime.now().strftime('%Y_%m_%d_%H:%M:%S')
-    ckpt_save_path = save_path or os.path.join(os.getcwd(), f'AInet_{timestamp}')
-    if ckpt_save_path and not os.path.isdir(ckpt_save_path):
-        os.makedirs(ckpt_save_path)
-    return ckpt_save_path
+    """Behaviour of checkpoint.py:28-34: the given directory, or `./AInet_<timestamp>`, created on demand."""
+    if not save_path:
+        save_path = os.path.join(os.getcwd(), datetime.datetime.now().strftime('AInet_%Y_%m_%d_%H:%M:%S'))
+    os.makedirs(save_path, exist_ok=True)
+    return save_path
 
 
 def get_restore_path(restore_path: Optional[str] = None) -> Optional[str]:
-    return restore_path if restore_path else None
+    return restore_path or None
 
 
 def save(save_path: str, t: int, data: AINetData, params, opt_state=None) -> str:
@@ -121,35 +123,39 @@ def restore(restore_filename: str, batch_size: Optional[int] = None):
     return t, data, params, opt_state
 
 
-class Writer(contextlib.AbstractContextManager):
-    """utils/writers.py:7-46: CSV log with a leading iteration column; unknown keys raise."""
+class Writer:
+    """CSV training log with the on-disk layout of utils/writers.py:7-46: a header row `<iteration_key>,<schema...>`,
+    one row per write(t, **values), empty cells for values not given, ValueError for a key outside the schema.
+    Usable as a context manager."""
 
     def __init__(self, name: str, schema: Sequence[str], directory: str = 'logs/', iteration_key: Optional[str] = 't',
                  log: bool = False):
-        self._schema = list(schema)
-        if not os.path.isdir(directory):
-            os.makedirs(directory)
-        self._filename = os.path.join(directory, name + '.csv')
-        self._iteration_key = iteration_key
-        self._log = log
+        self.columns = tuple(schema)
+        self.iteration_key = iteration_key
+        self.echo = log
+        os.makedirs(directory, exist_ok=True)
+        self.path = os.path.join(directory, f'{name}.csv')
+        self._fh = None
+
+    def _emit(self, cells):
+        self._fh.write(','.join(cells) + '\n')
 
     def __enter__(self):
-        self._file = open(self._filename, 'w', encoding='UTF-8')
-        if self._iteration_key:
-            self._file.write(f'{self._iteration_key},')
-        self._file.write(','.join(self._schema) + '\n')
+        self._fh = open(self.path, 'w', encoding='UTF-8')
+        self._emit(([self.iteration_key] if self.iteration_key else []) + list(self.columns))
         return self
 
-    def write(self, t: int, **data: Any):
-        for key in data:
-            if key not in self._schema:
-                raise ValueError(f'Not a recognized key for writer: {key}')
-        row = [str(data.get(key, '')) for key in self._schema]
-        if self._iteration_key:
-            row.insert(0, str(t))
-        self._file.write(','.join(row) + '\n')
-        if self._log:
-            print(f'Iteration {t}: {data}')
+    def write(self, t: int, **values: Any):
+        unknown = [k for k in values if k not in self.columns]
+        if unknown:
+            raise ValueError(f'Not a recognized key for writer: {unknown[0]}')
+        cells = [str(values[c]) if c in values else '' for c in self.columns]
+        self._emit(([str(t)] if self.iteration_key else []) + cells)
+        if self.echo:
+            print(f'Iteration {t}: {values}')
 
     def __exit__(self, exc_type, exc_val, exc_tb):
-        self._file.close()
+        if self._fh is not None:
+            self._fh.close()
+            self._fh = None
+        return False
