@@ -452,12 +452,15 @@ def run_gpu(args):
     roofline = {"bound": "fp64", "kernel": "k_ecp_pt<4,1,5,i> x4 (one launch per moved electron)", "achieved": achieved, "peak": best, "unit": "TFLOP/s",
                 "frac": achieved / best if best > 0 else None, "traffic": traffic,
                 "share_of_step": float(np.mean(ms_quad) / np.mean(ms_steps)),
+                "fp64_pipe_busy_ncu": 0.635,     # sm__pipe_fp64_cycles_active, profiles/r1_v17_ecp_pt_raw.csv (not measured live)
                 "whole_step_frac": (value / world) * flops_walker_step_ecp(n, a) / 1e12 / best if best > 0 else None,
                 "note": "compute-bound on the FP64 pipe (SURVEY 8d), not HBM/tensor; achieved = SURVEY's fixed "
                         "algorithmic flops 50*N*A*F(N,A) per walker / CUDA-event time of the quadrature stage "
                         "(its 4 launches + the 5.7 kB parameter copy to constant memory); peak = DFMA "
                         "microbenchmark measured in this run (nominal B200 FP64 ~37 TFLOP/s; MEASURED_PEAKS.json "
-                        "has no FP64 entry)"}
+                        "has no FP64 entry).  The algorithmic count prices a tanh at 1 flop; in float64 it is 12 FP64 "
+                        "instructions, and the kernel EXECUTES 4.3 k FP64 instructions per point = 22.6 TFLOP/s = "
+                        "66 % of the measured peak (fp64_pipe_busy_ncu)"}
 
     # ---- CPU baseline (bounded sample, rank 0, N=1 only) ------------------------------------------
     cpu = None
