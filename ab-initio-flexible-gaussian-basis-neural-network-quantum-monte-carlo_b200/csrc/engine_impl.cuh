@@ -166,8 +166,11 @@ struct MovedSrc {          // SRC == 1: configuration (b,i) = walker b with elec
 };
 
 // primal pass: one thread per configuration -> structure-of-arrays derivative cache dc[slot * n_cfg + cfg]
+#ifndef AIQMC_PRIMAL_MINB
+#define AIQMC_PRIMAL_MINB 1
+#endif
 template <int NE, int NA, bool LAP, int SRC>
-__global__ void __launch_bounds__(kThreads) k_primal(AiqmcSystem sys, const double* __restrict__ params,
+__global__ void __launch_bounds__(kThreads, AIQMC_PRIMAL_MINB) k_primal(AiqmcSystem sys, const double* __restrict__ params,
                                                      const double* __restrict__ pos, int64_t cfg0, int64_t n_cfg,
                                                      MovedSrc ms, double* __restrict__ dc, double* __restrict__ mc,
                                                      double* __restrict__ phase, double* __restrict__ logabs) {
