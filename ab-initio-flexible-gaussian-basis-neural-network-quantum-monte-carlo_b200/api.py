@@ -189,12 +189,11 @@ def local_energy(f, charges, nspins=None, use_scan: bool = False, complex_output
 
     def _e_l(params, key, data: AINetData):
         eng = _engine_of(f, params, data)
-        eng.ecp = ecp
         pos = _positions(eng, data)
         rot = None
         if ecp is not None:
             rot = key if not isinstance(key, (int, np.integer)) else random_rotations(pos.shape[0], int(key), eng.device)
-        return eng.local_energy(pos, rot), None
+        return eng.local_energy(pos, rot, ecp=ecp), None       # this closure's table; the shared engine is not mutated
     _e_l.engine_of = lambda params, data: _engine_of(f, params, data)
     return _e_l
 
@@ -457,17 +456,25 @@ def compute_tmoves(list_l, tstep: float, nelectrons: int, natoms: int, ndim: int
 
     def calculate_ratio_weight_tmoves(data: AINetData, params, key):
         eng = _engine_of(lognetwork, params, data)
-        eng.ecp = ecp
         pos = _positions(eng, data)
-        new_pos, acceptance, _ = eng.dmc_tmove(pos, key['rot'], key['u'], key['rnd'], tstep)
+        new_pos, acceptance, _ = eng.dmc_tmove(pos, key['rot'], key['u'], key['rnd'], tstep, ecp=ecp)
         return new_pos, acceptance
     return calculate_ratio_weight_tmoves
 
 
+def _real_scalar(x) -> float:
+    """jnp.real(x) of a python / numpy / torch scalar (ccECP energies are complex, quirk Q25)."""
+    if isinstance(x, torch.Tensor):
+        x = x.detach().reshape(-1)[0]
+        return float(x.real if x.is_complex() else x)
+    return float(np.real(x))
+
+
 def comput_S(engine: WalkerEngine, e_trial, e_est, branchcut, drift, tau, eloc, process_group=None):
     """DMC/S_matrix.py:4-25; `drift` is the limited drift whose square the reference passes as v2."""
-    m = parallel.allreduce_min(engine.dmc_ecut_min(eloc, float(e_est), branchcut), process_group)   # quirk Q20
-    return engine.dmc_s(eloc, drift, float(e_trial), float(e_est), m, tau)
+    e_est, e_trial = _real_scalar(e_est), _real_scalar(e_trial)          # S_matrix.py:18-20 takes jnp.real of all three
+    m = parallel.allreduce_min(engine.dmc_ecut_min(eloc, e_est, branchcut), process_group)   # quirk Q20
+    return engine.dmc_s(eloc, drift, e_trial, e_est, m, tau)
 
 
 def branch(engine: WalkerEngine, weights: torch.Tensor, key):

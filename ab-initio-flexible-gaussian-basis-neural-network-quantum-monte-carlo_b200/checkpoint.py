@@ -31,6 +31,8 @@ def _to_numpy_tree(t):
         return _to_numpy_tree(dataclasses.asdict(t))
     if isinstance(t, dict):
         return {k: _to_numpy_tree(v) for k, v in t.items()}
+    if isinstance(t, tuple) and hasattr(t, "_fields"):          # NamedTuple node (optax / kfac optimiser states)
+        return type(t)(*(_to_numpy_tree(v) for v in t))
     if isinstance(t, (list, tuple)):
         return type(t)(_to_numpy_tree(v) for v in t)
     if hasattr(t, "detach"):                      # torch tensor (device or host)

@@ -2,6 +2,7 @@
 // (n_elec, n_atoms) into the per-system translation units, plus the system-size independent
 // kernels (energy statistics, DMC S / weights / comb / gather).
 #include <cuda_runtime.h>
+#include <atomic>
 #include <math.h>
 #include <string.h>
 
@@ -11,8 +12,8 @@
 #include "psi_core.cuh"
 
 namespace aiqmc {
-int g_last_cuda_error = 0;
-int64_t g_launch_count = 0;
+std::atomic<int> g_last_cuda_error{0};
+std::atomic<int64_t> g_launch_count{0};
 
 int64_t sweep_ws_bytes_rt(int n, int a, int64_t B);
 int64_t energy_ws_bytes_rt(int n, int a, int64_t B, int with_ecp);

@@ -7,8 +7,10 @@
 // shared memory and read as warp-wide broadcasts.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <string.h>
 
+#include <mutex>
 #include <utility>
 
 #include "fastmath.cuh"
@@ -867,8 +869,8 @@ static __global__ void k_reduce_param_partials(const double* __restrict__ partia
     if (e_ != cudaSuccess) { g_last_cuda_error = (int)e_; return AIQMC_E_CUDA; } \
   } while (0)
 
-extern int g_last_cuda_error;
-extern int64_t g_launch_count;      // kernels launched by this library (aiqmc_launch_count)
+extern std::atomic<int> g_last_cuda_error;
+extern std::atomic<int64_t> g_launch_count;      // kernels launched by this library (aiqmc_launch_count)
 
 template <int NE, int NA>
 struct Launch {
@@ -881,6 +883,47 @@ struct Launch {
   static cudaError_t prep(K kernel) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
   }
+
+  // This instantiation's __constant__ copies (c_ecp, c_par, c_uni) are ONE set per device, shared by every engine
+  // and every stream of the process.  ConstScope makes their use safe: it serialises the host threads of the process
+  // on a mutex, keeps the "what was uploaded last" record PER DEVICE (a second engine on another GPU re-uploads),
+  // and orders streams -- a caller on stream S first waits for the event recorded behind the previous user's last
+  // kernel (uploaded table still being read, or upload still in flight, on another stream), and records its own
+  // event when it leaves.  Two engines with different parameters on two streams therefore interleave correctly
+  // (tests/test_gpu_streams.py); they serialise only at the kernels that read constant memory.
+  struct ConstSlot {
+    bool has_ev = false, ecp_valid = false;
+    cudaEvent_t ev{};
+    cudaStream_t last{};
+    AiqmcEcp ecp;
+  };
+  struct ConstScope {
+    static constexpr int kMaxDev = 64;
+    std::unique_lock<std::mutex> lock;
+    ConstSlot* slot = nullptr;
+    cudaStream_t st;
+    static std::mutex& mu() { static std::mutex m; return m; }
+    explicit ConstScope(cudaStream_t s) : lock(mu()), st(s) {
+      static ConstSlot slots[kMaxDev];
+      int dev = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return;
+      slot = &slots[dev];
+      if (slot->has_ev && slot->last != st) cudaStreamWaitEvent(st, slot->ev, 0);
+    }
+    ~ConstScope() {
+      if (!slot) return;
+      if (!slot->has_ev && cudaEventCreateWithFlags(&slot->ev, cudaEventDisableTiming) == cudaSuccess) slot->has_ev = true;
+      if (slot->has_ev) cudaEventRecord(slot->ev, st);
+      slot->last = st;
+    }
+    cudaError_t upload_ecp(const AiqmcEcp* ecp) {
+      if (slot && slot->ecp_valid && memcmp(&slot->ecp, ecp, sizeof(AiqmcEcp)) == 0) return cudaSuccess;
+      const cudaError_t e = cudaMemcpyToSymbolAsync(c_ecp, ecp, sizeof(AiqmcEcp), 0, cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) return e;
+      if (slot) { slot->ecp = *ecp; slot->ecp_valid = true; }
+      return cudaSuccess;
+    }
+  };
 
   // One chunked sweep of the two derivative passes over n_cfg configurations (deriv_split.cuh).
   //   SRC/OUT as in k_primal / k_tangent.  partials (may be null): block partials of sum g^2 go to rows
@@ -1071,7 +1114,8 @@ struct Launch {
       ++g_launch_count;
       k_energy_rest<NE, NA, false><<<g1, kThreads, kSmem, st>>>(*sys, params, pos, nullptr, B, e_l, w);
     } else {
-      AQ_CUDA_OK(upload_ecp(ecp, st));
+      ConstScope cs(st);
+      AQ_CUDA_OK(cs.upload_ecp(ecp));
       if (stages & 1) {
         AQ_CUDA_OK(prep(k_energy_rest<NE, NA, true>));
         const int rc = deriv<true, 0, 0>(sys, params, pos, B, ms, w.dcache, w.cache, w.phase, w.logabs, w.grad,
@@ -1141,7 +1185,8 @@ struct Launch {
     if (ws_bytes < tmove_ws_bytes(NE, NA, B)) return AIQMC_E_WORKSPACE;
     EnergyWs w = carve_energy_ws(ws, NE, NA, B, 1);
     double* tm = (double*)((char*)ws + energy_ws_bytes(NE, NA, B, 1));
-    AQ_CUDA_OK(upload_ecp(ecp, st));
+    ConstScope cs(st);
+    AQ_CUDA_OK(cs.upload_ecp(ecp));
     const unsigned g1 = (unsigned)((B + kThreads - 1) / kThreads);
     AQ_CUDA_OK(prep(k_tmove_prep<NE, NA>));
     ++g_launch_count;
@@ -1219,18 +1264,6 @@ struct Launch {
       AQ_CUDA_OK(cudaGetLastError());
       return AIQMC_OK;
     }
-  }
-
-  static cudaError_t upload_ecp(const AiqmcEcp* ecp, cudaStream_t st) {
-    static AiqmcEcp h_ecp;                 // last table uploaded to this TU's __constant__ copy
-    static bool h_valid = false;
-    if (!h_valid || memcmp(&h_ecp, ecp, sizeof(AiqmcEcp)) != 0) {
-      const cudaError_t e = cudaMemcpyToSymbolAsync(c_ecp, ecp, sizeof(AiqmcEcp), 0, cudaMemcpyHostToDevice, st);
-      if (e != cudaSuccess) return e;
-      h_ecp = *ecp;
-      h_valid = true;
-    }
-    return cudaSuccess;
   }
 
   static const OpsTable* table() {

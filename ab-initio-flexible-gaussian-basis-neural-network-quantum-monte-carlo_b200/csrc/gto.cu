@@ -10,14 +10,15 @@
 // and the loop over shells is uniform across the warp.  HBM-bound: 24 B in, 40 B out per (point, AO); exponentials
 // are the in-house fexp (10 FP64 ops) shared by value / gradient / Laplacian of a primitive.
 #include <cuda_runtime.h>
+#include <atomic>
 #include <string.h>
 
 #include "../../include/aiqmc_b200.h"
 #include "fastmath.cuh"
 
 namespace aiqmc {
-extern int g_last_cuda_error;
-extern int64_t g_launch_count;
+extern std::atomic<int> g_last_cuda_error;
+extern std::atomic<int64_t> g_launch_count;
 
 struct GtoTable {
   int32_t n_shells, n_centres;

@@ -23,6 +23,16 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_UNSET = object()
+
+
+def _nbytes(rc: int, what: str) -> int:
+    """A *_workspace_bytes query returns the size, or a negative AIQMC_E_* code."""
+    if rc < 0:
+        _lib.check(int(rc), what)
+    return int(rc)
+
+
 class WalkerEngine:
     """Owns the packed parameters + workspaces of one system on one GPU."""
 
@@ -60,6 +70,16 @@ class WalkerEngine:
         t = torch.as_tensor(pos)
         return t.to(device=self.device, dtype=torch.float64).contiguous()
 
+    def _arg(self, t, shape, name: str, dtype=torch.float64) -> torch.Tensor:
+        """Every tensor whose pointer crosses the ABI: on this engine's device, `dtype`, contiguous, exact shape
+        (converted when it is not; a wrong element count raises instead of reading out of bounds in the kernel)."""
+        t = torch.as_tensor(t)
+        if t.numel() != int(np.prod(shape)):
+            raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+        if t.device != self.device or t.dtype != dtype or not t.is_contiguous() or tuple(t.shape) != tuple(shape):
+            t = t.to(device=self.device, dtype=dtype).reshape(shape).contiguous()
+        return t
+
     # ---- wavefunction -----------------------------------------------------------------
     def psi(self, pos, mode: int = 0):
         """mode 0: (phase, logabs); 1: + grad; 2: + grad, lap.  pos (..., 3N)."""
@@ -73,7 +93,8 @@ class WalkerEngine:
         lap = torch.empty_like(phase) if mode == 2 else None
         ws = None
         if mode >= 1:
-            ws = self._workspace("psi", self.lib.aiqmc_psi_workspace_bytes(C.byref(self.sys), ncfg, 1 if mode == 2 else 0))
+            ws = self._workspace("psi", _nbytes(self.lib.aiqmc_psi_workspace_bytes(C.byref(self.sys), ncfg, 1 if mode == 2 else 0),
+                                                "aiqmc_psi_workspace_bytes"))
         with torch.cuda.device(self.device):
             if mode == 0:
                 rc = self.lib.aiqmc_psi_fwd(C.byref(self.sys), _ptr(self.params_dev), _ptr(p2), ncfg, _ptr(phase),
@@ -98,8 +119,13 @@ class WalkerEngine:
                   want_drift: bool = False, want_aux: bool = False):
         """In-place sweep on pos (B,3N) float64 cuda.  Returns dict(accept, grad_eff_old, aux)."""
         B = pos.shape[0]
-        assert pos.is_cuda and pos.dtype == torch.float64 and pos.is_contiguous()
-        nbytes = self.lib.aiqmc_vmc_workspace_bytes(C.byref(self.sys), B)
+        if not (pos.is_cuda and pos.device == self.device and pos.dtype == torch.float64 and pos.is_contiguous()
+                and tuple(pos.shape) == (B, 3 * self.n)):
+            raise ValueError("vmc_sweep updates pos in place: it must be a contiguous float64 (B,3N) tensor on the engine's device")
+        gauss1 = self._arg(gauss1, (B, 3 * self.n), "gauss1")
+        gauss2 = self._arg(gauss2, (B, self.n, 3 * self.n), "gauss2")
+        rnd = self._arg(rnd, (B, self.n), "rnd")
+        nbytes = _nbytes(self.lib.aiqmc_vmc_workspace_bytes(C.byref(self.sys), B), "aiqmc_vmc_workspace_bytes")
         ws = self._workspace("vmc", nbytes)
         accept = torch.empty((B, self.n), dtype=torch.uint8, device=self.device) if want_accept else None
         drift = torch.empty((B, 3 * self.n), dtype=torch.float64, device=self.device) if want_drift else None
@@ -114,20 +140,27 @@ class WalkerEngine:
 
     # ---- local energy -----------------------------------------------------------------
     def local_energy(self, pos: torch.Tensor, rot: Optional[torch.Tensor] = None, stages: int = 7,
-                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """All-electron (no ECP table): real (B,).  ccECP: complex128 (B,) (quirk Q25)."""
+                     out: Optional[torch.Tensor] = None, ecp=_UNSET) -> torch.Tensor:
+        """All-electron (no ECP table): real (B,).  ccECP: complex128 (B,) (quirk Q25).  `ecp` overrides the engine's
+        table for this call only (None = all-electron); closures pass their own table instead of mutating the engine."""
         p = self._pos(pos).reshape(-1, 3 * self.n)
         B = p.shape[0]
-        with_ecp = self.ecp is not None
-        nbytes = self.lib.aiqmc_energy_workspace_bytes(C.byref(self.sys), B, 1 if with_ecp else 0)
+        ecp_tab = self.ecp if ecp is _UNSET else ecp
+        with_ecp = ecp_tab is not None
+        nbytes = _nbytes(self.lib.aiqmc_energy_workspace_bytes(C.byref(self.sys), B, 1 if with_ecp else 0),
+                         "aiqmc_energy_workspace_bytes")
         ws = self._workspace("energy", nbytes)
         with torch.cuda.device(self.device):
             if with_ecp:
                 if rot is None:
                     raise ValueError("ccECP local energy needs the per-walker rotation matrices (B,3,3)")
-                r = torch.as_tensor(rot).to(device=self.device, dtype=torch.float64).reshape(B, 9).contiguous()
+                r = self._arg(rot, (B, 9), "rot")
                 e = out if out is not None else torch.empty((B, 2), dtype=torch.float64, device=self.device)
-                rc = self.lib.aiqmc_local_energy_ecp_stages(C.byref(self.sys), C.byref(self.ecp),
+                if out is not None:
+                    e = self._arg(out, (B, 2), "out")
+                    if e.data_ptr() != out.data_ptr():
+                        raise ValueError("out must be a contiguous float64 (B,2) tensor on the engine's device")
+                rc = self.lib.aiqmc_local_energy_ecp_stages(C.byref(self.sys), C.byref(ecp_tab),
                                                             _ptr(self.params_dev), _ptr(p), _ptr(r), B, _ptr(e),
                                                             _ptr(ws), ws.numel(), int(stages), _stream())
                 _lib.check(rc, "aiqmc_local_energy_ecp")
@@ -154,6 +187,7 @@ class WalkerEngine:
     def dmc_ecut_min(self, e_l: torch.Tensor, e_est: float, branchcut: torch.Tensor) -> torch.Tensor:
         raw, stride = (torch.view_as_real(e_l.contiguous()), 2) if e_l.is_complex() else (e_l.contiguous(), 1)
         out = torch.empty(1, dtype=torch.float64, device=self.device)
+        branchcut = self._arg(branchcut, (e_l.shape[0],), "branchcut")
         with torch.cuda.device(self.device):
             _lib.check(self.lib.aiqmc_dmc_ecut_min(_ptr(raw), stride, e_l.shape[0], float(e_est), _ptr(branchcut),
                                                    _ptr(out), _stream()), "aiqmc_dmc_ecut_min")
@@ -164,21 +198,28 @@ class WalkerEngine:
         raw, stride = (torch.view_as_real(e_l.contiguous()), 2) if e_l.is_complex() else (e_l.contiguous(), 1)
         B = e_l.shape[0]
         s = torch.empty(B, dtype=torch.float64, device=self.device)
+        drift = self._arg(drift, (B, 3 * self.n), "drift")
+        ecut_min = self._arg(ecut_min, (1,), "ecut_min")
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.aiqmc_dmc_s(_ptr(raw), stride, _ptr(drift.contiguous()), B, self.n, float(e_trial),
+            _lib.check(self.lib.aiqmc_dmc_s(_ptr(raw), stride, _ptr(drift), B, self.n, float(e_trial),
                                             float(e_est), _ptr(ecut_min), float(tau), _ptr(s), _stream()),
                        "aiqmc_dmc_s")
         return s
 
     def dmc_weights(self, weights: torch.Tensor, s_old: torch.Tensor, s_new: torch.Tensor, tau: float,
                     tdamp: float) -> None:
+        B = weights.shape[0]
+        if not (weights.device == self.device and weights.dtype == torch.float64 and weights.is_contiguous()):
+            raise ValueError("dmc_weights updates weights in place: contiguous float64 on the engine's device")
+        s_old, s_new = self._arg(s_old, (B,), "s_old"), self._arg(s_new, (B,), "s_new")
         with torch.cuda.device(self.device):
             _lib.check(self.lib.aiqmc_dmc_weights(_ptr(weights), _ptr(s_old), _ptr(s_new), weights.shape[0],
                                                   float(tau), float(tdamp), _stream()), "aiqmc_dmc_weights")
 
     def branch_comb(self, weights: torch.Tensor, u: float):
         B = weights.shape[0]
-        ws = self._workspace("branch", self.lib.aiqmc_branch_workspace_bytes(B))
+        weights = self._arg(weights, (B,), "weights")
+        ws = self._workspace("branch", _nbytes(self.lib.aiqmc_branch_workspace_bytes(B), "aiqmc_branch_workspace_bytes"))
         inds = torch.empty(B, dtype=torch.int32, device=self.device)
         neww = torch.empty(1, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
@@ -203,9 +244,7 @@ class WalkerEngine:
         B = p.shape[0]
         cv = lambda a: torch.as_tensor(a).to(device=self.device, dtype=torch.float64).reshape(B).contiguous()
         al, be = cv(alpha), cv(beta)
-        nbytes = self.lib.aiqmc_param_grad_workspace_bytes(C.byref(self.sys), B)
-        if nbytes < 0:
-            _lib.check(int(nbytes), "aiqmc_param_grad_workspace_bytes")
+        nbytes = _nbytes(self.lib.aiqmc_param_grad_workspace_bytes(C.byref(self.sys), B), "aiqmc_param_grad_workspace_bytes")
         ws = self._workspace("pgrad", nbytes)
         g = torch.empty(self.layout.total, dtype=torch.float64, device=self.device)
         ph = torch.empty(B, dtype=torch.float64, device=self.device)
@@ -223,7 +262,11 @@ class WalkerEngine:
         B = pos.shape[0]
         cv = lambda a, shape: torch.as_tensor(a).to(device=self.device, dtype=torch.float64).reshape(shape).contiguous()
         nz, uu = cv(noise, (B, 3 * self.n)), cv(u, (B,))
-        ws = self._workspace("mh", self.lib.aiqmc_mh_workspace_bytes(C.byref(self.sys), B))
+        for name, t, shape, dt in (("pos", pos, (B, 3 * self.n), torch.float64), ("lp", lp, (B,), torch.float64),
+                                   ("num_accepts", num_accepts, (), torch.int64)):
+            if not (t.device == self.device and t.dtype == dt and t.is_contiguous() and tuple(t.shape) == shape):
+                raise ValueError(f"mh_step updates {name} in place: contiguous {dt} {shape} on the engine's device")
+        ws = self._workspace("mh", _nbytes(self.lib.aiqmc_mh_workspace_bytes(C.byref(self.sys), B), "aiqmc_mh_workspace_bytes"))
         acc = torch.empty(B, dtype=torch.uint8, device=self.device) if want_accept else None
         with torch.cuda.device(self.device):
             _lib.check(self.lib.aiqmc_mh_step(C.byref(self.sys), _ptr(self.params_dev), _ptr(pos), _ptr(lp), _ptr(nz),
@@ -231,20 +274,24 @@ class WalkerEngine:
                                               _ptr(num_accepts), _ptr(ws), ws.numel(), _stream()), "aiqmc_mh_step")
         return acc
 
-    def dmc_tmove(self, pos: torch.Tensor, rot: torch.Tensor, u: torch.Tensor, rnd: torch.Tensor, tstep: float):
-        """DMC/Tmoves.py:32-225 for the whole batch: (new positions (B,3N), acceptance (B,N), selected move (B,N))."""
-        if self.ecp is None:
-            raise ValueError("T-moves need the ccECP tables (engine.ecp)")
+    def dmc_tmove(self, pos: torch.Tensor, rot: torch.Tensor, u: torch.Tensor, rnd: torch.Tensor, tstep: float,
+                  ecp=None):
+        """DMC/Tmoves.py:32-225 for the whole batch: (new positions (B,3N), acceptance (B,N), selected move (B,N)).
+        `ecp` overrides the engine's table for this call only."""
+        ecp_tab = ecp if ecp is not None else self.ecp
+        if ecp_tab is None:
+            raise ValueError("T-moves need the ccECP tables (engine.ecp or the ecp argument)")
         p = self._pos(pos).reshape(-1, 3 * self.n)
         B = p.shape[0]
         cv = lambda a, shape: torch.as_tensor(a).to(device=self.device, dtype=torch.float64).reshape(shape).contiguous()
         r, uu, rr = cv(rot, (B, 9)), cv(u, (B,)), cv(rnd, (B, self.n))
-        ws = self._workspace("tmove", self.lib.aiqmc_dmc_tmove_workspace_bytes(C.byref(self.sys), B))
+        ws = self._workspace("tmove", _nbytes(self.lib.aiqmc_dmc_tmove_workspace_bytes(C.byref(self.sys), B),
+                                              "aiqmc_dmc_tmove_workspace_bytes"))
         out = torch.empty_like(p)
         acc = torch.empty((B, self.n), dtype=torch.float64, device=self.device)
         sel = torch.empty((B, self.n), dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.aiqmc_dmc_tmove(C.byref(self.sys), C.byref(self.ecp), _ptr(self.params_dev), _ptr(p),
+            _lib.check(self.lib.aiqmc_dmc_tmove(C.byref(self.sys), C.byref(ecp_tab), _ptr(self.params_dev), _ptr(p),
                                                 _ptr(r), _ptr(uu), _ptr(rr), B, float(tstep), _ptr(out), _ptr(acc),
                                                 _ptr(sel), _ptr(ws), ws.numel(), _stream()), "aiqmc_dmc_tmove")
         return out, acc, sel
