@@ -1,7 +1,7 @@
 """aiqmc_b200 -- B200-native (sm_100a) walker engine for the VMC/DMC inner loop of AIQMCrelease3.
 
 Importable as `aiqmc_b200` (see the alias package at the repository root)."""
-from . import api, build, checkpoint, engine, gto, lib, parallel, system  # noqa: F401
+from . import api, build, checkpoint, engine, gto, lib, parallel, system, workloads  # noqa: F401
 from .gto import GaussianBasis  # noqa: F401
 from .api import (AINetData, Network, PackedParams, branch, comput_S, compute_tmoves, dmc_propagate, estimate_energy, reconfigure, trial_energy, local_energy, main_monte_carlo,  # noqa: F401
                   make_ai_net, propose_drift_diffusion, random_rotations, total_energy, branch_global, make_loss,

@@ -152,12 +152,9 @@ def _sweep_rand(eng: WalkerEngine, key, B: int, tstep: float, step: int):
     if isinstance(key, dict):
         cv = lambda a: torch.as_tensor(a).to(device=eng.device, dtype=torch.float64).contiguous()
         return cv(key['gauss1']), cv(key['gauss2']), cv(key['rnd'])
-    gen = torch.Generator(device=eng.device)
-    gen.manual_seed(int(key) * 1000003 + step)
-    g1 = torch.randn((B, 3 * n), generator=gen, device=eng.device, dtype=torch.float64) * math.sqrt(tstep)
-    g2 = torch.randn((B, n, 3 * n), generator=gen, device=eng.device, dtype=torch.float64) * math.sqrt(tstep)
-    u = torch.rand((B, n), generator=gen, device=eng.device, dtype=torch.float64)
-    return g1, g2, u
+    # throughput mode: counter-based Philox in the library's own kernels (csrc/rng.cu), keyed by (seed, walker, step);
+    # gauss2 comes in the compact (B,N,3) form -- only its diagonal blocks are ever read (VMCmcstep.py:86-94)
+    return eng.rng_sweep(int(key), step, 0, B, tstep)
 
 
 def main_monte_carlo(f, tstep: float, ndim: int, nelectrons: int, nsteps: int, batch_size: int):
@@ -198,12 +195,16 @@ def local_energy(f, charges, nspins=None, use_scan: bool = False, complex_output
     return _e_l
 
 
-def random_rotations(n: int, seed: int, device) -> torch.Tensor:
-    """Haar-random 3x3 orthogonal matrices (stand-in for jax.random.orthogonal, pseudopotential.py:234)."""
-    gen = torch.Generator(device=device)
-    gen.manual_seed(seed)
-    q, r = torch.linalg.qr(torch.randn((n, 3, 3), generator=gen, device=device, dtype=torch.float64))
-    return q * torch.sign(torch.diagonal(r, dim1=-2, dim2=-1))[:, None, :]
+def random_rotations(n: int, seed: int, device, step: int = 0, walker0: int = 0) -> torch.Tensor:
+    """Haar-random 3x3 orthogonal matrices (stand-in for jax.random.orthogonal, pseudopotential.py:234), from the
+    library's Philox kernel (csrc/rng.cu: aiqmc_rng_rotations)."""
+    import ctypes as C
+    from . import lib as _lib
+    rot = torch.empty((n, 3, 3), dtype=torch.float64, device=device)
+    with torch.cuda.device(rot.device):
+        _lib.check(_lib.load().aiqmc_rng_rotations(int(seed), int(step), int(walker0), n, C.c_void_p(rot.data_ptr()),
+                                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)), "aiqmc_rng_rotations")
+    return rot
 
 
 def total_energy(local_energy_fn, process_group=None):

@@ -73,7 +73,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             f.write('#include "' + os.path.join(CSRC, 'engine_impl.cuh') + '"\n'
                     f'extern "C" const aiqmc::OpsTable* aiqmc_ops_{n}_{a}() {{ return aiqmc::Launch<{n}, {a}>::table(); }}\n')
         jobs.append((src, os.path.join(BUILD, f"inst_{n}_{a}.o"), os.path.join(BUILD, f"inst_{n}_{a}.log")))
-    for name in ("abi", "wsizes", "gto"):
+    for name in ("abi", "wsizes", "gto", "rng"):
         jobs.append((os.path.join(CSRC, name + ".cu"), os.path.join(BUILD, name + ".o"),
                      os.path.join(BUILD, name + ".log")))
     with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:

@@ -75,8 +75,14 @@ def get_restore_path(restore_path: Optional[str] = None) -> Optional[str]:
 def save(save_path: str, t: int, data: AINetData, params, opt_state=None) -> str:
     """checkpoint.py:46-61: same file name, member names and nesting; leaves become numpy arrays."""
     ckpt_filename = os.path.join(save_path, f'qmcjax_ckpt_{t:06d}.npz')
+    def boxed(tree):
+        # a pytree member is ONE pickled object (what np.savez makes of a dict); sequences (optax / kfac states are
+        # tuples of NamedTuples) must be boxed explicitly or numpy tries to build a ragged array out of them
+        cell = np.empty((), dtype=object)
+        cell[()] = _to_numpy_tree(tree)
+        return cell
     with open(ckpt_filename, 'wb') as f:
-        np.savez(f, t=t, data=_to_numpy_tree(data), params=_to_numpy_tree(params), opt_state=_to_numpy_tree(opt_state))
+        np.savez(f, t=t, data=boxed(data), params=boxed(params), opt_state=boxed(opt_state))
     return ckpt_filename
 
 

@@ -317,16 +317,30 @@ int64_t aiqmc_vmc_workspace_bytes(const AiqmcSystem* sys, int64_t n_walkers) {
   if (!sys_ok(sys) || n_walkers < 0) return AIQMC_E_BADARG;
   return aiqmc::sweep_ws_bytes_rt(sys->n_elec, sys->n_atoms, n_walkers);
 }
-int aiqmc_vmc_sweep(const AiqmcSystem* sys, const double* params, double* pos, const double* gauss1,
-                    const double* gauss2, const double* rnd, int64_t n_walkers, double tstep, double acyrus,
-                    int32_t signed_ratio, uint8_t* accept, double* grad_eff_old, double* aux_out, void* workspace,
-                    int64_t workspace_bytes, void* stream) {
+static int sweep_any(const AiqmcSystem* sys, const double* params, double* pos, const double* gauss1,
+                     const double* gauss2, const double* rnd, int64_t n_walkers, double tstep, double acyrus,
+                     int32_t signed_ratio, int g2_compact, uint8_t* accept, double* grad_eff_old, double* aux_out,
+                     void* workspace, int64_t workspace_bytes, void* stream) {
   if (!sys_ok(sys) || !params || n_walkers < 0 || !(tstep > 0.0) || !(acyrus > 0.0)) return AIQMC_E_BADARG;
   if (n_walkers > 0 && (!pos || !gauss1 || !gauss2 || !rnd || !workspace)) return AIQMC_E_BADARG;
   const aiqmc::OpsTable* ops = find_ops(sys->n_elec, sys->n_atoms);
   if (!ops) return AIQMC_E_UNSUPPORTED;
-  return ops->sweep(sys, params, pos, gauss1, gauss2, rnd, n_walkers, tstep, acyrus, signed_ratio, accept,
+  return ops->sweep(sys, params, pos, gauss1, gauss2, rnd, n_walkers, tstep, acyrus, signed_ratio, g2_compact, accept,
                     grad_eff_old, aux_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int aiqmc_vmc_sweep(const AiqmcSystem* sys, const double* params, double* pos, const double* gauss1,
+                    const double* gauss2, const double* rnd, int64_t n_walkers, double tstep, double acyrus,
+                    int32_t signed_ratio, uint8_t* accept, double* grad_eff_old, double* aux_out, void* workspace,
+                    int64_t workspace_bytes, void* stream) {
+  return sweep_any(sys, params, pos, gauss1, gauss2, rnd, n_walkers, tstep, acyrus, signed_ratio, 0, accept,
+                   grad_eff_old, aux_out, workspace, workspace_bytes, stream);
+}
+int aiqmc_vmc_sweep_compact(const AiqmcSystem* sys, const double* params, double* pos, const double* gauss1,
+                            const double* gauss2c, const double* rnd, int64_t n_walkers, double tstep, double acyrus,
+                            int32_t signed_ratio, uint8_t* accept, double* grad_eff_old, double* aux_out,
+                            void* workspace, int64_t workspace_bytes, void* stream) {
+  return sweep_any(sys, params, pos, gauss1, gauss2c, rnd, n_walkers, tstep, acyrus, signed_ratio, 1, accept,
+                   grad_eff_old, aux_out, workspace, workspace_bytes, stream);
 }
 
 int64_t aiqmc_energy_workspace_bytes(const AiqmcSystem* sys, int64_t n_walkers, int32_t with_ecp) {

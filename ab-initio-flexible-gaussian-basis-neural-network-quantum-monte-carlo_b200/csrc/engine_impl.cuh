@@ -373,7 +373,7 @@ static __global__ void __launch_bounds__(kRedThreads) k_reduce_partials(const do
 static __global__ void __launch_bounds__(kRedThreads) k_sweep_accept(int n, double* __restrict__ pos,
                                                               const double* __restrict__ gauss2,
                                                               const double* __restrict__ rnd, int64_t B, double tau,
-                                                              double acyrus, int signed_ratio,
+                                                              double acyrus, int signed_ratio, int g2_compact,
                                                               uint8_t* __restrict__ accept,
                                                               double* __restrict__ grad_eff_old, SweepWs w) {
   __shared__ double red[kRedThreads / 32];
@@ -387,7 +387,9 @@ static __global__ void __launch_bounds__(kRedThreads) k_sweep_accept(int n, doub
     for (int c = 0; c < 3; ++c) {
       const double ge = w.grad[b * 3 * n + 3 * i + c] * te_old;
       const double gn = w.gnew[t * 3 + c] * te_new;
-      const double g2 = gauss2[(b * n + i) * 3 * n + 3 * i + c];
+      // only the diagonal 3-blocks of the reference's (B,N,3N) array are ever read (VMCmcstep.py:86-94);
+      // g2_compact: the caller passes just those, (B,N,3)
+      const double g2 = g2_compact ? gauss2[t * 3 + c] : gauss2[(b * n + i) * 3 * n + 3 * i + c];
       const double fwd = g2 * g2;
       const double bw = g2 + (ge + gn) * tau;
       tp += exp((fwd - bw * bw) / (2.0 * tau));
@@ -1064,7 +1066,7 @@ struct Launch {
 
   static int sweep(const AiqmcSystem* sys, const double* params, double* pos, const double* gauss1,
                    const double* gauss2, const double* rnd, int64_t B, double tau, double acyrus, int signed_ratio,
-                   uint8_t* accept, double* grad_eff_old, double* aux_out, void* ws, int64_t ws_bytes,
+                   int g2_compact, uint8_t* accept, double* grad_eff_old, double* aux_out, void* ws, int64_t ws_bytes,
                    cudaStream_t st) {
     if (B <= 0) return AIQMC_OK;
     if (ws_bytes < sweep_ws_bytes(NE, NA, B)) return AIQMC_E_WORKSPACE;
@@ -1085,7 +1087,7 @@ struct Launch {
     ++g_launch_count;
     k_reduce_partials<<<1, kRedThreads, 0, st>>>(w.partials, (int)rows, 1, 1, w.scal, 1);
     ++g_launch_count;
-    k_sweep_accept<<<g3, kRedThreads, 0, st>>>(NE, pos, gauss2, rnd, B, tau, acyrus, signed_ratio, accept,
+    k_sweep_accept<<<g3, kRedThreads, 0, st>>>(NE, pos, gauss2, rnd, B, tau, acyrus, signed_ratio, g2_compact, accept,
                                                grad_eff_old, w);
     ++g_launch_count;
     k_reduce_partials<<<1, kRedThreads, 0, st>>>(w.partials, (int)g3, 2, 2, w.scal, 2);

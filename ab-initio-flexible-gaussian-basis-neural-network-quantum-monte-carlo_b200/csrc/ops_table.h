@@ -11,7 +11,7 @@ struct OpsTable {
   int (*psi)(const AiqmcSystem*, const double*, const double*, int64_t, int, double*, double*, double*, double*,
              void*, int64_t, cudaStream_t);
   int (*sweep)(const AiqmcSystem*, const double*, double*, const double*, const double*, const double*, int64_t,
-               double, double, int, uint8_t*, double*, double*, void*, int64_t, cudaStream_t);
+               double, double, int, int, uint8_t*, double*, double*, void*, int64_t, cudaStream_t);
   int (*energy)(const AiqmcSystem*, const AiqmcEcp*, const double*, const double*, const double*, int64_t, double*,
                 void*, int64_t, int, cudaStream_t);
   int (*tmove)(const AiqmcSystem*, const AiqmcEcp*, const double*, const double*, const double*, const double*,

@@ -123,7 +123,8 @@ class WalkerEngine:
                 and tuple(pos.shape) == (B, 3 * self.n)):
             raise ValueError("vmc_sweep updates pos in place: it must be a contiguous float64 (B,3N) tensor on the engine's device")
         gauss1 = self._arg(gauss1, (B, 3 * self.n), "gauss1")
-        gauss2 = self._arg(gauss2, (B, self.n, 3 * self.n), "gauss2")
+        compact = torch.as_tensor(gauss2).numel() == B * self.n * 3 and self.n > 1     # (B,N,3): diagonal blocks only
+        gauss2 = self._arg(gauss2, (B, self.n, 3) if compact else (B, self.n, 3 * self.n), "gauss2")
         rnd = self._arg(rnd, (B, self.n), "rnd")
         nbytes = _nbytes(self.lib.aiqmc_vmc_workspace_bytes(C.byref(self.sys), B), "aiqmc_vmc_workspace_bytes")
         ws = self._workspace("vmc", nbytes)
@@ -131,12 +132,40 @@ class WalkerEngine:
         drift = torch.empty((B, 3 * self.n), dtype=torch.float64, device=self.device) if want_drift else None
         aux = torch.empty(4, dtype=torch.float64, device=self.device) if want_aux else None
         with torch.cuda.device(self.device):
-            rc = self.lib.aiqmc_vmc_sweep(C.byref(self.sys), _ptr(self.params_dev), _ptr(pos), _ptr(gauss1),
+            fn = self.lib.aiqmc_vmc_sweep_compact if compact else self.lib.aiqmc_vmc_sweep
+            rc = fn(C.byref(self.sys), _ptr(self.params_dev), _ptr(pos), _ptr(gauss1),
                                           _ptr(gauss2), _ptr(rnd), B, float(tstep), float(acyrus),
                                           1 if signed_ratio else 0, _ptr(accept), _ptr(drift), _ptr(aux), _ptr(ws),
                                           ws.numel(), _stream())
         _lib.check(rc, "aiqmc_vmc_sweep")
         return dict(accept=accept, grad_eff_old=drift, aux=aux)
+
+    # ---- device-side random inputs (throughput mode; csrc/rng.cu) ------------------------
+    def rng_sweep(self, seed: int, step: int, walker0: int, B: int, tstep: float, out=None):
+        """(gauss1 (B,3N), gauss2c (B,N,3), rnd (B,N)) from Philox keyed by (seed, global walker id, step)."""
+        if out is None:
+            out = (torch.empty((B, 3 * self.n), dtype=torch.float64, device=self.device),
+                   torch.empty((B, self.n, 3), dtype=torch.float64, device=self.device),
+                   torch.empty((B, self.n), dtype=torch.float64, device=self.device))
+        g1, g2c, u = out
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.aiqmc_rng_sweep(int(seed), int(step), int(walker0), B, self.n, float(tstep), _ptr(g1),
+                                                _ptr(g2c), _ptr(u), _stream()), "aiqmc_rng_sweep")
+        return out
+
+    def rng_rotations(self, seed: int, step: int, walker0: int, B: int, out=None) -> torch.Tensor:
+        rot = out if out is not None else torch.empty((B, 3, 3), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.aiqmc_rng_rotations(int(seed), int(step), int(walker0), B, _ptr(rot), _stream()),
+                       "aiqmc_rng_rotations")
+        return rot
+
+    def rng_uniform(self, seed: int, step: int, walker0: int, B: int, cols: int, tag: int) -> torch.Tensor:
+        out = torch.empty((B, cols), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.aiqmc_rng_uniform(int(seed), int(step), int(walker0), B, int(cols), int(tag), _ptr(out),
+                                                  _stream()), "aiqmc_rng_uniform")
+        return out
 
     # ---- local energy -----------------------------------------------------------------
     def local_energy(self, pos: torch.Tensor, rot: Optional[torch.Tensor] = None, stages: int = 7,
@@ -314,6 +343,46 @@ class HostStepPipeline:
         self.copy_stream = torch.cuda.Stream(device=engine.device)
         self.swept = torch.cuda.Event()
         self.e_l = None
+        self._rng_bufs = None
+
+    def run_seeded(self, pos_host: torch.Tensor, seed: int, step0: int, nsteps: int, stats_host: torch.Tensor,
+                   walker0: int = 0) -> None:
+        """Throughput mode: the host supplies positions and a seed only; gauss1 / gauss2 / uniforms / rotations are
+        generated on the device by the counter-based Philox kernels (csrc/rng.cu), as the reference draws them inside
+        its jitted graph.  Per step: positions host -> device, sweep, positions device -> host (overlapping the local
+        energy), statistics device -> host."""
+        eng, dev = self.eng, self.eng.device
+        B = pos_host.shape[0]
+        if self.e_l is None or self.e_l.shape[0] != B:
+            self.e_l = torch.empty((B, 2), dtype=torch.float64, device=dev)
+        if self._rng_bufs is None or self._rng_bufs[0].shape[0] != B:
+            self._rng_bufs = (torch.empty((B, 3 * eng.n), dtype=torch.float64, device=dev),
+                              torch.empty((B, eng.n, 3), dtype=torch.float64, device=dev),
+                              torch.empty((B, eng.n), dtype=torch.float64, device=dev),
+                              torch.empty((B, 3, 3), dtype=torch.float64, device=dev))
+        g1, g2c, u, rot = self._rng_bufs
+        cur = torch.cuda.current_stream(dev)
+        for k in range(nsteps):
+            p = pos_host.to(dev, non_blocking=True)
+            eng.rng_sweep(seed, step0 + k, walker0, B, self.tstep, out=(g1, g2c, u))
+            eng.vmc_sweep(p, g1, g2c, u, self.tstep, want_accept=False)
+            self.swept.record(cur)
+            self.copy_stream.wait_event(self.swept)
+            with torch.cuda.stream(self.copy_stream):
+                pos_host.copy_(p, non_blocking=True)
+            p.record_stream(self.copy_stream)
+            if eng.ecp is not None:
+                eng.rng_rotations(seed, step0 + k, walker0, B, out=rot)
+                eng.local_energy(p, rot, out=self.e_l)
+                e = torch.view_as_complex(self.e_l)
+            else:
+                e = eng.local_energy(p)
+            stats = eng.energy_stats(e)
+            if self.reduce_stats is not None:
+                self.reduce_stats(stats)
+            stats_host.copy_(stats, non_blocking=True)
+            cur.synchronize()
+            self.copy_stream.synchronize()
 
     def _prefetch(self, host_set):
         with torch.cuda.stream(self.copy_stream):

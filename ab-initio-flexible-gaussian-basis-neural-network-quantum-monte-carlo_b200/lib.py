@@ -22,7 +22,7 @@ EXPORTS = ["aiqmc_param_layout", "aiqmc_supported", "aiqmc_last_cuda_error", "ai
            "aiqmc_dmc_tmove_workspace_bytes", "aiqmc_dmc_tmove", "aiqmc_dmc_ecut_min", "aiqmc_dmc_s", "aiqmc_dmc_weights", "aiqmc_branch_workspace_bytes",
            "aiqmc_branch_comb", "aiqmc_gather_walkers", "aiqmc_bench_dfma", "aiqmc_gto_eval", "aiqmc_param_grad_workspace_bytes",
            "aiqmc_psi_param_grad", "aiqmc_mh_workspace_bytes", "aiqmc_mh_step", "aiqmc_correlated_samples",
-           "aiqmc_weights_jacobian"]
+           "aiqmc_weights_jacobian", "aiqmc_vmc_sweep_compact", "aiqmc_rng_sweep", "aiqmc_rng_rotations", "aiqmc_rng_uniform"]
 
 _lib = None
 
@@ -54,6 +54,10 @@ def load() -> C.CDLL:
         "aiqmc_psi_fwdlap": (C.c_int, [sysp, vp, vp, i64, vp, vp, vp, vp, vp, i64, vp]),
         "aiqmc_vmc_workspace_bytes": (i64, [sysp, i64]),
         "aiqmc_vmc_sweep": (C.c_int, [sysp, vp, vp, vp, vp, vp, i64, f64, f64, i32, vp, vp, vp, vp, i64, vp]),
+        "aiqmc_vmc_sweep_compact": (C.c_int, [sysp, vp, vp, vp, vp, vp, i64, f64, f64, i32, vp, vp, vp, vp, i64, vp]),
+        "aiqmc_rng_sweep": (C.c_int, [C.c_uint64, C.c_uint32, i64, i64, i32, f64, vp, vp, vp, vp]),
+        "aiqmc_rng_rotations": (C.c_int, [C.c_uint64, C.c_uint32, i64, i64, vp, vp]),
+        "aiqmc_rng_uniform": (C.c_int, [C.c_uint64, C.c_uint32, i64, i64, i32, C.c_uint32, vp, vp]),
         "aiqmc_energy_workspace_bytes": (i64, [sysp, i64, i32]),
         "aiqmc_local_energy_ae": (C.c_int, [sysp, vp, vp, i64, vp, vp, i64, vp]),
         "aiqmc_local_energy_ecp": (C.c_int, [sysp, ecpp, vp, vp, vp, i64, vp, vp, i64, vp]),

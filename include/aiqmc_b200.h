@@ -120,6 +120,28 @@ int aiqmc_vmc_sweep(const AiqmcSystem* sys, const double* params, double* pos, c
                     double acyrus, int32_t signed_ratio, uint8_t* accept, double* grad_eff_old,
                     double* aux_out, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Same sweep with the second Gaussian array in COMPACT form gauss2c (B,N,3) = gauss2[b,i,3i:3i+3]: the only entries
+ * of the reference's (B,N,3N) draw that walkers_update reads (VMCmcstep.py:86-94 indexes [b,i,i,d]).  12N instead of
+ * 12N^2 bytes per walker cross the boundary. */
+int aiqmc_vmc_sweep_compact(const AiqmcSystem* sys, const double* params, double* pos, const double* gauss1,
+                            const double* gauss2c, const double* rnd, int64_t n_walkers, double tstep,
+                            double acyrus, int32_t signed_ratio, uint8_t* accept, double* grad_eff_old,
+                            double* aux_out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- device-side random inputs ("throughput mode"): counter-based Philox4x32-10 keyed by `seed`, counter =
+ * (global walker id, step, slot), so a walker's numbers do not depend on the batch size or on the sharding over GPUs.
+ * They stand in for the draws the reference makes inside its jitted graph (jax.random.normal / uniform / orthogonal,
+ * VMC/VMCmcstep.py:19-20,58,83; pseudopotential/pseudopotential.py:233-235; DMC/Tmoves.py:146,216-217); jax's threefry
+ * streams themselves are not reproducible without jax.  walker0 = global index of this batch's first walker.
+ * aiqmc_rng_sweep: gauss1 (B,3N), gauss2c (B,N,3) ~ sqrt(tstep) N(0,1), rnd (B,N) ~ U[0,1).
+ * aiqmc_rng_rotations: rot (B,3,3) Haar-random orthogonal (QR of a Gaussian matrix, R's diagonal positive).
+ * aiqmc_rng_uniform: out (B,cols) ~ U[0,1); tag 0..15 selects an independent stream (T-move u, rnd, comb u ...). */
+int aiqmc_rng_sweep(uint64_t seed, uint32_t step, int64_t walker0, int64_t n_walkers, int32_t n_elec, double tstep,
+                    double* gauss1, double* gauss2c, double* rnd, void* stream);
+int aiqmc_rng_rotations(uint64_t seed, uint32_t step, int64_t walker0, int64_t n_walkers, double* rot, void* stream);
+int aiqmc_rng_uniform(uint64_t seed, uint32_t step, int64_t walker0, int64_t n_walkers, int32_t cols, uint32_t tag,
+                      double* out, void* stream);
+
 /* ---- local energy: replaces _e_l (Energy/hamiltonian.py:248-258, pphamiltonian.py:177-188)
  *      wrapped in jax.vmap over walkers (Loss/pploss.py:145-153) ---------------------------- */
 int64_t aiqmc_energy_workspace_bytes(const AiqmcSystem* sys, int64_t n_walkers, int32_t with_ecp);

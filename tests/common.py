@@ -95,3 +95,35 @@ CASES = {
     "odd": dict(n=5, natoms=2, spins=[1., 1., 1., -1., -1.], seed=14),
     "h2like": dict(n=2, natoms=2, spins=[1., -1.], seed=15),
 }
+
+
+# ---- the bench.py headline system (carbon ccECP, BASELINE configs[1]) as an oracle-backed Case ----
+TSTEP = 0.05
+BENCH_SEED = 20260101
+
+
+def build_bench_case(nwalkers, seed=BENCH_SEED):
+    case = Case(n=4, natoms=1, spins=[1., -1., 1., -1.], seed=seed, atoms=[[0., 0., 0.]], charges=[4.0],
+                nwalkers=nwalkers, width=1.0)
+    # "random-init params": the reference's init scales (weights N(0,1)/sqrt(fan_in), biases N(0,1),
+    # Jastrow/envelope = 1), SURVEY 8(d)
+    case.params = case.net.init(np.random.default_rng(seed), randomize_all=False)
+    return case, ecp_tables(1)
+
+
+def make_rand(rng, B, n, tstep):
+    return dict(gauss1=(rng.standard_normal((B, 3 * n)) * np.sqrt(tstep)),
+                gauss2=(rng.standard_normal((B, n, 3 * n)) * np.sqrt(tstep)),
+                rnd=rng.uniform(size=(B, n)))
+
+
+def random_rot(rng, B):
+    q, r = np.linalg.qr(rng.standard_normal((B, 3, 3)))
+    return q * np.sign(np.diagonal(r, axis1=-2, axis2=-1))[:, None, :]
+
+
+def benzene_case(nwalkers, seed=21, width=0.8):
+    import math
+    ring = lambda r, n: [[r * math.cos(2 * math.pi * k / n), r * math.sin(2 * math.pi * k / n), 0.0] for k in range(n)]
+    return Case(n=30, natoms=12, spins=[1.] * 15 + [-1.] * 15, seed=seed, atoms=ring(2.640, 6) + ring(4.689, 6),
+                charges=[4.0] * 6 + [1.0] * 6, nwalkers=nwalkers, width=width)

@@ -7,7 +7,7 @@ import torch
 from common import O, ecp_tables
 
 import aiqmc_b200
-import bench
+import common as bench
 
 pytestmark = pytest.mark.gpu
 B = 65536
@@ -15,7 +15,7 @@ B = 65536
 
 @pytest.fixture(scope="module")
 def setup():
-    case, tabs = bench.build_case(B)
+    case, tabs = bench.build_bench_case(B)
     eng = aiqmc_b200.WalkerEngine(case.spec(), case.params, ecp=aiqmc_b200.make_ecp(1, list_l=2, **tabs))
     rng = np.random.default_rng(77)
     rot = torch.from_numpy(bench.random_rot(rng, B)).cuda()
@@ -86,9 +86,9 @@ def test_gradient_and_laplacian_paths_agree_at_full_size(setup):
 def test_host_step_pipeline_matches_device_resident_steps():
     """aiqmc_b200.HostStepPipeline (host buffers in / out every step, copies overlapped with the kernels) gives exactly
     the positions and statistics of the same steps run on device-resident data."""
-    import bench
+    import common as bench
     B, nsteps = 4096, 3
-    case, tabs = bench.build_case(B)
+    case, tabs = bench.build_bench_case(B)
     eng = aiqmc_b200.WalkerEngine(case.spec(), case.params, ecp=aiqmc_b200.make_ecp(1, list_l=2, **tabs))
     rng = np.random.default_rng(3)
     host_sets = []
