@@ -460,6 +460,7 @@ def compute_tmoves(list_l, tstep: float, nelectrons: int, natoms: int, ndim: int
         pos = _positions(eng, data)
         new_pos, acceptance, _ = eng.dmc_tmove(pos, key['rot'], key['u'], key['rnd'], tstep, ecp=ecp)
         return new_pos, acceptance
+    calculate_ratio_weight_tmoves.ecp = ecp            # the table of this closure (local channel zeroed)
     return calculate_ratio_weight_tmoves
 
 

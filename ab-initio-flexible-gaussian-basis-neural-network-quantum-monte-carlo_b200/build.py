@@ -86,7 +86,26 @@ def build(force: bool = False, verbose: bool = False) -> str:
         f.write(digest)
     if verbose:
         print("built", LIB, file=sys.stderr)
+    build_xla_ffi(verbose)
     return LIB
+
+
+def build_xla_ffi(verbose: bool = False):
+    """csrc/xla_ffi.cc -> libaiqmc_b200_xla.so, only where the XLA FFI headers exist (jax.ffi.include_dir())."""
+    try:
+        import jax.ffi
+        inc = jax.ffi.include_dir()
+    except Exception:
+        return None                                   # no jax in this image: the shim is only type-checked (tests/)
+    out = os.path.join(HERE, "libaiqmc_b200_xla.so")
+    cmd = [NVCC, "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-I", inc, os.path.join(CSRC, "xla_ffi.cc"),
+           "-o", out, "-L", HERE, "-l:" + os.path.basename(LIB), "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN", "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"xla_ffi.cc failed to build against {inc}:\n{r.stdout}\n{r.stderr}")
+    if verbose:
+        print("built", out, file=sys.stderr)
+    return out
 
 
 if __name__ == "__main__":

@@ -124,9 +124,11 @@ inline int64_t tangent_rows(int n, int a, bool lap, int64_t n_cfg) {
   const int64_t groups = 3 * n <= 24 ? 1 : (3 * n + 14) / 15;          // >= tan_groups<n>()
   return (full * ((c + 31) / 32) + (rest + 31) / 32) * groups;
 }
+constexpr int kCoopMaxGrid = 148 * 16;     // persistent grids of the lane-per-electron kernels never exceed this
 inline int64_t sweep_partial_rows(int n, int a, int64_t B) {
   const int64_t r = tangent_rows(n, a, false, B * n), r3 = (B * n + kRedThreads - 1) / kRedThreads;
-  return (r > r3 ? r : r3) + 1;
+  const int64_t m = r > r3 ? r : r3;
+  return (m > kCoopMaxGrid ? m : kCoopMaxGrid) + 1;
 }
 inline int64_t psi_ws_bytes(int n, int a, int64_t n_cfg, int with_lap) {
   return deriv_cache_bytes(n, a, with_lap != 0, n_cfg) +
@@ -770,6 +772,7 @@ static __global__ void k_energy_final(int64_t B, double* __restrict__ e_l, Energ
 #include "ecp_coop.cuh"
 #include "ecp_pt.cuh"
 #include "ecp_grp.cuh"
+#include "coop_grad.cuh"
 #include "param_grad.cuh"
 namespace aiqmc {
 
@@ -1010,7 +1013,21 @@ struct Launch {
     return AIQMC_OK;
   }
 
-  static constexpr bool kReverse = (NE <= 16);   // fused reverse-mode gradient (its per-thread tape is 12 N^2 doubles)
+  static constexpr bool kReverse = (NE <= 16);   // fused forward + reverse gradient, lane per electron (coop_grad.cuh)
+
+  // persistent grid of a lane-per-electron kernel: every CTA resident at once, tiles dealt round-robin
+  template <class K>
+  static int coop_grid(K kernel, int threads, int smem_bytes, int64_t tiles, unsigned* grid) {
+    int dev = 0, sms = 148, per_sm = 1;
+    AQ_CUDA_OK(cudaGetDevice(&dev));
+    AQ_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    AQ_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem_bytes));
+    int64_t g = (int64_t)sms * (per_sm < 1 ? 1 : per_sm);
+    if (g > kCoopMaxGrid) g = kCoopMaxGrid;
+    if (g > tiles) g = tiles;
+    *grid = (unsigned)(g < 1 ? 1 : g);
+    return AIQMC_OK;
+  }
 
   // gradient of n_cfg configurations: fused reverse sweep for N <= 16, the two-pass path beyond
   template <int SRC, int OUT>
@@ -1018,11 +1035,22 @@ struct Launch {
                   double* dcache, double* phase, double* logabs, double* gout, double* partials, int pcol,
                   int64_t* rows, cudaStream_t st) {
     if constexpr (kReverse) {
+#ifdef AIQMC_GRAD_THREAD_PER_CFG      // round-1 kernel (one thread per configuration), kept for A/B timing only
       AQ_CUDA_OK(prep(k_grad_reverse<NE, NA, SRC, OUT>));
       const unsigned g = (unsigned)((n_cfg + kThreads - 1) / kThreads);
       ++g_launch_count;
       k_grad_reverse<NE, NA, SRC, OUT><<<g, kThreads, kSmem, st>>>(*sys, params, pos, n_cfg, ms, phase, logabs, gout,
                                                                     partials ? partials + *rows * 4 : nullptr, pcol);
+#else
+      using CG = CoopGradCfg<NE, NA>;
+      AQ_CUDA_OK(cudaFuncSetAttribute(k_grad_coop<NE, NA, SRC, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, CG::kBytes));
+      unsigned g = 1;
+      const int rc = coop_grid(k_grad_coop<NE, NA, SRC, OUT>, CG::T, CG::kBytes, (n_cfg + CG::NG - 1) / CG::NG, &g);
+      if (rc != AIQMC_OK) return rc;
+      ++g_launch_count;
+      k_grad_coop<NE, NA, SRC, OUT><<<g, CG::T, CG::kBytes, st>>>(*sys, params, pos, n_cfg, ms, phase, logabs, gout,
+                                                                   partials ? partials + *rows * 4 : nullptr, pcol);
+#endif
       if (rows) *rows += g;
       AQ_CUDA_OK(cudaGetLastError());
       return AIQMC_OK;

@@ -284,8 +284,8 @@ def test_dmc_tmoves_match_oracle(name, rich, tstep, scale):
     data = aiqmc_b200.AINetData(positions=torch.tensor(case.pos), spins=case.t_spins, atoms=case.t_atoms,
                                 charges=torch.tensor(case.charges))
     new_pos, acc = tm(data, case.params, dict(rot=torch.tensor(rot), u=torch.tensor(u), rnd=torch.tensor(rnd)))
-    eng = net.apply.bind(case.params, case.t_atoms)        # the engine `tm` ran on (ECP table already attached)
-    _, _, sel = eng.dmc_tmove(torch.tensor(case.pos), torch.tensor(rot), torch.tensor(u), torch.tensor(rnd), tstep)
+    eng = net.apply.bind(case.params, case.t_atoms)        # the engine `tm` ran on; the table travels with the closure
+    _, _, sel = eng.dmc_tmove(torch.tensor(case.pos), torch.tensor(rot), torch.tensor(u), torch.tensor(rnd), tstep, ecp=tm.ecp)
     ref = O.compute_tmoves(2, tstep, case.n, case.a, 3, O.make_log_network(case.net.apply), tabs['rn_non_local'],
                            tabs['non_local_coes'], tabs['non_local_exps'])
     moved = 0
