@@ -7,7 +7,7 @@ from .api import (AINetData, Network, PackedParams, branch, comput_S, compute_tm
                   make_ai_net, propose_drift_diffusion, random_rotations, total_energy, branch_global, make_loss,
                   clip_local_values, AuxiliaryLossData, make_mcmc_step, update_mcmc_width,
                   correlated_samples, weights_jacobian, read_ecp_nwchem)
-from .engine import HostStepPipeline, WalkerEngine  # noqa: F401
+from .engine import HostStepPipeline, NcclComm, WalkerEngine  # noqa: F401
 from .system import SystemSpec, jastrow_indices_ee, make_ecp, pack_params, spin_indices_h, unpack_param_grad  # noqa: F401
 
 __all__ = ["AINetData", "Network", "PackedParams", "WalkerEngine", "SystemSpec", "make_ai_net", "main_monte_carlo",

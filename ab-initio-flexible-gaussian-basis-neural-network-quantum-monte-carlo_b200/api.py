@@ -539,9 +539,18 @@ def trial_energy(e_est, weights: torch.Tensor, feedback: float):
     return e_est - feedback * torch.log(torch.as_tensor(weights).mean()).real
 
 
-def branch_global(engine: WalkerEngine, weights: torch.Tensor, positions: torch.Tensor, key, process_group=None):
+def branch_global(engine: WalkerEngine, weights: torch.Tensor, positions: torch.Tensor, key, process_group=None,
+                  return_bytes: bool = False):
     """Population control across all GPUs of the job (the reference combs per device only): the
-    systematic comb of DMC/branch.py:10-34 over the all-gathered weights + migration of the selected walkers.
-    Returns (new weight scalar, new positions (B,3N), global source indices (B,), walkers imported)."""
-    return parallel.global_branch(lambda w, u: engine.branch_comb(w, u), engine.gather_walkers, weights, positions,
-                                  float(key), process_group)
+    systematic comb of DMC/branch.py:10-34 over the weights of ALL ranks + migration of the selected walkers, through
+    the C ABI (aiqmc_rebalance_nccl): exchanged are the block totals of each rank's weight scan (all-gather) and, in one
+    grouped NCCL send/recv, only the walkers that change rank.  Returns (new weight scalar, new positions (B,3N),
+    source rank of every new walker (B,) int32, walkers imported from other ranks[, bytes this rank sent])."""
+    from .engine import NcclComm
+    import torch.distributed as dist
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
+    comm = NcclComm.for_group(process_group, engine.device) if multi else None
+    neww, new_pos, src, moved = engine.rebalance(weights, positions, float(key), comm)
+    rank = comm.rank if comm is not None else 0
+    imported = int((src != rank).sum())
+    return (neww, new_pos, src, imported, moved) if return_bytes else (neww, new_pos, src, imported)

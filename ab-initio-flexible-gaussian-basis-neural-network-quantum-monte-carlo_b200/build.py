@@ -73,12 +73,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
             f.write('#include "' + os.path.join(CSRC, 'engine_impl.cuh') + '"\n'
                     f'extern "C" const aiqmc::OpsTable* aiqmc_ops_{n}_{a}() {{ return aiqmc::Launch<{n}, {a}>::table(); }}\n')
         jobs.append((src, os.path.join(BUILD, f"inst_{n}_{a}.o"), os.path.join(BUILD, f"inst_{n}_{a}.log")))
-    for name in ("abi", "wsizes", "gto", "rng"):
+    for name in ("abi", "wsizes", "gto", "rng", "population"):
         jobs.append((os.path.join(CSRC, name + ".cu"), os.path.join(BUILD, name + ".o"),
                      os.path.join(BUILD, name + ".log")))
     with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
         objs = list(ex.map(lambda j: _compile(*j), jobs))
-    cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

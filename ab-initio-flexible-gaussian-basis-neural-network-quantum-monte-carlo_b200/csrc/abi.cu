@@ -64,40 +64,6 @@ __device__ __forceinline__ double wmin(double v) {
   return v;
 }
 
-// [sum Re E, sum Im E, sum |E|^2, count]; single CTA, fixed summation order (deterministic)
-__global__ void __launch_bounds__(kBig) k_energy_stats(const double* __restrict__ e, int stride, int64_t B,
-                                                       double* __restrict__ out) {
-  __shared__ double red[3][kBig / 32];
-  double sr = 0.0, si = 0.0, s2 = 0.0;
-  for (int64_t b = threadIdx.x; b < B; b += kBig) {
-    const double re = e[b * stride], im = stride > 1 ? e[b * stride + 1] : 0.0;
-    sr += re; si += im; s2 += re * re + im * im;
-  }
-  sr = wsum(sr); si = wsum(si); s2 = wsum(s2);
-  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sr; red[1][threadIdx.x >> 5] = si; red[2][threadIdx.x >> 5] = s2; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double a = 0, b2 = 0, c = 0;
-    for (int i = 0; i < kBig / 32; ++i) { a += red[0][i]; b2 += red[1][i]; c += red[2][i]; }
-    out[0] = a; out[1] = b2; out[2] = c; out[3] = (double)B;
-  }
-}
-
-__global__ void __launch_bounds__(kBig) k_ecut_min(const double* __restrict__ e, int stride, int64_t B, double e_est,
-                                                   const double* __restrict__ branchcut, double* __restrict__ out) {
-  __shared__ double red[kBig / 32];
-  double m = INFINITY;
-  for (int64_t b = threadIdx.x; b < B; b += kBig) m = fmin(m, fmin(fabs(e_est - e[b * stride]), branchcut[b]));
-  m = wmin(m);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double r = INFINITY;
-    for (int i = 0; i < kBig / 32; ++i) r = fmin(r, red[i]);
-    out[0] = r;
-  }
-}
-
 __global__ void k_dmc_s(const double* __restrict__ e, int stride, const double* __restrict__ drift, int64_t B, int n,
                         double e_trial, double e_est, const double* __restrict__ ecut_min, double tau,
                         double* __restrict__ s_out) {
@@ -218,48 +184,6 @@ __global__ void k_warp_jacobian(AtomPair at, int a, int n, const double* __restr
   jac[b] = prod;
 }
 
-// inclusive cumsum by one CTA: per-thread contiguous chunks + scan of chunk totals
-__global__ void __launch_bounds__(kBig) k_cumsum(const double* __restrict__ w, int64_t B, double* __restrict__ cum) {
-  __shared__ double tot[kBig];
-  const int64_t chunk = (B + kBig - 1) / kBig;
-  const int64_t lo = (int64_t)threadIdx.x * chunk, hi = lo + chunk < B ? lo + chunk : B;
-  double s = 0.0;
-  for (int64_t b = lo; b < hi; ++b) s += w[b];
-  tot[threadIdx.x] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double run = 0.0;
-    for (int i = 0; i < kBig; ++i) { const double t = tot[i]; tot[i] = run; run += t; }
-  }
-  __syncthreads();
-  double run = tot[threadIdx.x];
-  for (int64_t b = lo; b < hi; ++b) { run += w[b]; cum[b] = run; }
-}
-
-// newinds = searchsorted(cum, (u*wtot + k*wtot/B) mod wtot), side='left'  (branch.py:21-23)
-__global__ void k_comb(const double* __restrict__ cum, int64_t B, double u, int32_t* __restrict__ newinds,
-                       double* __restrict__ new_weight) {
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= B) return;
-  const double wtot = cum[B - 1];
-  const double base = u * wtot;
-  double v = base + (double)k * (wtot / (double)B);
-  v = fmod(v, wtot);
-  if (v < 0.0) v += wtot;
-  int64_t lo = 0, hi = B;
-  while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (cum[mid] < v) lo = mid + 1; else hi = mid; }
-  newinds[k] = (int32_t)lo;
-  if (k == 0) new_weight[0] = wtot / (double)B;
-}
-
-__global__ void k_gather(const double* __restrict__ in, const int32_t* __restrict__ idx, int64_t B, int row,
-                         double* __restrict__ out) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= B * row) return;
-  const int64_t b = t / row;
-  const int c = (int)(t - b * row);
-  out[t] = in[(int64_t)idx[b] * row + c];
-}
 __global__ void __launch_bounds__(256) k_bench_dfma(int64_t iters, double* __restrict__ sink) {
   double a[8];
   const double x = 1.0 + 1e-9 * threadIdx.x, y = 1e-12 * blockIdx.x;
@@ -404,22 +328,6 @@ int aiqmc_local_energy_ecp(const AiqmcSystem* sys, const AiqmcEcp* ecp, const do
                                        stream);
 }
 
-int aiqmc_energy_stats(const double* e_l, int32_t e_l_stride, int64_t n_walkers, double* stats, void* stream) {
-  if (!e_l || !stats || n_walkers < 0 || (e_l_stride != 1 && e_l_stride != 2)) return AIQMC_E_BADARG;
-  ++g_launch_count;
-  k_energy_stats<<<1, kBig, 0, (cudaStream_t)stream>>>(e_l, e_l_stride, n_walkers, stats);
-  AQ_CUDA_OK(cudaGetLastError());
-  return AIQMC_OK;
-}
-
-int aiqmc_dmc_ecut_min(const double* e_l, int32_t e_l_stride, int64_t n_walkers, double e_est, const double* branchcut,
-                       double* ecut_min, void* stream) {
-  if (!e_l || !branchcut || !ecut_min || n_walkers < 0 || (e_l_stride != 1 && e_l_stride != 2)) return AIQMC_E_BADARG;
-  ++g_launch_count;
-  k_ecut_min<<<1, kBig, 0, (cudaStream_t)stream>>>(e_l, e_l_stride, n_walkers, e_est, branchcut, ecut_min);
-  AQ_CUDA_OK(cudaGetLastError());
-  return AIQMC_OK;
-}
 int aiqmc_dmc_s(const double* e_l, int32_t e_l_stride, const double* drift, int64_t n_walkers, int32_t n_elec,
                 double e_trial, double e_est, const double* ecut_min, double tau, double* s_out, void* stream) {
   if (!e_l || !drift || !ecut_min || !s_out || n_walkers < 0 || n_elec < 1 || (e_l_stride != 1 && e_l_stride != 2))
@@ -505,19 +413,6 @@ int aiqmc_weights_jacobian(const double* atoms, const double* new_atoms, int32_t
   return AIQMC_OK;
 }
 
-int64_t aiqmc_branch_workspace_bytes(int64_t n_walkers) { return n_walkers < 0 ? AIQMC_E_BADARG : (n_walkers + 32) * 8; }
-int aiqmc_branch_comb(const double* weights, int64_t n_walkers, double u, int32_t* newinds, double* new_weight,
-                      void* workspace, int64_t workspace_bytes, void* stream) {
-  if (!weights || !newinds || !new_weight || !workspace || n_walkers <= 0) return AIQMC_E_BADARG;
-  if (workspace_bytes < aiqmc_branch_workspace_bytes(n_walkers)) return AIQMC_E_WORKSPACE;
-  double* cum = (double*)workspace;
-  ++g_launch_count;
-  k_cumsum<<<1, kBig, 0, (cudaStream_t)stream>>>(weights, n_walkers, cum);
-  ++g_launch_count;
-  k_comb<<<(unsigned)((n_walkers + 255) / 256), 256, 0, (cudaStream_t)stream>>>(cum, n_walkers, u, newinds, new_weight);
-  AQ_CUDA_OK(cudaGetLastError());
-  return AIQMC_OK;
-}
 int aiqmc_bench_dfma(int64_t iters, double* sink, double* flops_out, void* stream) {
   if (iters <= 0 || !sink || !flops_out) return AIQMC_E_BADARG;
   const int grid = 148 * 8;
@@ -527,16 +422,4 @@ int aiqmc_bench_dfma(int64_t iters, double* sink, double* flops_out, void* strea
   *flops_out = (double)grid * 256.0 * 8.0 * 2.0 * (double)iters;
   return AIQMC_OK;
 }
-int aiqmc_gather_walkers(const double* pos_in, const int32_t* newinds, int64_t n_walkers, int32_t row_doubles,
-                         double* pos_out, void* stream) {
-  if (!pos_in || !newinds || !pos_out || n_walkers < 0 || row_doubles < 1) return AIQMC_E_BADARG;
-  if (n_walkers == 0) return AIQMC_OK;
-  const int64_t nt = n_walkers * row_doubles;
-  ++g_launch_count;
-  k_gather<<<(unsigned)((nt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pos_in, newinds, n_walkers, row_doubles,
-                                                                           pos_out);
-  AQ_CUDA_OK(cudaGetLastError());
-  return AIQMC_OK;
-}
-
 }  // extern "C"

@@ -42,7 +42,11 @@ struct CoopGradCfg {
   static constexpr int oGACC = oHS + 4 * NE;                 // [N][3]   gradient contributions to the other electron
   static constexpr int oMS = (oGACC + 3 * NE + 1) & ~1;      // [N][N][2] matrix transpose / inverse exchange
   static constexpr int oPIV = oMS + 2 * NE * NE;             // [2][N][2] pivot rows (double buffered)
-  static constexpr int SCR = (oPIV + 4 * NE + 1) & ~1;
+  // group stride: even (double2 rows stay 16-byte aligned) and = 2 mod 16 doubles, so that the <= 8 groups of a warp
+  // start 4 banks apart: the scratch accesses of different groups never collide (a stride of 120 doubles put groups
+  // 0,2,4,6 on the same banks: 20 M conflicts per sweep in the first ncu capture)
+  static constexpr int kScrRaw = (oPIV + 4 * NE + 1) & ~1;
+  static constexpr int SCR = kScrRaw + ((2 - kScrRaw % 16) + 16) % 16;
   static constexpr int TAPE = 9 * NE;                        // per thread: [N pairs][r, h1[4], h2[4]]
   static constexpr int kPar = (make_layout(NE, NA).total + 1) & ~1;
   static constexpr int kDoubles = kPar + NG * SCR + T * TAPE;

@@ -19,6 +19,18 @@
 #pragma once
 #include "psi_core.cuh"
 
+// The tangent pass keeps ~170 doubles of per-thread state in small arrays indexed by loop variables; nvcc leaves loops
+// with large inlined bodies rolled, so those arrays live in local memory (1.3 kB of stack per thread at N = 4).
+// Measured alternative (AIQMC_TANGENT_UNROLL): full unrolling makes every index a compile-time constant, but the state
+// does not fit 168 registers (3.5 kB of spills) and at 255 registers the kernel lost a third of its occupancy and
+// 3.5 minutes of compile time per instantiation: 1.52 ms against 0.97 ms for the kinetic stage of carbon.  Rolled it is.
+#if defined(__CUDACC__) && defined(AIQMC_TANGENT_UNROLL)
+#define AQ_PRAGMA_(x) _Pragma(#x)
+#define AQ_UNROLL_N AQ_PRAGMA_(unroll (NE <= 6 ? 64 : 1))
+#else
+#define AQ_UNROLL_N
+#endif
+
 namespace aiqmc {
 
 template <int NE, int NA>
@@ -153,6 +165,7 @@ struct DerivSplit {
     // ---- electron-local jets (the only transcendental work of this pass)
     double xe[3];
     J xj[3];
+    AQ_UNROLL_N
     for (int c = 0; c < 3; ++c) {
       xe[c] = ld(DC::X + 3 * e + c);
       xj[c] = Op::cst(xe[c]);
@@ -164,9 +177,11 @@ struct DerivSplit {
 
     // ---- level-0 tangents of the pair chains through e: row (e,k): d = x_k - x_e, column (k,e): d = x_e - x_k
     Tan4 cr[N], cc[N];
+    AQ_UNROLL_N
     for (int k = 0; k < N; ++k) {
       if (k == e) continue;
       double dd = 0.0;
+      AQ_UNROLL_N
       for (int c = 0; c < 3; ++c) { const double d = ld(DC::X + 3 * k + c) - xe[c]; dd = (c == dir) ? d : dd; }
       const double r = ld(DC::HP + ((0 * N + e) * N + k) * 4);
       const double ri = s_inv(r);
@@ -174,6 +189,7 @@ struct DerivSplit {
       const double rs = (1.0 - rt * rt) * ri;                     // d2r/dx_{e,dir}^2
       cr[k].d[0] = rt; cc[k].d[0] = rt;
       cr[k].s[0] = LAP ? rs : 0.0; cc[k].s[0] = LAP ? rs : 0.0;
+      AQ_UNROLL_N
       for (int c = 0; c < 3; ++c) {
         cr[k].d[1 + c] = (c == dir) ? -1.0 : 0.0;
         cc[k].d[1 + c] = (c == dir) ? 1.0 : 0.0;
@@ -189,12 +205,16 @@ struct DerivSplit {
 
     // ---- one-electron stream tangents for every electron k; the pair chains advance with the layers
     double hd[N][4], hs[N][4];
+    AQ_UNROLL_N
     for (int l = 0; l < 3; ++l) {
       // block sums of the column chains: tangent of G_l[s][e]
       double sud[2][4], sus[2][4];
+      AQ_UNROLL_N
       for (int s = 0; s < 2; ++s) for (int c = 0; c < 4; ++c) { sud[s][c] = 0.0; sus[s][c] = 0.0; }
+      AQ_UNROLL_N
       for (int k = 0; k < N; ++k) {
         if (k == e) continue;
+        AQ_UNROLL_N
         for (int c = 0; c < 4; ++c) {      // no runtime-indexed register arrays
           if (k < sys.n_up) { sud[0][c] += cc[k].d[c]; if (LAP) sus[0][c] += cc[k].s[c]; }
           else { sud[1][c] += cc[k].d[c]; if (LAP) sus[1][c] += cc[k].s[c]; }
@@ -204,13 +224,16 @@ struct DerivSplit {
       double gmd[2][4 * A > 4 ? 4 * A : 4], gms[2][4 * A > 4 ? 4 * A : 4];
       constexpr int DIN0 = 4 * A;
       if (l == 0) {
+        AQ_UNROLL_N
         for (int q = 0; q < DIN0; ++q) {
           gmd[0][q] = se == 0 ? h0e[q].d[0] * inv_se : 0.0; gmd[1][q] = se == 1 ? h0e[q].d[0] * inv_se : 0.0;
           gms[0][q] = (LAP && se == 0) ? h0e[q].s[0] * inv_se : 0.0; gms[1][q] = (LAP && se == 1) ? h0e[q].s[0] * inv_se : 0.0;
         }
       } else {
+        AQ_UNROLL_N
         for (int c = 0; c < 4; ++c) {
           double u = 0.0, d = 0.0, us = 0.0, ds = 0.0;
+          AQ_UNROLL_N
           for (int k = 0; k < N; ++k) {
             if (k < sys.n_up) { u += hd[k][c]; if (LAP) us += hs[k][c]; } else { d += hd[k][c]; if (LAP) ds += hs[k][c]; }
           }
@@ -218,15 +241,18 @@ struct DerivSplit {
           gms[0][c] = us * inv_n[0]; gms[1][c] = ds * inv_n[1];
         }
       }
+      AQ_UNROLL_N
       for (int k = 0; k < N; ++k) {
         if (l == 0) row_layer<LAP, DIN0>(P, 0, k, e, se, inv_n, dc, stride, h0e, hd[k], hs[k], gmd, gms, cr[k], sud, sus);
         else row_layer<LAP, 4>(P, l, k, e, se, inv_n, dc, stride, h0e, hd[k], hs[k], gmd, gms, cr[k], sud, sus);
       }
       if (l < 2) {   // advance the tangents of the 2(N-1) pair chains through double-layer l
         const double* W = P + L.dbl_w[l];
+        AQ_UNROLL_N
         for (int k = 0; k < N; ++k) {
           if (k == e) continue;
           double tr[4], tc[4];
+          AQ_UNROLL_N
           for (int m = 0; m < 4; ++m) {
             tr[m] = kSqrt2 * ld(DC::HP + (((l + 1) * N + e) * N + k) * 4 + m) - ld(DC::HP + ((l * N + e) * N + k) * 4 + m);
             tc[m] = kSqrt2 * ld(DC::HP + (((l + 1) * N + k) * N + e) * 4 + m) - ld(DC::HP + ((l * N + k) * N + e) * 4 + m);
@@ -245,20 +271,25 @@ struct DerivSplit {
     const double* Bv = P + L.orb_b[srow];
     const int eh = sys.sigma[e];
     double h3[4], h3d[4];
+    AQ_UNROLL_N
     for (int c = 0; c < 4; ++c) {
       h3[c] = ld(DC::H + (2 * N + eh) * 4 + c);
       double v = hd[0][c];
+      AQ_UNROLL_N
       for (int q = 1; q < N; ++q) v = (eh == q) ? hd[q][c] : v;
       h3d[c] = v;
     }
     cplx S1[LAP ? N : 1];
     cplx S1e = {0.0, 0.0}, S2 = {0.0, 0.0};
     if (LAP) for (int l = 0; l < N; ++l) S1[l] = {0.0, 0.0};
+    AQ_UNROLL_N
     for (int j = 0; j < N; ++j) {
       J yo = Op::cst(0.0);
+      AQ_UNROLL_N
       for (int m = 0; m < 6; ++m) yo = yo + ye[m] * P[L.y_w + m * N + j];
       const J E = enve * yo;
       cplx p = {Bv[2 * j], Bv[2 * j + 1]}, dp = {0.0, 0.0};
+      AQ_UNROLL_N
       for (int c = 0; c < 4; ++c) {
         const double wr = W[c * 2 * N + 2 * j], wi = W[c * 2 * N + 2 * j + 1];
         p.re += h3[c] * wr; p.im += h3[c] * wi;
@@ -268,6 +299,7 @@ struct DerivSplit {
       const cplx mje = {ld(DC::MI + (j * N + e) * 2), ld(DC::MI + (j * N + e) * 2 + 1)};
       cfma(S1e, pdE, mje);
       if (LAP) {
+        AQ_UNROLL_N
         for (int l = 0; l < N; ++l) {
           const cplx mjl = {ld(DC::MI + (j * N + l) * 2), ld(DC::MI + (j * N + l) * 2 + 1)};
           cfma(S1[l], pdE, mjl);
@@ -278,10 +310,13 @@ struct DerivSplit {
     }
     // gradient: Re tr(X) = Re [ sum_k sum_c dh[sigma_k,c] Gm[k,c] + S1[e] ]
     double gsum = S1e.re + dJ, l2 = S2.re + sJ;
+    AQ_UNROLL_N
     for (int k = 0; k < N; ++k) {
       const int ek = sys.sigma[k];
+      AQ_UNROLL_N
       for (int c = 0; c < 4; ++c) {
         double vd = hd[0][c], vs = LAP ? hs[0][c] : 0.0;
+        AQ_UNROLL_N
         for (int q = 1; q < N; ++q) { vd = (ek == q) ? hd[q][c] : vd; if (LAP) vs = (ek == q) ? hs[q][c] : vs; }
         const double gm = ld(DC::GMAT + (k * 4 + c) * 2);
         gsum += vd * gm;
@@ -292,16 +327,21 @@ struct DerivSplit {
     if (LAP) {
       // X[k,l] = sum_c dh[sigma_k,c] T[k,c,l] + delta_ke S1[l];  subtract Re tr(X X)
       cplx X[N * N];
+      AQ_UNROLL_N
       for (int k = 0; k < N; ++k) {
         const int ek = sys.sigma[k];
         double dh[4];
+        AQ_UNROLL_N
         for (int c = 0; c < 4; ++c) {
           double v = hd[0][c];
+          AQ_UNROLL_N
           for (int q = 1; q < N; ++q) v = (ek == q) ? hd[q][c] : v;
           dh[c] = v;
         }
+        AQ_UNROLL_N
         for (int l = 0; l < N; ++l) {
           cplx acc = (k == e) ? S1[l] : cplx{0.0, 0.0};
+          AQ_UNROLL_N
           for (int c = 0; c < 4; ++c) {
             acc.re += dh[c] * ld(DC::TT + ((k * 4 + c) * N + l) * 2);
             acc.im += dh[c] * ld(DC::TT + ((k * 4 + c) * N + l) * 2 + 1);
@@ -310,7 +350,9 @@ struct DerivSplit {
         }
       }
       double trxx = 0.0;
+      AQ_UNROLL_N
       for (int k = 0; k < N; ++k)
+        AQ_UNROLL_N
         for (int l = 0; l < N; ++l) trxx += X[k * N + l].re * X[l * N + k].re - X[k * N + l].im * X[l * N + k].im;
       lap_out = l2 - trxx;
     }
@@ -333,12 +375,14 @@ struct DerivSplit {
     const bool diag = (k == e);
     // tangent of the layer input [h_k (DIN), g_up (DIN), g_dn (DIN), G_up[k]/n_up (4), G_dn[k]/n_dn (4)]
     double xd[DTOT], xs[DTOT];
+    AQ_UNROLL_N
     for (int q = 0; q < DIN; ++q) {
       if (l == 0) { xd[q] = diag ? h0e[q].d[0] : 0.0; xs[q] = (LAP && diag) ? h0e[q].s[0] : 0.0; }
       else { xd[q] = hd[q]; xs[q] = LAP ? hs[q] : 0.0; }
       xd[DIN + q] = gmd[0][q]; xd[2 * DIN + q] = gmd[1][q];
       xs[DIN + q] = LAP ? gms[0][q] : 0.0; xs[2 * DIN + q] = LAP ? gms[1][q] : 0.0;
     }
+    AQ_UNROLL_N
     for (int c = 0; c < 4; ++c) {
       // k == e: column block sums; otherwise only block s_e moves, by the row chain (e,k)
       xd[3 * DIN + c] = (diag ? sud[0][c] : (se == 0 ? crk.d[c] : 0.0)) * inv_n[0];
@@ -347,16 +391,20 @@ struct DerivSplit {
       xs[3 * DIN + 4 + c] = LAP ? (diag ? sus[1][c] : (se == 1 ? crk.s[c] : 0.0)) * inv_n[1] : 0.0;
     }
     double zd[4] = {0.0, 0.0, 0.0, 0.0}, zs[4] = {0.0, 0.0, 0.0, 0.0};
+    AQ_UNROLL_N
     for (int q = 0; q < Q; ++q) {
       double pd = 0.0, ps = 0.0;
+      AQ_UNROLL_N
       for (int c = 0; c < 4; ++c) { pd += xd[4 * q + c] * cw[4 * q + c]; if (LAP) ps += xs[4 * q + c] * cw[4 * q + c]; }
       pd *= 0.25; ps *= 0.25;
       const double t = ld(DC::T1 + (l * N + k) * QM + q);
       const double g = 1.0 - t * t;
       const double od = g * pd;
       const double os = LAP ? g * (ps - 2.0 * t * pd * pd) : 0.0;
+      AQ_UNROLL_N
       for (int m = 0; m < 4; ++m) { zd[m] += od * sw[q * 4 + m]; if (LAP) zs[m] += os * sw[q * 4 + m]; }
     }
+    AQ_UNROLL_N
     for (int m = 0; m < 4; ++m) {
       const double hn = ld(DC::H + (l * N + k) * 4 + m);                 // h_{l+1}[k][m]
       double t, ind, ins;

@@ -773,6 +773,7 @@ static __global__ void k_energy_final(int64_t B, double* __restrict__ e_l, Energ
 #include "ecp_pt.cuh"
 #include "ecp_grp.cuh"
 #include "coop_grad.cuh"
+#include "coop_lap.cuh"
 #include "param_grad.cuh"
 namespace aiqmc {
 
@@ -964,6 +965,32 @@ struct Launch {
     return AIQMC_OK;
   }
 
+  // gradient + per-coordinate second derivatives (+ MoveCache) of n_cfg configurations: the two-phase shared-memory
+  // kernel of coop_lap.cuh for N <= 16, the two-pass HBM-cache path beyond
+  static constexpr bool kLapCoop = (NE <= 16);
+  static int lap_pass(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_cfg, double* dcache,
+                 double* mc, double* phase, double* logabs, double* gout, double* lap_parts, int64_t lap_stride,
+                 cudaStream_t st) {
+#ifndef AIQMC_LAP_TWO_PASS
+    if constexpr (kLapCoop) {
+      using CL = CoopLapCfg<NE, NA>;
+      AQ_CUDA_OK(cudaFuncSetAttribute(k_lap_coop<NE, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, CL::kBytes));
+      AQ_CUDA_OK(cudaFuncSetAttribute(k_lap_coop<NE, NA>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+      unsigned g = 1;
+      const int rc = coop_grid(k_lap_coop<NE, NA>, CL::T, CL::kBytes, (n_cfg + CL::NG - 1) / CL::NG, &g);
+      if (rc != AIQMC_OK) return rc;
+      ++g_launch_count;
+      k_lap_coop<NE, NA><<<g, CL::T, CL::kBytes, st>>>(*sys, params, pos, n_cfg, mc, phase, logabs, gout, lap_parts, lap_stride);
+      AQ_CUDA_OK(cudaGetLastError());
+      return AIQMC_OK;
+    }
+#endif
+    MovedSrc ms{};
+    return deriv<true, 0, 0>(sys, params, pos, n_cfg, ms, dcache, mc, phase, logabs, gout, lap_parts, lap_stride, nullptr, 0,
+                             nullptr, st);
+  }
+
   // spin layouts the quadrature kernel is specialised for (ecp_pt.cuh): 0 = up-first, 1 = alternating; -1 = other
   static int spin_layout(const AiqmcSystem* sys) {
     constexpr int NUP = (NE + 1) / 2;
@@ -1082,8 +1109,8 @@ struct Launch {
     const int64_t chunk = deriv_chunk(NE, NA, true);
     for (int64_t c0 = 0; c0 < n_cfg; c0 += chunk) {
       const int64_t nc = (n_cfg - c0 < chunk) ? n_cfg - c0 : chunk;
-      const int rc = deriv<true, 0, 0>(sys, params, pos + c0 * 3 * NE, nc, ms, dcache, nullptr, phase + c0, logabs + c0,
-                                       grad + c0 * 3 * NE, parts, nc, nullptr, 0, nullptr, st);
+      const int rc = lap_pass(sys, params, pos + c0 * 3 * NE, nc, dcache, nullptr, phase + c0, logabs + c0, grad + c0 * 3 * NE,
+                         parts, nc, st);
       if (rc != AIQMC_OK) return rc;
       ++g_launch_count;
       k_sum_lap_parts<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(3 * NE, parts, nc, nc, lap + c0);
@@ -1138,8 +1165,7 @@ struct Launch {
     MovedSrc ms{};
     if (!with_ecp) {
       AQ_CUDA_OK(prep(k_energy_rest<NE, NA, false>));
-      const int rc = deriv<true, 0, 0>(sys, params, pos, B, ms, w.dcache, nullptr, w.phase, w.logabs, w.grad, w.lap_parts,
-                                       B, nullptr, 0, nullptr, st);
+      const int rc = lap_pass(sys, params, pos, B, w.dcache, nullptr, w.phase, w.logabs, w.grad, w.lap_parts, B, st);
       if (rc != AIQMC_OK) return rc;
       ++g_launch_count;
       k_energy_rest<NE, NA, false><<<g1, kThreads, kSmem, st>>>(*sys, params, pos, nullptr, B, e_l, w);
@@ -1148,8 +1174,7 @@ struct Launch {
       AQ_CUDA_OK(cs.upload_ecp(ecp));
       if (stages & 1) {
         AQ_CUDA_OK(prep(k_energy_rest<NE, NA, true>));
-        const int rc = deriv<true, 0, 0>(sys, params, pos, B, ms, w.dcache, w.cache, w.phase, w.logabs, w.grad,
-                                         w.lap_parts, B, nullptr, 0, nullptr, st);
+        const int rc = lap_pass(sys, params, pos, B, w.dcache, w.cache, w.phase, w.logabs, w.grad, w.lap_parts, B, st);
         if (rc != AIQMC_OK) return rc;
         ++g_launch_count;
         k_energy_rest<NE, NA, true><<<g1, kThreads, kSmem, st>>>(*sys, params, pos, rot, B, e_l, w);

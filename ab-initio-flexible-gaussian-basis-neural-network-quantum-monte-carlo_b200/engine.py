@@ -256,6 +256,27 @@ class WalkerEngine:
                                                   _ptr(ws), ws.numel(), _stream()), "aiqmc_branch_comb")
         return neww, inds
 
+    def rebalance(self, weights: torch.Tensor, pos: torch.Tensor, u: float, comm: Optional["NcclComm"] = None):
+        """Cross-GPU systematic comb + migration through the C ABI (aiqmc_rebalance_nccl): only the block totals of the
+        blocked weight scan and the walkers that change rank are exchanged.  Returns (new weight (device scalar), new
+        positions (B,row), source rank of every new walker (B,) int32, bytes this rank sent to other ranks)."""
+        B, row = pos.shape[0], pos.shape[1]
+        world, rank = (comm.world, comm.rank) if comm is not None else (1, 0)
+        weights = self._arg(weights, (B,), "weights")
+        pos = self._arg(pos, (B, row), "pos")
+        ws = self._workspace("rebalance", _nbytes(self.lib.aiqmc_rebalance_workspace_bytes(B, row, world),
+                                                  "aiqmc_rebalance_workspace_bytes"))
+        out = torch.empty_like(pos)
+        neww = torch.empty(1, dtype=torch.float64, device=self.device)
+        src = torch.empty(B, dtype=torch.int32, device=self.device)
+        moved = C.c_int64(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.aiqmc_rebalance_nccl(_ptr(weights), _ptr(pos), B, row, float(u), world, rank,
+                                                     comm.handle if comm is not None else None, _ptr(out), _ptr(neww),
+                                                     _ptr(src), C.byref(moved), _ptr(ws), ws.numel(), _stream()),
+                       "aiqmc_rebalance_nccl")
+        return neww, out, src, int(moved.value)
+
     def gather_walkers(self, pos: torch.Tensor, inds: torch.Tensor) -> torch.Tensor:
         """out[k] = pos[inds[k]]; pos may hold more rows than inds selects (cross-GPU population control)."""
         out = torch.empty((inds.shape[0], pos.shape[1]), dtype=pos.dtype, device=pos.device)
@@ -324,6 +345,46 @@ class WalkerEngine:
                                                 _ptr(r), _ptr(uu), _ptr(rr), B, float(tstep), _ptr(out), _ptr(acc),
                                                 _ptr(sel), _ptr(ws), ws.numel(), _stream()), "aiqmc_dmc_tmove")
         return out, acc, sel
+
+
+class NcclComm:
+    """An ncclComm_t owned by the C library (csrc/population.cu), created from a torch.distributed process group: rank 0
+    makes the 128-byte unique id, the group broadcasts it, every rank joins.  Used by the C-ABI collectives
+    (aiqmc_energy_allreduce, aiqmc_ecut_allreduce_min, aiqmc_rebalance_nccl)."""
+    _cache = {}
+
+    def __init__(self, process_group=None, device=None):
+        import torch.distributed as dist
+        self.lib = _lib.load()
+        self.group = process_group
+        self.rank, self.world = dist.get_rank(process_group), dist.get_world_size(process_group)
+        if not self.lib.aiqmc_nccl_available():
+            _lib.check(-5, "NCCL")
+        dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_ubyte * 128)()
+            _lib.check(self.lib.aiqmc_nccl_unique_id(buf), "aiqmc_nccl_unique_id")
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        bdev = dev if dist.get_backend(process_group) == "nccl" else torch.device("cpu")
+        ident = ident.to(bdev)
+        dist.broadcast(ident, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0, group=process_group)
+        raw = bytes(ident.cpu().tolist())
+        self.handle = C.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.aiqmc_nccl_comm_init(self.world, self.rank, raw, C.byref(self.handle)), "aiqmc_nccl_comm_init")
+
+    @classmethod
+    def for_group(cls, process_group=None, device=None) -> "NcclComm":
+        key = (id(process_group), str(device))
+        if key not in cls._cache:
+            cls._cache[key] = cls(process_group, device)
+        return cls._cache[key]
+
+    def close(self):
+        if self.handle:
+            self.lib.aiqmc_nccl_comm_destroy(self.handle)
+            self.handle = C.c_void_p()
 
 
 class HostStepPipeline:

@@ -14,7 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AIQMC_LIB", os.path.join(HERE, "libaiqmc_b200.so"))
 
 ERRORS = {-1: "AIQMC_E_UNSUPPORTED: no compiled instantiation for this (n_elec, n_atoms); add it to csrc/dispatch.h",
-          -2: "AIQMC_E_BADARG", -3: "AIQMC_E_CUDA", -4: "AIQMC_E_WORKSPACE"}
+          -2: "AIQMC_E_BADARG", -3: "AIQMC_E_CUDA", -4: "AIQMC_E_WORKSPACE",
+          -5: "AIQMC_E_NCCL: libnccl.so.2 could not be bound (set AIQMC_NCCL_LIB) or an NCCL call failed"}
 
 EXPORTS = ["aiqmc_param_layout", "aiqmc_supported", "aiqmc_last_cuda_error", "aiqmc_launch_count", "aiqmc_version", "aiqmc_psi_fwd",
            "aiqmc_psi_workspace_bytes", "aiqmc_psi_grad", "aiqmc_psi_fwdlap", "aiqmc_vmc_workspace_bytes", "aiqmc_vmc_sweep",
@@ -22,7 +23,9 @@ EXPORTS = ["aiqmc_param_layout", "aiqmc_supported", "aiqmc_last_cuda_error", "ai
            "aiqmc_dmc_tmove_workspace_bytes", "aiqmc_dmc_tmove", "aiqmc_dmc_ecut_min", "aiqmc_dmc_s", "aiqmc_dmc_weights", "aiqmc_branch_workspace_bytes",
            "aiqmc_branch_comb", "aiqmc_gather_walkers", "aiqmc_bench_dfma", "aiqmc_gto_eval", "aiqmc_param_grad_workspace_bytes",
            "aiqmc_psi_param_grad", "aiqmc_mh_workspace_bytes", "aiqmc_mh_step", "aiqmc_correlated_samples",
-           "aiqmc_weights_jacobian", "aiqmc_vmc_sweep_compact", "aiqmc_rng_sweep", "aiqmc_rng_rotations", "aiqmc_rng_uniform"]
+           "aiqmc_weights_jacobian", "aiqmc_vmc_sweep_compact", "aiqmc_rng_sweep", "aiqmc_rng_rotations", "aiqmc_rng_uniform",
+           "aiqmc_nccl_available", "aiqmc_nccl_unique_id", "aiqmc_nccl_comm_init", "aiqmc_nccl_comm_destroy", "aiqmc_energy_allreduce",
+           "aiqmc_ecut_allreduce_min", "aiqmc_rebalance_workspace_bytes", "aiqmc_rebalance_nccl"]
 
 _lib = None
 
@@ -58,6 +61,14 @@ def load() -> C.CDLL:
         "aiqmc_rng_sweep": (C.c_int, [C.c_uint64, C.c_uint32, i64, i64, i32, f64, vp, vp, vp, vp]),
         "aiqmc_rng_rotations": (C.c_int, [C.c_uint64, C.c_uint32, i64, i64, vp, vp]),
         "aiqmc_rng_uniform": (C.c_int, [C.c_uint64, C.c_uint32, i64, i64, i32, C.c_uint32, vp, vp]),
+        "aiqmc_nccl_available": (C.c_int, []),
+        "aiqmc_nccl_unique_id": (C.c_int, [vp]),
+        "aiqmc_nccl_comm_init": (C.c_int, [i32, i32, vp, C.POINTER(vp)]),
+        "aiqmc_nccl_comm_destroy": (C.c_int, [vp]),
+        "aiqmc_energy_allreduce": (C.c_int, [vp, vp, vp]),
+        "aiqmc_ecut_allreduce_min": (C.c_int, [vp, vp, vp]),
+        "aiqmc_rebalance_workspace_bytes": (i64, [i64, i32, i32]),
+        "aiqmc_rebalance_nccl": (C.c_int, [vp, vp, i64, i32, f64, i32, i32, vp, vp, vp, vp, C.POINTER(i64), vp, i64, vp]),
         "aiqmc_energy_workspace_bytes": (i64, [sysp, i64, i32]),
         "aiqmc_local_energy_ae": (C.c_int, [sysp, vp, vp, i64, vp, vp, i64, vp]),
         "aiqmc_local_energy_ecp": (C.c_int, [sysp, ecpp, vp, vp, vp, i64, vp, vp, i64, vp]),

@@ -5,15 +5,12 @@ replicated.  The data path has exactly three exchanges:
     (the two pmean's of Loss/pploss.py:165-167, DMC/total_energy.py:28-30);
   * the DMC e_cut of quirk Q20: a 1-double MIN all-reduce (DMC/S_matrix.py:4-25);
   * DMC population control across GPUs (new capability; the reference combs per device,
-    DMC/branch.py:10-34 inside pmap): the weights of all ranks are all-gathered, every rank runs the SAME
-    systematic comb over the global weight vector (so the result is independent of the rank count), keeps the
-    slice of source indices that fills its own B slots, and pulls those walkers out of an all-gather of the
-    positions (12N bytes per walker: 6 MB per rank at 65,536 carbon walkers -- bandwidth-trivial on NVLink, so
-    no point-to-point schedule is built).
-
-Everything here is device-agnostic torch + torch.distributed: on the GPU box the callables handed in are the
-CUDA kernels (WalkerEngine.branch_comb / gather_walkers) over NCCL; tests/test_distributed_gloo.py drives the
-same code with world_size 2 over gloo.
+    DMC/branch.py:10-34 inside pmap): ONE weight total per rank is all-gathered, every rank scans those totals the
+    same way, locates every tooth of the GLOBAL systematic comb rank-first and its own teeth walker-exact, and a
+    single uneven all-to-all moves only the walkers that change rank.  On the GPU this schedule runs
+    behind the C ABI (csrc/population.cu: aiqmc_rebalance_nccl over raw ncclSend/ncclRecv, block totals of a blocked
+    scan instead of rank totals so that the result is bit-identical to the single-GPU comb); `global_branch` below
+    is its device-agnostic torch statement, driven with world_size 2 over gloo by tests/test_distributed_gloo.py.
 """
 from __future__ import annotations
 
@@ -76,26 +73,48 @@ def allreduce_min(x: torch.Tensor, group=None) -> torch.Tensor:
     return x
 
 
-def global_branch(comb: Callable, gather: Callable, weights: torch.Tensor, positions: torch.Tensor, u: float,
-                  group=None):
-    """Cross-GPU systematic comb + walker migration.
+def global_branch(weights: torch.Tensor, positions: torch.Tensor, u: float, group=None):
+    """Cross-rank systematic comb + walker migration, device-agnostic torch statement of the schedule the CUDA/NCCL
+    path runs (csrc/population.cu: aiqmc_rebalance_nccl).  Exchanged: ONE weight total per rank
+    (all-gather), then only the walkers that change rank (all_to_all_single with uneven splits); the weights and the
+    positions of the other ranks are never gathered.
 
-    comb(weights_all (G*B,), u) -> (new_weight scalar, source indices (G*B,) int)   [DMC/branch.py:10-34]
-    gather(rows (G*B, 3N), idx (B,)) -> rows[idx]
-    weights (B,), positions (B,3N): this rank's shard (equal B on every rank).
-    Returns (new_weight, new_positions (B,3N), source (B,) global indices, n_imported) where n_imported counts
-    the walkers this rank received from other ranks.
-    """
+    weights (B,), positions (B,3N): this rank's shard (equal B on every rank); u in [0,1): the comb's uniform
+    (DMC/branch.py:21).  Slot k of rank r receives the walker that tooth r*B + k of the GLOBAL comb selects.
+    Returns (new_weight, new_positions (B,3N), source rank of every new walker (B,), walkers imported from other
+    ranks, bytes sent to other ranks).  tests/test_distributed_gloo.py drives it with world_size 2 over gloo."""
     rank, world = _world(group)
     B = weights.shape[0]
-    if world == 1:
-        neww, inds = comb(weights, u)
-        return neww, gather(positions, inds), inds, 0
-    w_all = torch.empty(world * B, dtype=weights.dtype, device=weights.device)
-    p_all = torch.empty((world * B,) + tuple(positions.shape[1:]), dtype=positions.dtype, device=positions.device)
-    dist.all_gather_into_tensor(w_all, weights.contiguous(), group=group)
-    dist.all_gather_into_tensor(p_all, positions.contiguous(), group=group)
-    neww, inds_all = comb(w_all, u)                       # identical on every rank (same inputs, same kernel)
-    mine = inds_all[rank * B:(rank + 1) * B]
-    imported = int(((mine < rank * B) | (mine >= (rank + 1) * B)).sum())
-    return neww, gather(p_all, mine), mine, imported
+    Bt = world * B
+    dev = weights.device
+    cum = torch.cumsum(weights, 0)
+    totals = cum[-1:].clone()
+    if world > 1:
+        parts = [torch.empty_like(totals) for _ in range(world)]
+        dist.all_gather(parts, totals, group=group)
+        totals = torch.cat(parts)
+    off = torch.zeros(world + 1, dtype=weights.dtype, device=dev)
+    for r in range(world):                                    # sequential: the same association on every rank
+        off[r + 1] = off[r] + totals[r]
+    wtot = off[world]
+    k = torch.arange(Bt, device=dev)
+    v = torch.remainder(u * wtot + k.to(weights.dtype) * (wtot / Bt), wtot)
+    src_rank = torch.searchsorted(off[1:].contiguous(), v, right=False).clamp_(max=world - 1)
+    mine = src_rank == rank
+    local = torch.searchsorted((off[rank] + cum).contiguous(), v[mine], right=False).clamp_(max=B - 1)
+    dest = torch.div(k[mine], B, rounding_mode="floor")
+    rows = positions[local].contiguous()                      # tooth order = grouped by destination, ascending
+    send_counts = torch.bincount(dest, minlength=world).tolist()
+    my_src = src_rank[rank * B:(rank + 1) * B]
+    recv_counts = torch.bincount(my_src, minlength=world).tolist()
+    if world > 1:
+        got = torch.empty((B,) + tuple(positions.shape[1:]), dtype=positions.dtype, device=dev)
+        dist.all_to_all_single(got, rows, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=group)
+    else:
+        got = rows
+    order = torch.sort(my_src, stable=True).indices           # messages arrive grouped by source, each in tooth order
+    new_pos = torch.empty_like(got)
+    new_pos[order] = got
+    row_bytes = positions[0].numel() * positions.element_size() if B else 0
+    moved = (sum(send_counts) - send_counts[rank]) * row_bytes
+    return wtot / Bt, new_pos, my_src, int((my_src != rank).sum()), int(moved)

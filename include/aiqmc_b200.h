@@ -30,7 +30,8 @@ enum {
   AIQMC_E_UNSUPPORTED = -1,  /* (n_elec, n_atoms) pair has no compiled instantiation */
   AIQMC_E_BADARG = -2,
   AIQMC_E_CUDA = -3,         /* a CUDA runtime call failed; aiqmc_last_cuda_error() has the code */
-  AIQMC_E_WORKSPACE = -4     /* workspace too small */
+  AIQMC_E_WORKSPACE = -4,    /* workspace too small */
+  AIQMC_E_NCCL = -5          /* NCCL could not be bound at run time (libnccl.so.2), or an NCCL call failed */
 };
 
 /* Static description of the molecule + spin layout.  Mirrors the arguments of
@@ -258,13 +259,43 @@ int aiqmc_dmc_s(const double* e_l, int32_t e_l_stride, const double* drift, int6
 int aiqmc_dmc_weights(double* weights, const double* s_old, const double* s_new, int64_t n_walkers,
                       double tau, double tdamp, void* stream);
 /* Systematic comb (branch.py:17-23): newinds (B) int32, new_weight (device scalar) = wtot/B.
- * u in [0,1) is the uniform the reference draws at branch.py:21. */
+ * u in [0,1) is the uniform the reference draws at branch.py:21.  The prefix sum is a blocked scan (2048 walkers per
+ * block, one CTA each; block totals scanned sequentially): its association order does not depend on B, which is what
+ * lets aiqmc_rebalance_nccl reproduce it across GPUs.  weights must be 16-byte aligned. */
 int64_t aiqmc_branch_workspace_bytes(int64_t n_walkers);
 int aiqmc_branch_comb(const double* weights, int64_t n_walkers, double u, int32_t* newinds,
                       double* new_weight, void* workspace, int64_t workspace_bytes, void* stream);
 /* Gather walkers by index: pos_out[b] = pos_in[newinds[b]]  (HBM-bound, 24N+4 B/walker). */
 int aiqmc_gather_walkers(const double* pos_in, const int32_t* newinds, int64_t n_walkers,
                          int32_t row_doubles, double* pos_out, void* stream);
+
+/* ---- multi-GPU: the three exchanges of the walker path behind the C ABI ------------------------
+ * NCCL is bound at run time (dlopen of libnccl.so.2 or $AIQMC_NCCL_LIB); the communicator is created once by the
+ * host from a 128-byte unique id that rank 0 makes and the host distributes (any transport), and is passed in as an
+ * opaque handle (an ncclComm_t). */
+int aiqmc_nccl_available(void);
+int aiqmc_nccl_unique_id(void* id128);
+int aiqmc_nccl_comm_init(int32_t world, int32_t rank, const void* id128, void** comm_out);
+int aiqmc_nccl_comm_destroy(void* comm);
+/* (1) energy mean / variance: in-place SUM all-reduce of the 4-double statistics of aiqmc_energy_stats
+ *     (the two pmean's of Loss/pploss.py:165-167). */
+int aiqmc_energy_allreduce(double* stats, void* comm, void* stream);
+/* (2) quirk Q20: in-place MIN all-reduce of the e_cut scalar of aiqmc_dmc_ecut_min (DMC/S_matrix.py:23). */
+int aiqmc_ecut_allreduce_min(double* ecut_min, void* comm, void* stream);
+/* (3) cross-GPU DMC population control (new capability; the reference combs per device, DMC/branch.py:10-34 under
+ *     pmap): the systematic comb over the weights of ALL ranks + migration of the selected walkers.  Exchanged: the
+ *     block totals of each rank's blocked scan (n_walkers/2048 doubles per rank) by all-gather, then ONE grouped
+ *     ncclSend/ncclRecv of only the walkers that change rank.  Equal n_walkers on every rank.  The result is identical,
+ *     bit for bit, to aiqmc_branch_comb + aiqmc_gather_walkers run on one GPU over the concatenated batch.
+ *     pos (B,row) -> pos_out (B,row): slot k of rank r receives the walker tooth r*B + k selects; new_weight (device
+ *     scalar) = total weight / (world*B); src_rank_out (B) int32 (may be NULL) = rank each new walker came from;
+ *     *moved_bytes_out (host, may be NULL) = bytes this rank sent to other ranks.  Synchronises the stream once (the
+ *     message sizes must reach the host).  world == 1 needs no communicator. */
+int64_t aiqmc_rebalance_workspace_bytes(int64_t n_walkers, int32_t row_doubles, int32_t world);
+int aiqmc_rebalance_nccl(const double* weights, const double* pos, int64_t n_walkers, int32_t row_doubles, double u,
+                         int32_t world, int32_t rank, void* comm, double* pos_out, double* new_weight,
+                         int32_t* src_rank_out, int64_t* moved_bytes_out, void* workspace, int64_t workspace_bytes,
+                         void* stream);
 
 /* ---- measurement aid ------------------------------------------------------------------ */
 /* Dependent-free FP64 FMA loop over the whole chip (148*8 CTAs x 256 threads x 8 chains):

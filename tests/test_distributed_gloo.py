@@ -44,13 +44,15 @@ def _worker(rank, world, port, B, out):
         m = parallel.allreduce_min(e.real.min().reshape(1).clone())
         assert float(m) == float(e_all.real.min())
         # global comb + migration against the single-process oracle on the concatenated arrays
-        neww, newp, src, imported = parallel.global_branch(O.branch, lambda rows, idx: rows[idx.long()], w_all[lo:hi],
-                                                           p_all[lo:hi], 0.37)
+        neww, newp, src, imported, moved = parallel.global_branch(w_all[lo:hi], p_all[lo:hi].contiguous(), 0.37)
         neww_ref, inds_ref = O.branch(w_all, 0.37)
-        assert float(neww) == float(neww_ref)
-        assert np.array_equal(src.numpy(), inds_ref.numpy()[lo:hi])
+        np.testing.assert_allclose(float(neww), float(neww_ref), rtol=1e-15)
+        assert np.array_equal(src.numpy(), inds_ref.numpy()[lo:hi] // B)          # source rank of every new walker
         np.testing.assert_array_equal(newp.numpy(), p_all.numpy()[inds_ref.numpy()[lo:hi]])
         assert imported == int(((inds_ref[lo:hi] < lo) | (inds_ref[lo:hi] >= hi)).sum())
+        # only the migrating walkers were sent: what this rank exported = what the other rank imported from it
+        exported = int(((inds_ref // B == rank) & (torch.arange(world * B) // B != rank)).sum())
+        assert moved == exported * 12 * 8 and moved < B * 12 * 8 * world
         # loss side (pploss.py:73-135 across ranks): pmean'ed clipping statistics, all-gathered median, pmean(grad)
         g_local = torch.tensor(rng.normal(size=5)) * (rank + 1)
         np.testing.assert_allclose(parallel.allreduce_mean(g_local).numpy(),
@@ -91,7 +93,7 @@ def test_single_process_global_branch_is_the_local_comb():
     rng = np.random.default_rng(3)
     w = torch.tensor(rng.uniform(0.1, 2.0, size=100))
     p = torch.tensor(rng.normal(size=(100, 6)))
-    neww, newp, src, imported = parallel.global_branch(O.branch, lambda rows, idx: rows[idx.long()], w, p, 0.9)
+    neww, newp, src, imported, moved = parallel.global_branch(w, p, 0.9)
     neww_ref, inds_ref = O.branch(w, 0.9)
-    assert imported == 0 and float(neww) == float(neww_ref)
+    assert imported == 0 and moved == 0 and abs(float(neww) - float(neww_ref)) < 1e-15
     np.testing.assert_array_equal(newp.numpy(), p.numpy()[inds_ref.numpy()])
