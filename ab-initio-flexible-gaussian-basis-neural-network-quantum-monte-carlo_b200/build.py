@@ -1,6 +1,7 @@
-"""Builds libaiqmc_b200.so (sm_100a) in-tree: one translation unit per (n_elec, n_atoms)
-instantiation, compiled in parallel with nvcc, linked into a plain CUDA-runtime shared
-library that exports the C ABI of include/aiqmc_b200.h."""
+"""Builds the CUDA libraries (sm_100a) in-tree with nvcc: libaiqmc_b200.so -- the C ABI of include/aiqmc_b200.h, the
+system-independent kernels and the plugin loader -- plus one libaiqmc_sys_<N>_<A>.so per (n_elec, n_atoms) instantiation
+of the per-system kernels (csrc/engine_impl.cuh), compiled in parallel.  csrc/dispatch.h names the prebuilt set;
+ensure_system(n, a) adds any other system at run time."""
 from __future__ import annotations
 
 import concurrent.futures as cf
@@ -27,16 +28,25 @@ def systems():
     return [(int(a), int(b)) for a, b in re.findall(r"X\((\d+),\s*(\d+)\)", body)]
 
 
-def _sources_digest():
+def _digest(files):
     h = hashlib.sha256()
-    for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
-        for name in sorted(os.listdir(root)):
-            p = os.path.join(root, name)
-            if os.path.isfile(p) and name.endswith((".cu", ".cuh", ".h")):
-                h.update(name.encode())
-                h.update(open(p, "rb").read())
+    for p in files:
+        h.update(os.path.basename(p).encode())
+        h.update(open(p, "rb").read())
     h.update(" ".join(FLAGS + ARCH + _extra_flags()).encode())
     return h.hexdigest()
+
+
+def _headers():
+    out = []
+    for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
+        out += [os.path.join(root, n) for n in sorted(os.listdir(root)) if n.endswith((".cuh", ".h"))]
+    return out
+
+
+def _sources_digest():
+    """What a per-system plugin depends on: every header (the .cu files of the core library do not enter)."""
+    return _digest(_headers())
 
 
 def _extra_flags():
@@ -50,6 +60,55 @@ def _extra_flags():
     return extra
 
 
+def plugin_path(n: int, a: int) -> str:
+    return os.path.join(HERE, f"libaiqmc_sys_{n}_{a}.so")
+
+
+def _inst_source(n: int, a: int) -> str:
+    os.makedirs(BUILD, exist_ok=True)
+    src = os.path.join(BUILD, f"inst_{n}_{a}.cu")
+    with open(src, "w") as f:
+        f.write('#include "' + os.path.join(CSRC, 'engine_impl.cuh') + '"\n'
+                f'extern "C" const aiqmc::OpsTable* aiqmc_ops_{n}_{a}() {{ return aiqmc::Launch<{n}, {a}>::table(); }}\n')
+    return src
+
+
+def _link_plugin(n: int, a: int, obj: str) -> str:
+    """One shared object per system, depending on the core library (g_launch_count / g_last_cuda_error live there)."""
+    out = plugin_path(n, a)
+    cmd = [NVCC] + ARCH + ["-shared", "-o", out, obj, "-L", HERE, "-l:" + os.path.basename(LIB), "-Xlinker", "-rpath",
+                           "-Xlinker", "$ORIGIN", "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link of {out} failed:\n{r.stdout}\n{r.stderr}")
+    return out
+
+
+def ensure_system(n: int, a: int, verbose: bool = False) -> str:
+    """Builds the kernel plugin of one (n_elec, n_atoms) system if it is missing or stale (any n <= 32, a <= 16; the
+    prebuilt set is csrc/dispatch.h) and makes the loaded library look again.  Needs nvcc at run time."""
+    if not (2 <= n <= 32 and 1 <= a <= 16):
+        raise ValueError(f"system size out of range: N={n}, A={a}")
+    build()                                            # the core library (and the prebuilt set) first
+    out = plugin_path(n, a)
+    stamp = os.path.join(BUILD, f"inst_{n}_{a}.stamp")
+    digest = _sources_digest()
+    if os.path.exists(out) and os.path.exists(stamp) and open(stamp).read() == digest:
+        return out
+    obj = _compile(_inst_source(n, a), os.path.join(BUILD, f"inst_{n}_{a}.o"), os.path.join(BUILD, f"inst_{n}_{a}.log"))
+    _link_plugin(n, a, obj)
+    with open(stamp, "w") as f:
+        f.write(digest)
+    if verbose:
+        print("built", out, file=sys.stderr)
+    try:
+        import ctypes
+        ctypes.CDLL(LIB).aiqmc_rescan_systems()
+    except OSError:
+        pass
+    return out
+
+
 def _compile(src, obj, log):
     cmd = [NVCC] + ARCH + FLAGS + _extra_flags() + ["-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -60,32 +119,44 @@ def _compile(src, obj, log):
     return obj
 
 
+def _fresh(stamp_file, digest, *outputs):
+    return all(os.path.exists(o) for o in outputs) and os.path.exists(stamp_file) and open(stamp_file).read() == digest
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compiles what is stale: a per-system plugin depends on the headers only, a core object on the headers and its own
+    .cu file -- editing abi.cu / rng.cu / population.cu does not recompile the ~8 MB per-system translation units."""
     os.makedirs(BUILD, exist_ok=True)
-    digest = _sources_digest()
-    stamp = os.path.join(BUILD, "stamp.txt")
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
-        return LIB
-    jobs = []
+    hdr = _sources_digest()
+    jobs = []                                     # (kind, key, src, obj, log, stamp, digest)
     for n, a in systems():
-        src = os.path.join(BUILD, f"inst_{n}_{a}.cu")
-        with open(src, "w") as f:
-            f.write('#include "' + os.path.join(CSRC, 'engine_impl.cuh') + '"\n'
-                    f'extern "C" const aiqmc::OpsTable* aiqmc_ops_{n}_{a}() {{ return aiqmc::Launch<{n}, {a}>::table(); }}\n')
-        jobs.append((src, os.path.join(BUILD, f"inst_{n}_{a}.o"), os.path.join(BUILD, f"inst_{n}_{a}.log")))
+        stamp = os.path.join(BUILD, f"inst_{n}_{a}.stamp")
+        obj = os.path.join(BUILD, f"inst_{n}_{a}.o")
+        if force or not _fresh(stamp, hdr, obj, plugin_path(n, a)):
+            jobs.append(("sys", (n, a), _inst_source(n, a), obj, os.path.join(BUILD, f"inst_{n}_{a}.log"), stamp, hdr))
+    core_objs, core_stale = [], False
     for name in ("abi", "wsizes", "gto", "rng", "population"):
-        jobs.append((os.path.join(CSRC, name + ".cu"), os.path.join(BUILD, name + ".o"),
-                     os.path.join(BUILD, name + ".log")))
-    with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
-        objs = list(ex.map(lambda j: _compile(*j), jobs))
-    cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    with open(stamp, "w") as f:
-        f.write(digest)
+        src, obj = os.path.join(CSRC, name + ".cu"), os.path.join(BUILD, name + ".o")
+        stamp, dg = os.path.join(BUILD, name + ".stamp"), _digest(_headers() + [src])
+        core_objs.append(obj)
+        if force or not _fresh(stamp, dg, obj):
+            jobs.append(("core", name, src, obj, os.path.join(BUILD, name + ".log"), stamp, dg))
+            core_stale = True
+    if jobs:
+        with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            list(ex.map(lambda j: _compile(j[2], j[3], j[4]), jobs))
+    if core_stale or not os.path.exists(LIB):
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + core_objs + ["-lcudart", "-ldl"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    for kind, key, src, obj, log, stamp, dg in jobs:
+        if kind == "sys":
+            _link_plugin(key[0], key[1], obj)         # one plugin per system, bound by the core on first use
+        with open(stamp, "w") as f:
+            f.write(dg)
     if verbose:
-        print("built", LIB, file=sys.stderr)
+        print("built", LIB, f"({len(jobs)} translation units recompiled)", file=sys.stderr)
     build_xla_ffi(verbose)
     return LIB
 

@@ -22,18 +22,48 @@ int64_t tmove_ws_bytes_rt(int n, int a, int64_t B);
 int64_t pgrad_ws_bytes_rt(int n, int a, int64_t B);
 }  // namespace aiqmc
 
-#define X(NE, NA) extern "C" const aiqmc::OpsTable* aiqmc_ops_##NE##_##NA();
-AIQMC_FOR_EACH_SYSTEM(X)
-#undef X
+// Per-system kernels live in their own shared objects (libaiqmc_sys_<N>_<A>.so next to this library, one per
+// (n_elec, n_atoms) instantiation of engine_impl.cuh, ~8 MB of SASS each) and are bound on first use: the core
+// library stays small, a process maps only the systems it runs, and a new molecule needs no edit of any source list --
+// aiqmc_b200.build.ensure_system(n, a) compiles its plugin (csrc/dispatch.h only names the set that is prebuilt).
+#include <dlfcn.h>
+#include <mutex>
+#include <stdio.h>
 
 using aiqmc::g_last_cuda_error;
 using aiqmc::g_launch_count;
 
+static std::mutex g_ops_mu;
+static const aiqmc::OpsTable* g_ops[AIQMC_MAX_ELEC + 1][AIQMC_MAX_ATOMS + 1];
+static bool g_ops_tried[AIQMC_MAX_ELEC + 1][AIQMC_MAX_ATOMS + 1];
+
 static const aiqmc::OpsTable* find_ops(int n, int a) {
-#define X(NE, NA) if (n == NE && a == NA) return aiqmc_ops_##NE##_##NA();
-  AIQMC_FOR_EACH_SYSTEM(X)
-#undef X
-  return nullptr;
+  auto& table = g_ops;
+  auto& tried = g_ops_tried;
+  if (n < 1 || n > AIQMC_MAX_ELEC || a < 1 || a > AIQMC_MAX_ATOMS) return nullptr;
+  std::lock_guard<std::mutex> lock(g_ops_mu);
+  if (table[n][a] || tried[n][a]) return table[n][a];
+  tried[n][a] = true;
+  Dl_info info;
+  if (!dladdr((const void*)&aiqmc_version, &info) || !info.dli_fname) return nullptr;
+  char path[4096], sym[64];
+  const char* slash = strrchr(info.dli_fname, '/');
+  const int dirlen = slash ? (int)(slash - info.dli_fname) : 0;
+  const char* env = getenv("AIQMC_PLUGIN_DIR");
+  if (env && *env) snprintf(path, sizeof(path), "%s/libaiqmc_sys_%d_%d.so", env, n, a);
+  else snprintf(path, sizeof(path), "%.*s/libaiqmc_sys_%d_%d.so", dirlen, info.dli_fname, n, a);
+  void* h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+  if (!h) return nullptr;
+  snprintf(sym, sizeof(sym), "aiqmc_ops_%d_%d", n, a);
+  typedef const aiqmc::OpsTable* (*Getter)();
+  Getter get = (Getter)dlsym(h, sym);
+  if (get) table[n][a] = get();
+  return table[n][a];
+}
+// forget a failed lookup (a plugin was built after the first query)
+extern "C" void aiqmc_rescan_systems(void) {
+  std::lock_guard<std::mutex> lock(g_ops_mu);
+  memset(g_ops_tried, 0, sizeof(g_ops_tried));
 }
 
 #define AQ_CUDA_OK(call)                                   \
@@ -209,7 +239,7 @@ int aiqmc_param_layout(int32_t n_elec, int32_t n_atoms, AiqmcLayout* out) {
 int aiqmc_supported(int32_t n_elec, int32_t n_atoms) { return find_ops(n_elec, n_atoms) != nullptr; }
 int aiqmc_last_cuda_error(void) { return g_last_cuda_error; }
 int64_t aiqmc_launch_count(void) { return g_launch_count; }
-const char* aiqmc_version(void) { return "aiqmc_b200 0.2 (sm_100a, fp64, two-pass derivatives, cached single-electron-move quadrature)"; }
+const char* aiqmc_version(void) { return "aiqmc_b200 0.3 (sm_100a, fp64, lane-per-electron derivative kernels, cached single-electron-move quadrature, per-system plugins)"; }
 
 static int psi_any(const AiqmcSystem* sys, const double* params, const double* pos, int64_t n_cfg, int mode,
                    double* phase, double* logabs, double* grad, double* lap, void* ws, int64_t ws_bytes, void* stream) {

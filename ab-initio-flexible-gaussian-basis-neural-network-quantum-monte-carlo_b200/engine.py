@@ -46,7 +46,19 @@ class WalkerEngine:
         self.sys = spec.c_struct()
         self.n, self.a = spec.nelectrons, spec.natoms
         if not self.lib.aiqmc_supported(self.n, self.a):
-            _lib.check(-1, f"system N={self.n}, A={self.a}")
+            # not in the prebuilt set (csrc/dispatch.h): compile this system's kernel plugin now, if nvcc is here
+            from . import build as _build
+            import os
+            try:
+                if os.environ.get("AIQMC_NO_AUTOBUILD"):
+                    raise RuntimeError("AIQMC_NO_AUTOBUILD is set")
+                _build.ensure_system(self.n, self.a)
+            except (OSError, RuntimeError, ValueError) as exc:
+                raise _lib.AiqmcError(f"system N={self.n}, A={self.a}: its kernel plugin is not built and could not be "
+                                      f"compiled here ({exc})") from exc
+            self.lib.aiqmc_rescan_systems()
+            if not self.lib.aiqmc_supported(self.n, self.a):
+                _lib.check(-1, f"system N={self.n}, A={self.a}")
         self.layout = _lib.param_layout(self.n, self.a)
         self.ecp = ecp
         self.params_dev: Optional[torch.Tensor] = None

@@ -13,11 +13,11 @@ from .system import AiqmcEcp, AiqmcLayout, AiqmcSystem
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AIQMC_LIB", os.path.join(HERE, "libaiqmc_b200.so"))
 
-ERRORS = {-1: "AIQMC_E_UNSUPPORTED: no compiled instantiation for this (n_elec, n_atoms); add it to csrc/dispatch.h",
+ERRORS = {-1: "AIQMC_E_UNSUPPORTED: the kernel plugin of this (n_elec, n_atoms) is not built; aiqmc_b200.build.ensure_system(n, a)",
           -2: "AIQMC_E_BADARG", -3: "AIQMC_E_CUDA", -4: "AIQMC_E_WORKSPACE",
           -5: "AIQMC_E_NCCL: libnccl.so.2 could not be bound (set AIQMC_NCCL_LIB) or an NCCL call failed"}
 
-EXPORTS = ["aiqmc_param_layout", "aiqmc_supported", "aiqmc_last_cuda_error", "aiqmc_launch_count", "aiqmc_version", "aiqmc_psi_fwd",
+EXPORTS = ["aiqmc_param_layout", "aiqmc_supported", "aiqmc_rescan_systems", "aiqmc_last_cuda_error", "aiqmc_launch_count", "aiqmc_version", "aiqmc_psi_fwd",
            "aiqmc_psi_workspace_bytes", "aiqmc_psi_grad", "aiqmc_psi_fwdlap", "aiqmc_vmc_workspace_bytes", "aiqmc_vmc_sweep",
            "aiqmc_energy_workspace_bytes", "aiqmc_local_energy_ae", "aiqmc_local_energy_ecp", "aiqmc_local_energy_ecp_stages", "aiqmc_energy_stats",
            "aiqmc_dmc_tmove_workspace_bytes", "aiqmc_dmc_tmove", "aiqmc_dmc_ecut_min", "aiqmc_dmc_s", "aiqmc_dmc_weights", "aiqmc_branch_workspace_bytes",
@@ -48,6 +48,7 @@ def load() -> C.CDLL:
     sig = {
         "aiqmc_param_layout": (C.c_int, [i32, i32, C.POINTER(AiqmcLayout)]),
         "aiqmc_supported": (C.c_int, [i32, i32]),
+        "aiqmc_rescan_systems": (None, []),
         "aiqmc_last_cuda_error": (C.c_int, []),
         "aiqmc_launch_count": (i64, []),
         "aiqmc_version": (C.c_char_p, []),

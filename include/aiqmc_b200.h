@@ -82,8 +82,12 @@ typedef struct AiqmcLayout {
 } AiqmcLayout;
 
 int aiqmc_param_layout(int32_t n_elec, int32_t n_atoms, AiqmcLayout* out);
-/* 1 if (n_elec,n_atoms) has a compiled kernel instantiation, else 0. */
+/* 1 if the kernels of (n_elec,n_atoms) can be bound, else 0.  Every system is its own shared object
+ * (libaiqmc_sys_<N>_<A>.so beside this library, or in $AIQMC_PLUGIN_DIR), loaded on first use; any n_elec <= 32,
+ * n_atoms <= 16 can be built (aiqmc_b200.build.ensure_system).  aiqmc_rescan_systems() forgets failed look-ups after
+ * a plugin has been built at run time. */
 int aiqmc_supported(int32_t n_elec, int32_t n_atoms);
+void aiqmc_rescan_systems(void);
 int aiqmc_last_cuda_error(void);
 /* Number of CUDA kernels this library has launched so far in this process (all entry points). */
 int64_t aiqmc_launch_count(void);

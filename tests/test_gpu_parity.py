@@ -196,15 +196,30 @@ def test_branch_comb_bit_exact_on_dyadic_weights_and_gather(B):
     assert np.mean(ig.cpu().numpy() != ir.numpy()) < 1e-3
 
 
-def test_unsupported_system_and_bad_args_fail_loudly():
+def test_unsupported_system_and_bad_args_fail_loudly(monkeypatch):
+    monkeypatch.setenv("AIQMC_NO_AUTOBUILD", "1")          # (7,3) is not in the prebuilt set; do not compile it here
     case = Case(n=7, natoms=3, spins=[1.] * 4 + [-1.] * 3, seed=3)
     with pytest.raises(aiqmc_b200.lib.AiqmcError):
         engine(case)
+    monkeypatch.delenv("AIQMC_NO_AUTOBUILD")
     case = Case(**CASES["C_ecp"], nwalkers=4)
     eng = engine(case)
     with pytest.raises(ValueError):
         eng.ecp = aiqmc_b200.make_ecp(1, list_l=2, **ecp_tables(1))
         eng.local_energy(torch.tensor(case.pos))           # rotation missing
+
+
+def test_system_outside_the_prebuilt_set_runs_through_its_own_plugin():
+    """(N, A) = (3, 2) is not named in csrc/dispatch.h: its kernels come from libaiqmc_sys_3_2.so, built on demand by
+    aiqmc_b200.build.ensure_system (tests/test_plugins.py builds it on the CPU box; here it is bound and checked)."""
+    case = Case(n=3, natoms=2, spins=[1., 1., -1.], seed=31, nwalkers=9, width=0.8)
+    eng = engine(case)
+    ph, la, g, lap = eng.psi(torch.tensor(case.pos), mode=2)
+    f = lambda x: case.net.apply(case.params, x, case.t_spins, case.t_atoms)[1]
+    lat, gt, d2 = O.grad_and_hess_diag(f, torch.tensor(case.pos))
+    np.testing.assert_allclose(la.cpu().numpy(), lat.detach().numpy(), rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(g.cpu().numpy(), gt.numpy(), rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(lap.cpu().numpy(), d2.sum(-1).numpy(), rtol=1e-7, atol=1e-7)
 
 
 @pytest.mark.parametrize("name,rich", [("C_ecp", True), ("C_ecp", False), ("N2_ecp", True), ("odd", True), ("h2like", False)])
