@@ -371,45 +371,99 @@ static __global__ void __launch_bounds__(kRedThreads) k_reduce_partials(const do
   }
 }
 
-// accept/reject (VMCmcstep.py:80-109, walkers_accept :18-25); HBM-bound, 1 thread per (b,i)
+// accept/reject (VMCmcstep.py:80-109, walkers_accept :18-25); HBM-bound, 1 thread per (b,i), 44N B/walker.
+// A CTA owns kRedThreads consecutive (walker, electron) pairs: its slices of grad, gnew, xprop, pos, gauss2 (compact
+// form), log|psi(x2)| and rnd are seven CONTIGUOUS blocks of HBM.  Full tiles are staged by seven TMA bulk copies
+// (cp.async.bulk, SASS UBLKCP) signalled on one mbarrier -- no thread issues a global load for them -- and the
+// accepted coordinates leave by a bulk store of the tile; the ragged last tile and unaligned callers take plain loads.
+struct AcceptTile {
+  double grad[kRedThreads * 3], gnew[kRedThreads * 3], xprop[kRedThreads * 3], pos[kRedThreads * 3], g2[kRedThreads * 3];
+  double la2[kRedThreads], rnd[kRedThreads];
+};
 static __global__ void __launch_bounds__(kRedThreads) k_sweep_accept(int n, double* __restrict__ pos,
                                                               const double* __restrict__ gauss2,
                                                               const double* __restrict__ rnd, int64_t B, double tau,
-                                                              double acyrus, int signed_ratio, int g2_compact,
+                                                              double acyrus, int signed_ratio, int g2_compact, int use_tma,
                                                               uint8_t* __restrict__ accept,
                                                               double* __restrict__ grad_eff_old, SweepWs w) {
   __shared__ double red[kRedThreads / 32];
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ __align__(16) AcceptTile tile;
+  __shared__ __align__(8) unsigned long long bar;
+  const int64_t t0 = (int64_t)blockIdx.x * kRedThreads;
+  const int64_t t = t0 + threadIdx.x;
+  const bool staged = use_tma && g2_compact && (t0 + kRedThreads <= B * n);
+  if (staged) {
+    const unsigned b32 = (unsigned)__cvta_generic_to_shared(&bar);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b32));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      constexpr unsigned b3 = kRedThreads * 3 * sizeof(double), b1 = kRedThreads * sizeof(double);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b32), "r"(5 * b3 + 2 * b1) : "memory");
+      auto bulk = [&](void* dst, const void* src, unsigned bytes) {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"(b32) : "memory");
+      };
+      bulk(tile.grad, w.grad + t0 * 3, b3);
+      bulk(tile.gnew, w.gnew + t0 * 3, b3);
+      bulk(tile.xprop, w.xprop + t0 * 3, b3);
+      bulk(tile.pos, pos + t0 * 3, b3);
+      bulk(tile.g2, gauss2 + t0 * 3, b3);
+      bulk(tile.la2, w.logabs2 + t0, b1);
+      bulk(tile.rnd, rnd + t0, b1);
+    }
+    __syncthreads();
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "AQ_ACC_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra AQ_ACC_READY;\n"
+        "bra AQ_ACC_WAIT;\n"
+        "AQ_ACC_READY:\n"
+        "}\n" ::"r"(b32) : "memory");
+  }
   double s_new = 0.0, s_prop = 0.0;
   if (t < B * n) {
     const int64_t b = t / n;
     const int i = (int)(t - b * n);
+    const int lt = threadIdx.x;
     const double te_old = taueff_of(w.scal[0], tau, acyrus), te_new = taueff_of(w.scal[1], tau, acyrus);
     double tp = 0.0;
     for (int c = 0; c < 3; ++c) {
-      const double ge = w.grad[b * 3 * n + 3 * i + c] * te_old;
-      const double gn = w.gnew[t * 3 + c] * te_new;
+      const double ge = (staged ? tile.grad[lt * 3 + c] : w.grad[b * 3 * n + 3 * i + c]) * te_old;
+      const double gn = (staged ? tile.gnew[lt * 3 + c] : w.gnew[t * 3 + c]) * te_new;
       // only the diagonal 3-blocks of the reference's (B,N,3N) array are ever read (VMCmcstep.py:86-94);
       // g2_compact: the caller passes just those, (B,N,3)
-      const double g2 = g2_compact ? gauss2[t * 3 + c] : gauss2[(b * n + i) * 3 * n + 3 * i + c];
+      const double g2 = staged ? tile.g2[lt * 3 + c] : (g2_compact ? gauss2[t * 3 + c] : gauss2[(b * n + i) * 3 * n + 3 * i + c]);
       const double fwd = g2 * g2;
       const double bw = g2 + (ge + gn) * tau;
       tp += exp((fwd - bw * bw) / (2.0 * tau));
       if (grad_eff_old) grad_eff_old[b * 3 * n + 3 * i + c] = ge;
     }
-    const double ratio = exp(w.logabs2[t] - w.logabs1[b]);
+    const double ratio = exp((staged ? tile.la2[lt] : w.logabs2[t]) - w.logabs1[b]);
     double acc = fabs(ratio) * fabs(ratio) * tp;
     if (signed_ratio) acc *= (ratio > 0.0) ? 1.0 : (ratio < 0.0 ? -1.0 : 0.0);
-    const bool ok = acc > rnd[t];
+    const bool ok = acc > (staged ? tile.rnd[lt] : rnd[t]);
     for (int c = 0; c < 3; ++c) {
-      const double xp = w.xprop[t * 3 + c];
-      const double xo = pos[b * 3 * n + 3 * i + c];
+      const double xp = staged ? tile.xprop[lt * 3 + c] : w.xprop[t * 3 + c];
+      const double xo = staged ? tile.pos[lt * 3 + c] : pos[b * 3 * n + 3 * i + c];
       const double xn = ok ? xp : xo;
-      if (ok) pos[b * 3 * n + 3 * i + c] = xp;
+      if (staged) tile.pos[lt * 3 + c] = xn;
+      else if (ok) pos[b * 3 * n + 3 * i + c] = xp;
       s_new += xn;
       s_prop += xp;
     }
     if (accept) accept[t] = ok ? 1 : 0;
+  }
+  if (staged) {                         // the tile of new positions goes back by ONE bulk store
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   ::"l"(pos + t0 * 3), "r"((unsigned)__cvta_generic_to_shared(tile.pos)), "r"((unsigned)(kRedThreads * 3 * sizeof(double))) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
   }
   const double a = block_sum<kRedThreads>(s_new, red);
   const double c2 = block_sum<kRedThreads>(s_prop, red);
@@ -1142,7 +1196,8 @@ struct Launch {
     ++g_launch_count;
     k_reduce_partials<<<1, kRedThreads, 0, st>>>(w.partials, (int)rows, 1, 1, w.scal, 1);
     ++g_launch_count;
-    k_sweep_accept<<<g3, kRedThreads, 0, st>>>(NE, pos, gauss2, rnd, B, tau, acyrus, signed_ratio, g2_compact, accept,
+    const int use_tma = ((((uintptr_t)pos) | ((uintptr_t)gauss2) | ((uintptr_t)rnd)) & 15) == 0;   // bulk copies need 16-byte alignment
+    k_sweep_accept<<<g3, kRedThreads, 0, st>>>(NE, pos, gauss2, rnd, B, tau, acyrus, signed_ratio, g2_compact, use_tma, accept,
                                                grad_eff_old, w);
     ++g_launch_count;
     k_reduce_partials<<<1, kRedThreads, 0, st>>>(w.partials, (int)g3, 2, 2, w.scal, 2);

@@ -11,6 +11,7 @@
 // are the in-house fexp (10 FP64 ops) shared by value / gradient / Laplacian of a primitive.
 #include <cuda_runtime.h>
 #include <atomic>
+#include <mutex>
 #include <string.h>
 
 #include "../../include/aiqmc_b200.h"
@@ -114,6 +115,63 @@ __global__ void __launch_bounds__(128) k_gto_eval(const double* __restrict__ poi
     }
   }
 }
+// Tiled variant: a CTA owns 128 consecutive points.  The coordinates arrive by coalesced loads through shared memory,
+// every thread evaluates its point into a shared-memory tile [point][AO] (rows of odd length: conflict-free), and the
+// tile -- a CONTIGUOUS block of val / grad / lap in HBM because the outputs are point-major -- leaves by coalesced
+// 16-byte stores.  The direct kernel above writes 65 doubles per thread at a stride of nao*8 bytes between lanes (one
+// 32-byte sector per store): 24 B in + 520 B out per point at C/cc-pVDZ ran at a few hundred GB/s.
+constexpr int kGtoTile = 128;
+__global__ void __launch_bounds__(kGtoTile) k_gto_eval_tiled(const double* __restrict__ points, int64_t n, int nao,
+                                                             double* __restrict__ val, double* __restrict__ grad,
+                                                             double* __restrict__ lap) {
+  extern __shared__ __align__(16) double s_gto[];
+  double* spts = s_gto;                                 // [128][3]
+  double* sval = spts + 3 * kGtoTile;                   // [128][nao]
+  double* sgrad = sval + kGtoTile * nao;                // [128][nao][3]
+  double* slap = sgrad + 3 * kGtoTile * nao;            // [128][nao]
+  if (threadIdx.x < kExpTab) g_exp_tab[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / kExpTab));
+  const int64_t t0 = (int64_t)blockIdx.x * kGtoTile;
+  const int np = (int)((n - t0) < kGtoTile ? (n - t0) : kGtoTile);
+  for (int q = threadIdx.x; q < 3 * np; q += kGtoTile) spts[q] = points[3 * t0 + q];
+  __syncthreads();
+  const double* tab = g_exp_tab;
+  if ((int)threadIdx.x < np) {
+    const double x = spts[3 * threadIdx.x], y = spts[3 * threadIdx.x + 1], z = spts[3 * threadIdx.x + 2];
+    for (int sidx = 0; sidx < c_gto.n_shells; ++sidx) {
+      const AiqmcGtoShell& sh = c_gto.shells[sidx];
+      const double dx = x - c_gto.centres[sh.centre][0], dy = y - c_gto.centres[sh.centre][1],
+                   dz = z - c_gto.centres[sh.centre][2];
+      const double d2 = dx * dx + dy * dy + dz * dz;
+      double f = 0.0, f1 = 0.0, f2 = 0.0;
+      for (int p = 0; p < sh.n_prim; ++p) {
+        const double a = sh.alpha[p];
+        const double e = sh.coef[p] * fexp(-a * d2, tab);
+        f += e;
+        f1 -= a * e;
+        f2 += a * a * e;
+      }
+      switch (sh.l) {            // uniform across the grid
+        case 0: shell_out<0>(sh, dx, dy, dz, f, f1, f2, d2, threadIdx.x, nao, sval, grad ? sgrad : nullptr, lap ? slap : nullptr); break;
+        case 1: shell_out<1>(sh, dx, dy, dz, f, f1, f2, d2, threadIdx.x, nao, sval, grad ? sgrad : nullptr, lap ? slap : nullptr); break;
+        case 2: shell_out<2>(sh, dx, dy, dz, f, f1, f2, d2, threadIdx.x, nao, sval, grad ? sgrad : nullptr, lap ? slap : nullptr); break;
+        default: shell_out<3>(sh, dx, dy, dz, f, f1, f2, d2, threadIdx.x, nao, sval, grad ? sgrad : nullptr, lap ? slap : nullptr); break;
+      }
+    }
+  }
+  __syncthreads();
+  auto stream_out = [&](const double* src, double* dst, int64_t count) {        // dst + t0*... is 16-byte aligned when count is even
+    if ((count & 1) == 0 && (((uintptr_t)dst) & 15) == 0) {
+      const double2* s2 = reinterpret_cast<const double2*>(src);
+      double2* d2p = reinterpret_cast<double2*>(dst);
+      for (int64_t q = threadIdx.x; q < count / 2; q += kGtoTile) d2p[q] = s2[q];
+    } else {
+      for (int64_t q = threadIdx.x; q < count; q += kGtoTile) dst[q] = src[q];
+    }
+  };
+  stream_out(sval, val + t0 * nao, (int64_t)np * nao);
+  if (grad) stream_out(sgrad, grad + t0 * nao * 3, (int64_t)np * nao * 3);
+  if (lap) stream_out(slap, lap + t0 * nao, (int64_t)np * nao);
+}
 }  // namespace aiqmc
 
 extern "C" int aiqmc_gto_eval(const AiqmcGtoShell* shells, int32_t n_shells, const double* centres, int32_t n_centres,
@@ -124,7 +182,12 @@ extern "C" int aiqmc_gto_eval(const AiqmcGtoShell* shells, int32_t n_shells, con
       n_centres > AIQMC_GTO_MAX_CENTRES || n_points < 0 || nao < 1)
     return AIQMC_E_BADARG;
   if (n_points > 0 && (!points || !val)) return AIQMC_E_BADARG;
-  static GtoTable h;
+  static GtoTable h[64];                 // what each DEVICE's constant copy holds (a second GPU re-uploads)
+  static bool valid[64];
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return AIQMC_E_CUDA;
   GtoTable t;
   memset(&t, 0, sizeof(t));
   t.n_shells = n_shells;
@@ -139,16 +202,22 @@ extern "C" int aiqmc_gto_eval(const AiqmcGtoShell* shells, int32_t n_shells, con
   memcpy(t.centres, centres, sizeof(double) * 3 * n_centres);
   if (n_points == 0) return AIQMC_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool valid = false;
-  if (!valid || memcmp(&h, &t, sizeof(t)) != 0) {
+  if (!valid[dev] || memcmp(&h[dev], &t, sizeof(t)) != 0) {
     const cudaError_t e = cudaMemcpyToSymbolAsync(c_gto, &t, sizeof(t), 0, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) { g_last_cuda_error = (int)e; return AIQMC_E_CUDA; }
     cudaStreamSynchronize(st);       // `t` is a stack object: the copy must have read it before we return
-    h = t;
-    valid = true;
+    h[dev] = t;
+    valid[dev] = true;
   }
   ++g_launch_count;
-  k_gto_eval<<<(unsigned)((n_points + 127) / 128), 128, 0, st>>>(points, n_points, nao, val, grad, lap);
+  const size_t smem = (size_t)(3 * kGtoTile + 5 * kGtoTile * nao) * sizeof(double);
+  if (smem <= 200 * 1024) {              // the output tile fits shared memory: coalesced stores
+    const cudaError_t ea = cudaFuncSetAttribute(k_gto_eval_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ea != cudaSuccess) { g_last_cuda_error = (int)ea; return AIQMC_E_CUDA; }
+    k_gto_eval_tiled<<<(unsigned)((n_points + kGtoTile - 1) / kGtoTile), kGtoTile, smem, st>>>(points, n_points, nao, val, grad, lap);
+  } else {
+    k_gto_eval<<<(unsigned)((n_points + 127) / 128), 128, 0, st>>>(points, n_points, nao, val, grad, lap);
+  }
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_last_cuda_error = (int)e; return AIQMC_E_CUDA; }
   return AIQMC_OK;

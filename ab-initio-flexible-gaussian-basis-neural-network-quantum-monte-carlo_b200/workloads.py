@@ -35,6 +35,37 @@ C_ECP_TABLES = dict(rn_local=np.array([[1.0, 3.0, 2.0]]), local_coes=np.array([[
                     non_local_exps=np.array([[[7.76079, 0], [0, 0], [0, 0]]]))
 
 
+# the reference's own contracted-Gaussian basis file, AIQMC/C.cc-pVDZ.nwchem:1-27 verbatim (2s + 2p + 1d = 13 AOs from
+# 21 primitives): the A0 micro-benchmark of SURVEY 8(d) evaluates it at walkers x electrons points
+C_CC_PVDZ = """C s
+13.073594 0.0051583
+6.541187 0.0603424
+4.573411 -0.1978471
+1.637494 -0.0810340
+0.819297 0.2321726
+0.409924 0.2914643
+0.231300 0.4336405
+0.102619 0.2131940
+0.051344 0.0049848
+C s
+0.127852 1.000000
+C p
+9.934169 0.0209076
+3.886955 0.0572698
+1.871016 0.1122682
+0.935757 0.2130082
+0.468003 0.2835815
+0.239473 0.3011207
+0.117063 0.2016934
+0.058547 0.0453575
+0.029281 0.0029775
+C p
+0.149161 1.000000
+C d
+0.561160 1.000000
+"""
+
+
 def ecp_tables(natoms: int) -> Dict[str, np.ndarray]:
     return {k: np.repeat(v, natoms, axis=0).copy() for k, v in C_ECP_TABLES.items()}
 

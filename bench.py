@@ -417,6 +417,16 @@ def time_hbm_kernels(eng, B, n, dev, flush):
     out["energy_stats"] = {"ms": ms, "GB_per_s": (B * 16) / (ms * 1e-3) / 1e9, "bytes": B * 16}
     ms = timed(lambda: eng.branch_comb(w, 0.37))
     out["branch_comb"] = {"ms": ms, "GB_per_s": (B * 28) / (ms * 1e-3) / 1e9, "bytes": B * 28}
+    # A0 micro-benchmark: the reference's C cc-pVDZ basis (13 AOs) with gradient and Laplacian at
+    # walkers x 6 electron positions: 24 B in, 65 doubles out per point
+    import aiqmc_b200
+    from aiqmc_b200 import workloads as W
+    basis = aiqmc_b200.GaussianBasis.from_nwchem(W.C_CC_PVDZ, np.zeros((1, 3)), device=dev)
+    pts = torch.randn((B * 6, 3), dtype=torch.float64, device=dev)
+    ms = timed(lambda: basis.eval(pts))
+    nbytes = B * 6 * (24 + 65 * 8)
+    out["gto_eval_A0"] = {"ms": ms, "GB_per_s": nbytes / (ms * 1e-3) / 1e9, "bytes": nbytes, "points": B * 6,
+                          "points_per_s": B * 6 / (ms * 1e-3), "what": "C cc-pVDZ, 13 AOs, value + gradient + Laplacian"}
     return out
 
 
