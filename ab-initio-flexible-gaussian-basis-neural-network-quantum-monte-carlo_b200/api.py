@@ -540,17 +540,20 @@ def trial_energy(e_est, weights: torch.Tensor, feedback: float):
 
 
 def branch_global(engine: WalkerEngine, weights: torch.Tensor, positions: torch.Tensor, key, process_group=None,
-                  return_bytes: bool = False):
+                  return_bytes: bool = False, mode: str = "balanced"):
     """Population control across all GPUs of the job (the reference combs per device only): the
     systematic comb of DMC/branch.py:10-34 over the weights of ALL ranks + migration of the selected walkers, through
     the C ABI (aiqmc_rebalance_nccl): exchanged are the block totals of each rank's weight scan (all-gather) and, in one
     grouped NCCL send/recv, only the walkers that change rank.  Returns (new weight scalar, new positions (B,3N),
-    source rank of every new walker (B,) int32, walkers imported from other ranks[, bytes this rank sent])."""
+    source rank of every new walker (B,) int32, walkers imported from other ranks[, bytes this rank sent]).
+    mode "balanced" (default): same survivors and multiplicities as the global comb, each rank keeps its own walkers
+    and only the population imbalance travels; "ordered": the exact slot order of a single-GPU comb over the
+    concatenated batch (moves nearly every walker: the comb's base offset rotates the teeth)."""
     from .engine import NcclComm
     import torch.distributed as dist
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
     comm = NcclComm.for_group(process_group, engine.device) if multi else None
-    neww, new_pos, src, moved = engine.rebalance(weights, positions, float(key), comm)
+    neww, new_pos, src, moved = engine.rebalance(weights, positions, float(key), comm, mode=mode)
     rank = comm.rank if comm is not None else 0
     imported = int((src != rank).sum())
     return (neww, new_pos, src, imported, moved) if return_bytes else (neww, new_pos, src, imported)

@@ -245,6 +245,47 @@ __global__ void __launch_bounds__(1024) k_plan(const int32_t* __restrict__ src_r
   if (threadIdx.x == 0) counts[mode * world + p] = base_s;
 }
 
+// Balanced mode: one CTA per rank p counts the teeth rank p owns (counts[p]); the CTA of this rank also writes the
+// stable list of its own teeth, owned_idx[pos] = local source index, in tooth order (up to world*B entries).
+__global__ void __launch_bounds__(1024) k_owned(const int32_t* __restrict__ src_rank, const int32_t* __restrict__ src_local,
+                                                int world, int rank, int64_t Btot, int32_t* __restrict__ owned_idx,
+                                                int32_t* __restrict__ counts) {
+  __shared__ int wcnt[32];
+  __shared__ int base_s;
+  const int p = blockIdx.x;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base_s = 0;
+  __syncthreads();
+  for (int64_t c0 = 0; c0 < Btot; c0 += 1024) {
+    const int64_t k = c0 + threadIdx.x;
+    const bool flag = k < Btot && src_rank[k] == p;
+    const unsigned m = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) wcnt[wp] = __popc(m);
+    __syncthreads();
+    int woff = 0;
+    for (int i = 0; i < wp; ++i) woff += wcnt[i];
+    const int pos = base_s + woff + __popc(m & ((1u << lane) - 1u));
+    if (flag && p == rank) owned_idx[pos] = src_local[k];
+    __syncthreads();
+    if (threadIdx.x == 0) { int tot = 0; for (int i = 0; i < 32; ++i) tot += wcnt[i]; base_s += tot; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) counts[p] = base_s;
+}
+// rows[t] = pos[idx[t]], t < n
+__global__ void k_gather_rows(const double* __restrict__ pos, const int32_t* __restrict__ idx, int64_t n, int row,
+                              double* __restrict__ out) {
+  const int64_t total = n * row;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / row;
+    out[t] = pos[(int64_t)idx[r] * row + (int)(t - r * row)];
+  }
+}
+__global__ void k_fill_i32(int32_t* __restrict__ out, int64_t n, int32_t v) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = v;
+}
+
 // rows[t] = pos[idx[t]] for the concatenated send lists (seg_off[p] = first row of destination p's message)
 __global__ void k_pack_rows(const double* __restrict__ pos, const int32_t* __restrict__ send_idx, const int64_t* __restrict__ seg_off,
                             const int32_t* __restrict__ counts, int world, int64_t B, int row, double* __restrict__ sendbuf) {
@@ -415,6 +456,23 @@ int aiqmc_nccl_comm_init(int32_t world, int32_t rank, const void* id128, void** 
   memcpy(&id, id128, sizeof(id));
   ncclComm_t c = nullptr;
   AQ_NCCL_OK(a->CommInitRank(&c, world, id, rank));
+  // NCCL connects a pair of ranks lazily, on the first send/recv between them (~100 ms per new pair); the comb's
+  // rotation sends to different peers from step to step, so every pair is connected here, once, by one tiny grouped
+  // all-to-all (measured without it: a DMC step on 8 GPUs took 348 ms instead of 19 ms while new pairs kept appearing)
+  if (world > 1) {
+    double* scratch = nullptr;
+    AQ_CUDA_OK(cudaMalloc(&scratch, 2 * world * sizeof(double)));
+    AQ_CUDA_OK(cudaMemset(scratch, 0, 2 * world * sizeof(double)));
+    AQ_NCCL_OK(a->GroupStart());
+    for (int q = 0; q < world; ++q) {
+      if (q == rank) continue;
+      AQ_NCCL_OK(a->Send(scratch + q, 1, ncclDouble, q, c, 0));
+      AQ_NCCL_OK(a->Recv(scratch + world + q, 1, ncclDouble, q, c, 0));
+    }
+    AQ_NCCL_OK(a->GroupEnd());
+    AQ_CUDA_OK(cudaStreamSynchronize(0));
+    AQ_CUDA_OK(cudaFree(scratch));
+  }
   *comm_out = c;
   return AIQMC_OK;
 }
@@ -452,10 +510,11 @@ int64_t aiqmc_rebalance_workspace_bytes(int64_t n_walkers, int32_t row_doubles, 
 
 /* see include/aiqmc_b200.h */
 int aiqmc_rebalance_nccl(const double* weights, const double* pos, int64_t n_walkers, int32_t row_doubles, double u,
-                         int32_t world, int32_t rank, void* comm, double* pos_out, double* new_weight, int32_t* src_rank_out,
-                         int64_t* moved_bytes_out, void* workspace, int64_t workspace_bytes, void* stream) {
+                         int32_t world, int32_t rank, void* comm, int32_t mode, double* pos_out, double* new_weight,
+                         int32_t* src_rank_out, int64_t* moved_bytes_out, void* workspace, int64_t workspace_bytes,
+                         void* stream) {
   if (!weights || !pos || !pos_out || !new_weight || !workspace || n_walkers <= 0 || row_doubles < 1 || world < 1 || rank < 0 ||
-      rank >= world)
+      rank >= world || (mode != 0 && mode != 1))
     return AIQMC_E_BADARG;
   if (workspace_bytes < aiqmc_rebalance_workspace_bytes(n_walkers, row_doubles, world)) return AIQMC_E_WORKSPACE;
   if (((uintptr_t)weights & 15) != 0 || world > 64) return AIQMC_E_BADARG;
@@ -484,6 +543,55 @@ int aiqmc_rebalance_nccl(const double* weights, const double* pos, int64_t n_wal
   k_scan_offsets<<<1, 32, 0, st>>>(totals_all, nba, off);
   // 2. every tooth of the global comb: owner rank (+ local index when it is ours); send / receive plans
   k_teeth<<<(unsigned)((Bt + 255) / 256), 256, 0, st>>>(in_block, off, nb, world, rank, B, u, src_rank, src_local, new_weight);
+  if (mode == 1) {
+    // ---- balanced: every rank keeps its own selected walkers (in tooth order) and only the SURPLUS of ranks that own
+    //      more than B teeth travels, to the ranks that own fewer -- the multiset of walkers is that of the global comb,
+    //      their order is not.  Walkers are exchangeable, so a DMC run is unaffected; the wire carries the population
+    //      imbalance only (the ordered mode moves almost every walker: the comb's base offset u*wtot rotates the teeth
+    //      by a fraction u of the whole population).
+    int32_t* owned_idx = send_idx;
+    k_owned<<<world, 1024, 0, st>>>(src_rank, src_local, world, rank, Bt, owned_idx, counts);
+    AQ_CUDA_OK(cudaGetLastError());
+    int32_t c[64];
+    AQ_CUDA_OK(cudaMemcpyAsync(c, counts, world * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    AQ_CUDA_OK(cudaStreamSynchronize(st));
+    int64_t tot = 0;
+    for (int q = 0; q < world; ++q) tot += c[q];
+    if (tot != Bt) return AIQMC_E_CUDA;                       // every tooth has exactly one owner
+    const int64_t mine = c[rank], keep = mine < B ? mine : B;
+    g_launch_count += 2;
+    if (mine > 0) k_gather_rows<<<148 * 4, 256, 0, st>>>(pos, owned_idx, mine, row_doubles, sendbuf);
+    if (keep > 0) AQ_CUDA_OK(cudaMemcpyAsync(pos_out, sendbuf, (size_t)keep * row_doubles * 8, cudaMemcpyDeviceToDevice, st));
+    if (src_rank_out) k_fill_i32<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(src_rank_out, B, rank);
+    // deterministic matching of surplus to deficit, identical on every rank: walk both lists in rank order
+    int64_t moved = 0;
+    if (world > 1) {
+      AQ_NCCL_OK(a->GroupStart());
+      int d = 0;
+      int64_t dfill = 0;                                       // rows already assigned to deficit rank d
+      for (int sidx = 0; sidx < world; ++sidx) {
+        int64_t extra = (int64_t)c[sidx] - B, sent = 0;
+        while (extra > 0) {
+          while (d < world && (int64_t)c[d] + dfill >= B) { ++d; dfill = 0; }
+          if (d >= world) return AIQMC_E_CUDA;
+          const int64_t room = B - c[d] - dfill, n = extra < room ? extra : room;
+          if (sidx == rank) {
+            AQ_NCCL_OK(a->Send(sendbuf + (B + sent) * row_doubles, (size_t)n * row_doubles, ncclDouble, d, (ncclComm_t)comm, st));
+            moved += n * row_doubles * 8;
+          }
+          if (d == rank) {
+            AQ_NCCL_OK(a->Recv(pos_out + (c[d] + dfill) * row_doubles, (size_t)n * row_doubles, ncclDouble, sidx, (ncclComm_t)comm, st));
+            if (src_rank_out) k_fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src_rank_out + c[d] + dfill, n, sidx);
+          }
+          extra -= n; sent += n; dfill += n;
+        }
+      }
+      AQ_NCCL_OK(a->GroupEnd());
+    }
+    AQ_CUDA_OK(cudaGetLastError());
+    if (moved_bytes_out) *moved_bytes_out = moved;
+    return AIQMC_OK;
+  }
   k_plan<<<2 * world, 1024, 0, st>>>(src_rank, src_local, world, rank, B, send_idx, slot_pos, counts);
   AQ_CUDA_OK(cudaGetLastError());
   int32_t h_counts[2 * 64];

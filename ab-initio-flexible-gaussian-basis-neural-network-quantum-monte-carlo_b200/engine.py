@@ -268,10 +268,15 @@ class WalkerEngine:
                                                   _ptr(ws), ws.numel(), _stream()), "aiqmc_branch_comb")
         return neww, inds
 
-    def rebalance(self, weights: torch.Tensor, pos: torch.Tensor, u: float, comm: Optional["NcclComm"] = None):
+    def rebalance(self, weights: torch.Tensor, pos: torch.Tensor, u: float, comm: Optional["NcclComm"] = None,
+                  mode: str = "balanced"):
         """Cross-GPU systematic comb + migration through the C ABI (aiqmc_rebalance_nccl): only the block totals of the
-        blocked weight scan and the walkers that change rank are exchanged.  Returns (new weight (device scalar), new
-        positions (B,row), source rank of every new walker (B,) int32, bytes this rank sent to other ranks)."""
+        blocked weight scan and the walkers that change rank are exchanged.  mode "ordered": slot k of rank r gets the
+        walker of tooth r*B + k (identical to the single-GPU comb, moves almost every walker); "balanced": the same
+        multiset of walkers, every rank keeps its own and only the population imbalance moves.  Returns (new weight
+        (device scalar), new positions (B,row), source rank of every new walker (B,) int32, bytes this rank sent)."""
+        if mode not in ("ordered", "balanced"):
+            raise ValueError("mode must be 'ordered' or 'balanced'")
         B, row = pos.shape[0], pos.shape[1]
         world, rank = (comm.world, comm.rank) if comm is not None else (1, 0)
         weights = self._arg(weights, (B,), "weights")
@@ -284,7 +289,8 @@ class WalkerEngine:
         moved = C.c_int64(0)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.aiqmc_rebalance_nccl(_ptr(weights), _ptr(pos), B, row, float(u), world, rank,
-                                                     comm.handle if comm is not None else None, _ptr(out), _ptr(neww),
+                                                     comm.handle if comm is not None else None,
+                                                     1 if mode == "balanced" else 0, _ptr(out), _ptr(neww),
                                                      _ptr(src), C.byref(moved), _ptr(ws), ws.numel(), _stream()),
                        "aiqmc_rebalance_nccl")
         return neww, out, src, int(moved.value)

@@ -69,7 +69,7 @@ def load() -> C.CDLL:
         "aiqmc_energy_allreduce": (C.c_int, [vp, vp, vp]),
         "aiqmc_ecut_allreduce_min": (C.c_int, [vp, vp, vp]),
         "aiqmc_rebalance_workspace_bytes": (i64, [i64, i32, i32]),
-        "aiqmc_rebalance_nccl": (C.c_int, [vp, vp, i64, i32, f64, i32, i32, vp, vp, vp, vp, C.POINTER(i64), vp, i64, vp]),
+        "aiqmc_rebalance_nccl": (C.c_int, [vp, vp, i64, i32, f64, i32, i32, vp, i32, vp, vp, vp, C.POINTER(i64), vp, i64, vp]),
         "aiqmc_energy_workspace_bytes": (i64, [sysp, i64, i32]),
         "aiqmc_local_energy_ae": (C.c_int, [sysp, vp, vp, i64, vp, vp, i64, vp]),
         "aiqmc_local_energy_ecp": (C.c_int, [sysp, ecpp, vp, vp, vp, i64, vp, vp, i64, vp]),

@@ -251,7 +251,7 @@ def stage_table(ctx, peak_tflops):
     return out
 
 
-def measure_dmc(D: Dist, B: int, steps: int, warmup: int, flush):
+def measure_dmc(D: Dist, B: int, steps: int, warmup: int, flush, args_mode: str = "balanced"):
     """DMC walker-steps/s: dmc_propagate_run (T-move, drift-diffusion sweep, two ccECP local energies, S, weights)
     + the cross-GPU population control (global systematic comb + migration of the selected walkers over NCCL)."""
     import aiqmc_b200
@@ -282,7 +282,7 @@ def measure_dmc(D: Dist, B: int, steps: int, warmup: int, flush):
 
     def step(k):
         e_new, w, new_data = run(packed, keys[k], state["data"], state["w"], branchcut, -5.39, -5.41)
-        neww, new_pos, src, imported = aiqmc_b200.branch_global(eng, w, new_data.positions, 0.37 + 0.01 * k, group)
+        neww, new_pos, src, imported = aiqmc_b200.branch_global(eng, w, new_data.positions, 0.37 + 0.01 * k, group, mode=args_mode)
         state["data"] = aiqmc_b200.AINetData(positions=new_pos, spins=state["data"].spins, atoms=state["data"].atoms,
                                              charges=state["data"].charges)
         state["w"] = torch.ones(B, dtype=torch.float64, device=D.dev) * neww
@@ -307,7 +307,9 @@ def measure_dmc(D: Dist, B: int, steps: int, warmup: int, flush):
             "steps": steps, "warmup": warmup, "ms_per_step": total / steps * 1e3, "n_elec": n, "n_atoms": a,
             "algorithmic_flops_per_walker_step": fl, "algorithmic_tflops_per_gpu": value / D.world * fl / 1e12,
             "walkers_imported_from_other_ranks_last_step": moved[-1] if moved else 0, "gpu_launches": launches,
-            "population_control": "global systematic comb over all ranks + NCCL migration, every step"}
+            "population_control": f"global systematic comb over all ranks + NCCL migration every step, mode '{args_mode}' "
+                                  "(balanced: the comb's survivors and multiplicities, every rank keeps its own walkers, only "
+                                  "the population imbalance crosses NVLink; ordered: the single-GPU slot order, moves ~all)"}
 
 
 def measure_e2e(D: Dist, ctx, steps: int, warmup: int):
@@ -430,6 +432,18 @@ def time_hbm_kernels(eng, B, n, dev, flush):
     return out
 
 
+def make_config(label, head, B, world):
+    """The `config` object of the JSON line -- identical for the b200 and the reference arm of the same command."""
+    return {"workload": label, "workload_key": head, "walkers_per_gpu": B, "global_walkers": B * world,
+            "tstep": TSTEP, "nsteps_per_step": 1, "params": "random-init (reference init scales)",
+            "parallelism": f"walker-sharded x{world}",
+            "l2": "256 MiB flush write between timed iterations (untimed)",
+            "rng": "per-step gauss/uniform/rotation arrays generated ahead of the timed region by the library's "
+                   "Philox kernels (counter = global walker id, step) and resident in HBM",
+            "tables": "carbon ccECP verbatim from the reference example; N/H atoms re-use the carbon table and "
+                      "the N2 / C6H6 geometries are builder-defined (the reference ships neither)"}
+
+
 def run_gpu(args):
     D = Dist()
     from aiqmc_b200 import workloads as W
@@ -504,20 +518,21 @@ def run_gpu(args):
                 v["frac_of_hbm_peak"] = v["GB_per_s"] / peaks.get("hbm_gbs", 6537.6)
         except Exception as exc:
             hbm = {"error": repr(exc)}
+    if ctx is None:                      # DMC headline: whole-step roofline against the live DFMA peak
+        import aiqmc_b200
+        from aiqmc_b200 import workloads as W
+        peak = measure_fp64_peak(W.build("dmc", 2).engine(D.dev), D.dev)
+        roofline = {"bound": "fp64", "kernel": "whole DMC step (T-move + drift-diffusion sweep + 2 ccECP local energies + S + comb)",
+                    "achieved": res["algorithmic_tflops_per_gpu"], "peak": peak, "unit": "TFLOP/s",
+                    "frac": res["algorithmic_tflops_per_gpu"] / peak if peak else None, "traffic": None,
+                    "note": "algorithmic flops (150NA + 9N + 11) F(N,A) per walker (SURVEY 8d) / CUDA-event step time / DFMA microbenchmark"}
     if D.world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(head if head != "dmc" else "c_ecp", args.cpu_walkers, 5, 1)
 
     line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": D.world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": res["label"], "workload_key": head, "walkers_per_gpu": B, "global_walkers": B * D.world,
-                       "tstep": TSTEP, "nsteps_per_step": 1, "params": "random-init (reference init scales)",
-                       "parallelism": f"walker-sharded x{D.world}",
-                       "l2": "256 MiB flush write between timed iterations (untimed)",
-                       "rng": "per-step gauss/uniform/rotation arrays generated ahead of the timed region by the library's "
-                              "Philox kernels (counter = global walker id, step) and resident in HBM",
-                       "tables": "carbon ccECP verbatim from the reference example; N/H atoms re-use the carbon table and "
-                                 "the N2 / C6H6 geometries are builder-defined (the reference ships neither)"},
+            "config": make_config(res["label"], head, B, D.world),
             "clocks": clocks, "gpu_launches": res.get("gpu_launches"),
             "e2e": ({**e2e["seeded"], "mode": "seeded: positions + seed from the host, randoms drawn on the device",
                      "parity_inputs": e2e["parity"]} if e2e else None),
@@ -637,10 +652,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": nwalk / value * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": W.SYSTEMS[args.workload]["label"], "workload_key": args.workload, "walkers_per_gpu": B,
-                       "global_walkers": B * args.gpus, "tstep": TSTEP, "nsteps_per_step": 1,
-                       "params": "random-init (reference init scales)", "sample_walkers_per_step": nwalk,
-                       "note": "CPU arm on a bounded sample of the same workload: " + cpu["sample"]},
+            "config": make_config(W.SYSTEMS[args.workload]["label"], args.workload, B, args.gpus),
+            "reference_arm_note": "CPU arm on a bounded sample of the same workload: " + cpu["sample"],
             "cpu_baseline": cpu, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 

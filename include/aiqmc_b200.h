@@ -294,10 +294,16 @@ int aiqmc_ecut_allreduce_min(double* ecut_min, void* comm, void* stream);
  *     pos (B,row) -> pos_out (B,row): slot k of rank r receives the walker tooth r*B + k selects; new_weight (device
  *     scalar) = total weight / (world*B); src_rank_out (B) int32 (may be NULL) = rank each new walker came from;
  *     *moved_bytes_out (host, may be NULL) = bytes this rank sent to other ranks.  Synchronises the stream once (the
- *     message sizes must reach the host).  world == 1 needs no communicator. */
+ *     message sizes must reach the host).  world == 1 needs no communicator.
+ *     mode 0 ("ordered"): the layout above, identical to the single-GPU comb; because the comb's base offset u*wtot
+ *     rotates the teeth by a fraction u of the population, almost every walker changes rank.
+ *     mode 1 ("balanced"): the SAME multiset of walkers (same survivors, same multiplicities), but every rank keeps the
+ *     walkers it already holds (in tooth order) and only the surplus of ranks owning more than B teeth moves, to the
+ *     ranks owning fewer (a deterministic rank-order matching computed identically everywhere): the wire carries the
+ *     population imbalance only.  Walkers are exchangeable, so the DMC estimators are unaffected. */
 int64_t aiqmc_rebalance_workspace_bytes(int64_t n_walkers, int32_t row_doubles, int32_t world);
 int aiqmc_rebalance_nccl(const double* weights, const double* pos, int64_t n_walkers, int32_t row_doubles, double u,
-                         int32_t world, int32_t rank, void* comm, double* pos_out, double* new_weight,
+                         int32_t world, int32_t rank, void* comm, int32_t mode, double* pos_out, double* new_weight,
                          int32_t* src_rank_out, int64_t* moved_bytes_out, void* workspace, int64_t workspace_bytes,
                          void* stream);
 

@@ -188,3 +188,25 @@ def test_dmc_loop_feeds_complex_estimates_back():
         e_trial = aiqmc_b200.trial_energy(e_est, w, 1.0)            # complex tensor
         assert torch.is_complex(e_est)
     assert torch.isfinite(w).all()
+
+
+def test_rebalance_on_one_rank_equals_comb_plus_gather():
+    """aiqmc_rebalance_nccl with world = 1 (no communicator): 'ordered' is the single-GPU comb + gather bit for bit,
+    'balanced' holds the same walkers with the same multiplicities (the multi-rank paths are checked on real GPUs by
+    tools/multigpu_check.py, profiles/r2_multigpu_check_*.txt, and on CPU by tests/test_distributed_gloo.py)."""
+    case = Case(**CASES["C_ecp"], nwalkers=2)
+    eng = engine(case)
+    rng = np.random.default_rng(5)
+    for B in (1000, 65536):
+        w = torch.tensor(rng.uniform(0.05, 3.0, size=B)).cuda()
+        p = torch.tensor(rng.normal(size=(B, 12))).cuda()
+        neww, inds = eng.branch_comb(w, 0.61)
+        ref = eng.gather_walkers(p, inds)
+        n0, p0, s0, m0 = eng.rebalance(w, p, 0.61, None, mode="ordered")
+        assert float(n0) == float(neww) and torch.equal(p0, ref) and m0 == 0 and int(s0.abs().sum()) == 0
+        n1, p1, s1, m1 = eng.rebalance(w, p, 0.61, None, mode="balanced")
+        assert float(n1) == float(neww) and m1 == 0
+        assert torch.equal(torch.sort(p1[:, 0]).values, torch.sort(ref[:, 0]).values)
+        # oracle: the comb of DMC/branch.py on the same weights selects the same walkers (ulp ties aside)
+        _, io = O.branch(w.cpu(), 0.61)
+        assert float((inds.cpu() != io).double().mean()) < 1e-3

@@ -54,7 +54,7 @@ for name, B in (("c_ecp", 65536), ("c6h6", 4096)):
     assert float(m_c) == float(m)
 
     # population control through the C ABI vs one GPU doing the whole batch
-    neww, newp, src, imported, moved = aiqmc_b200.branch_global(eng, w, p, 0.37, return_bytes=True)
+    neww, newp, src, imported, moved = aiqmc_b200.branch_global(eng, w, p, 0.37, return_bytes=True, mode="ordered")
     neww1, inds1 = eng.branch_comb(w_all.to(dev), 0.37)
     ref = p_all.to(dev)[inds1[lo:hi].long()]
     assert float(neww) == float(neww1), (float(neww), float(neww1))
@@ -65,12 +65,25 @@ for name, B in (("c_ecp", 65536), ("c6h6", 4096)):
     same = float((newp2 == newp).all(dim=1).double().mean())
     tot = torch.tensor([imported, moved], device=dev, dtype=torch.float64)
     dist.all_reduce(tot)
+    # balanced mode: the same MULTISET of walkers as the single-GPU comb, but only the population imbalance moves
+    nb_w, nb_p, nb_src, nb_imp, nb_moved = aiqmc_b200.branch_global(eng, w, p, 0.37, return_bytes=True, mode="balanced")
+    assert float(nb_w) == float(neww1)
+    allp = [torch.empty_like(nb_p) for _ in range(world)]
+    dist.all_gather(allp, nb_p.contiguous())
+    got_rows = torch.cat(allp).cpu().numpy()
+    ref_rows = p_all.numpy()[inds1.cpu().numpy().astype(np.int64)]
+    key_cols = tuple(got_rows[:, c] for c in range(min(3, row) - 1, -1, -1))
+    ref_cols = tuple(ref_rows[:, c] for c in range(min(3, row) - 1, -1, -1))
+    assert np.array_equal(got_rows[np.lexsort(key_cols)], ref_rows[np.lexsort(ref_cols)]), "balanced mode changed the multiset"
+    tb = torch.tensor([nb_imp, nb_moved], device=dev, dtype=torch.float64)
+    dist.all_reduce(tb)
     gathered_everything = world * B * row * 8 * (world - 1)          # what round 1 moved: every rank received all positions
     if rank == 0:
         lines.append(f"{name}: world {world}, {world * B} walkers x {row * 8} B: {int(tot[0])} walkers migrated, "
                      f"{tot[1] / 1e6:.2f} MB sent in total ({tot[1] / world / 1e6:.2f} MB per rank; own shard {B * row * 8 / 1e6:.2f} MB; "
                      f"the all-gather of round 1 moved {gathered_everything / 1e6:.1f} MB), new weight {float(neww):.6f}, "
-                     f"bit-identical to the single-GPU comb; torch/rank-totals schedule agrees on {same * 100:.4f} % of the rows")
+                     f"bit-identical to the single-GPU comb; torch/rank-totals schedule agrees on {same * 100:.4f} % of the rows; "
+                     f"BALANCED mode: same multiset of walkers, {int(tb[0])} walkers migrated, {tb[1] / 1e6:.3f} MB sent in total")
 if rank == 0:
     print("multigpu_check ok")
     for ln in lines:
