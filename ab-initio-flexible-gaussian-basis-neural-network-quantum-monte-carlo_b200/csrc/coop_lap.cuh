@@ -22,6 +22,12 @@
 #ifndef AIQMC_LAP_PIPE
 #define AIQMC_LAP_PIPE 0           // 1: producer warp + tangent warps as a double-buffered pipeline (measured: 1.04 vs 0.97 ms
 #endif                             //    on carbon -- the second record buffer costs two resident CTAs per SM)
+#ifndef AIQMC_LAP_COOP_TANGENT
+#define AIQMC_LAP_COOP_TANGENT 0   // 0: one thread per (cfg, electron, direction) = DerivSplit::tangent (1.3 kB of local arrays);
+                                   // 1: lane-per-row tangent pass below: no local memory (176 B stack), but the moved electron's
+                                   //    jets serialise inside each group and every lane repeats the block sums -- 2x the
+                                   //    instructions: measured 1.66 ms against 0.97 ms for the kinetic stage of carbon
+#endif
 #ifndef AIQMC_LAP_MINB
 #define AIQMC_LAP_MINB (AIQMC_LAP_PIPE ? 2 : 4)   // resident CTAs/SM the register allocator must allow
 #endif
@@ -43,15 +49,260 @@ struct CoopLapCfg {
   static constexpr int oPIV = oMS + 2 * NE * NE;              // [2][N][2]
   static constexpr int kScrRaw = (oPIV + 4 * NE + 1) & ~1;
   static constexpr int SCR = kScrRaw + ((2 - kScrRaw % 16) + 16) % 16;
+  // phase-2 scratch per (direction, configuration) group of the lane-per-row tangent pass
+  static constexpr int o2H0 = 0;                              // [2][4A]   d, s of the moved electron's layer-0 features
+  static constexpr int o2A = o2H0 + 8 * NA;                   // [N][8]    per-row deposits (column-chain tangents / row tangents)
+  static constexpr int o2S1 = o2A + 8 * NE;                   // [N][2]    S1[l] of the moved electron's row
+  static constexpr int o2X = o2S1 + 2 * NE;                   // [N][N][2] X = dM M^-1, row k from lane k
+  static constexpr int o2R = o2X + 2 * NE * NE;               // [N][2]    per-lane partial results
+  static constexpr int kScr2Raw = (o2R + 2 * NE + 1) & ~1;
+  static constexpr int SCR2 = kScr2Raw + ((2 - kScr2Raw % 16) + 16) % 16;
+  static constexpr bool kCoopTan = AIQMC_LAP_COOP_TANGENT != 0;
   static constexpr int kTan = NG * 3 * NE;                    // phase-2 threads that have work
   static constexpr int T2 = ((kTan > 32 ? kTan : 32) + 31) / 32 * 32;   // tangent (consumer) threads
   static constexpr bool kPipe = AIQMC_LAP_PIPE != 0;
   static constexpr int T = kPipe ? 32 + T2 : T2;              // pipeline: + a dedicated producer warp
   static constexpr int kPar = (make_layout(NE, NA).total + 1) & ~1;
-  static constexpr int kDoubles = kPar + NG * ((kPipe ? 2 : 1) * REC + SCR);
+  static constexpr int kDoubles = kPar + NG * ((kPipe ? 2 : 1) * REC + SCR) + (kCoopTan ? 3 * NG * SCR2 : 0);
+  static_assert(T2 == 96, "phase 2 maps one warp to one Cartesian direction");
   static constexpr int kBytes = kDoubles * 8;
-  static constexpr int kMinBlocks = kBytes * AIQMC_LAP_MINB <= 224 * 1024 ? AIQMC_LAP_MINB : (kBytes * 2 <= 224 * 1024 ? 2 : 1);
+  static constexpr int fit_blocks(int want) { return want <= 1 ? 1 : (kBytes * want <= 224 * 1024 ? want : fit_blocks(want - 1)); }
+  static constexpr int kMinBlocks = fit_blocks(AIQMC_LAP_MINB);
 };
+
+
+// ---- phase 2, lane-per-row: one group of N lanes = (configuration, Cartesian direction); lane k carries the tangent
+//      (first and second derivative along x_{e,dir}) of ROW k of the one-electron stream and of the two pair chains
+//      (e,k), (k,e) through electron e, for e = 0..N-1 in turn.  The per-thread version (DerivSplit::tangent) keeps
+//      those for ALL rows in arrays indexed by a loop variable: 1.3 kB of local memory per thread, 1 GB of DRAM writes
+//      per launch.  Here every array index is a compile-time constant; cross-lane traffic (block means, the gather
+//      through sigma, X = dM M^-1 for tr(XX)) goes through a small per-group scratch.  Same mathematics, same record.
+template <int NE, int NA>
+__device__ __forceinline__ void lap_tangent_coop(const AiqmcSystem& sys, const double* __restrict__ P,
+                                                 const double* __restrict__ rec, double* __restrict__ scr, int k, bool idle,
+                                                 int dir, double& g_out, double& l_out, int e_sel) {
+  using DC = DerivCache<NE, NA>;
+  using DS = DerivSplit<NE, NA>;
+  using PS = Psi<NE, NA>;
+  using CF = CoopLapCfg<NE, NA>;
+  using Tan4 = typename DS::Tan4;
+  using J = Jet<true, 1>;
+  using Op = ScalarOps<J>;
+  constexpr int N = NE, A = NA, QM = DC::QM;
+  constexpr LayoutC<NE, NA> L{};
+  constexpr double kSqrt2 = 1.41421356237309504880;
+  const int e = e_sel;
+  const int n_up = sys.n_up;
+  const double inv_n[2] = {1.0 / sys.n_up, 1.0 / sys.n_dn};
+  const int se = e < n_up ? 0 : 1;
+  const bool diag = (k == e);
+  double* S_H0 = scr + CF::o2H0;
+  double* S_A = scr + CF::o2A;
+  double2* S_S1 = reinterpret_cast<double2*>(scr + CF::o2S1);
+  double2* S_X = reinterpret_cast<double2*>(scr + CF::o2X);
+  double* S_R = scr + CF::o2R;
+
+  // ---- T0: the moved electron's local part as a jet (lane e only); its layer-0 feature tangents go to the scratch
+  double xe[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) xe[c] = rec[DC::X + 3 * e + c];
+  J h0e[4 * A], ye[6], enve, jaee;
+#pragma unroll
+  for (int q = 0; q < 4 * A; ++q) h0e[q] = Op::cst(0.0);
+#pragma unroll
+  for (int m = 0; m < 6; ++m) ye[m] = Op::cst(0.0);
+  enve = Op::cst(0.0); jaee = Op::cst(0.0);
+  __syncwarp();                                        // the previous electron's readers of the scratch are done
+  if (diag && !idle) {
+    J xj[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { xj[c] = Op::cst(xe[c]); xj[c].d[0] = (c == dir) ? 1.0 : 0.0; }
+    PS::template electron_local<J>(P, e, xj, h0e, ye, enve, jaee);
+#pragma unroll
+    for (int q = 0; q < 4 * A; ++q) { S_H0[q] = h0e[q].d[0]; S_H0[4 * A + q] = h0e[q].s[0]; }
+  }
+  __syncwarp();
+  double dJ = diag ? jaee.d[0] : 0.0, sJ = diag ? jaee.s[0] : 0.0;
+
+  // ---- T1: level-0 tangents of the two pair chains through e that end in this lane: row (e,k): d = x_k - x_e,
+  //      column (k,e): d = x_e - x_k
+  Tan4 cr, cc;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { cr.d[c] = 0.0; cr.s[c] = 0.0; cc.d[c] = 0.0; cc.s[c] = 0.0; }
+  if (!diag) {
+    const double dd = rec[DC::X + 3 * k + dir] - xe[dir];
+    const double r = rec[DC::HP + ((0 * N + e) * N + k) * 4];
+    const double ri = s_inv(r);
+    const double rt = -dd * ri;                                 // dr/dx_{e,dir}
+    const double rs = (1.0 - rt * rt) * ri;                     // d2r/dx_{e,dir}^2
+    cr.d[0] = rt; cc.d[0] = rt; cr.s[0] = rs; cc.s[0] = rs;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { cr.d[1 + c] = (c == dir) ? -1.0 : 0.0; cc.d[1 + c] = (c == dir) ? 1.0 : 0.0; }
+    const int lo = e < k ? e : k, hi = e < k ? k : e;           // e-e Pade term (Jastrow.py:23-41)
+    const double cu = P[L.jas_cusp + lo * N + hi], al = P[L.jas_alpha + lo * N + hi];
+    const double q = s_inv(1.0 + al * r);
+    const double u1 = cu * q * q, u2 = -2.0 * al * u1 * q;
+    dJ += u1 * rt;
+    sJ += u2 * rt * rt + u1 * rs;
+  }
+
+  // ---- the three one-electron layers of row k; the pair chains advance with them
+  double hd[4] = {0.0, 0.0, 0.0, 0.0}, hs[4] = {0.0, 0.0, 0.0, 0.0};
+  constexpr int GW = 4 * A > 4 ? 4 * A : 4;
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    // column block sums (only lane e uses them): every other lane deposits its column-chain tangent
+    __syncwarp();
+    if (!idle) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { S_A[k * 8 + c] = cc.d[c]; S_A[k * 8 + 4 + c] = cc.s[c]; }
+    }
+    __syncwarp();
+    double sud[2][4], sus[2][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      double ud = 0.0, dd2 = 0.0, us = 0.0, ds = 0.0;
+      if (diag) {
+        for (int r = 0; r < N; ++r) {
+          const double vd = S_A[r * 8 + c], vs = S_A[r * 8 + 4 + c];       // lane e deposited zeros
+          if (r < n_up) { ud += vd; us += vs; } else { dd2 += vd; ds += vs; }
+        }
+      }
+      sud[0][c] = ud; sud[1][c] = dd2; sus[0][c] = us; sus[1][c] = ds;
+    }
+    // tangents of the block means fed to every row
+    double gmd[2][GW], gms[2][GW];
+    if (l == 0) {
+#pragma unroll
+      for (int q = 0; q < 4 * A; ++q) {
+        const double d0 = S_H0[q] * inv_n[se], s0 = S_H0[4 * A + q] * inv_n[se];
+        gmd[0][q] = se == 0 ? d0 : 0.0; gmd[1][q] = se == 1 ? d0 : 0.0;
+        gms[0][q] = se == 0 ? s0 : 0.0; gms[1][q] = se == 1 ? s0 : 0.0;
+      }
+    } else {
+      __syncwarp();
+      if (!idle) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { S_A[k * 8 + c] = hd[c]; S_A[k * 8 + 4 + c] = hs[c]; }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        double ud = 0.0, dd2 = 0.0, us = 0.0, ds = 0.0;
+        for (int r = 0; r < N; ++r) {
+          const double vd = S_A[r * 8 + c], vs = S_A[r * 8 + 4 + c];
+          if (r < n_up) { ud += vd; us += vs; } else { dd2 += vd; ds += vs; }
+        }
+        gmd[0][c] = ud * inv_n[0]; gmd[1][c] = dd2 * inv_n[1];
+        gms[0][c] = us * inv_n[0]; gms[1][c] = ds * inv_n[1];
+      }
+    }
+    if (l == 0) DS::template row_layer<true, 4 * A>(P, 0, k, e, se, inv_n, rec, 1, h0e, hd, hs, gmd, gms, cr, sud, sus);
+    else DS::template row_layer<true, 4>(P, l, k, e, se, inv_n, rec, 1, h0e, hd, hs, gmd, gms, cr, sud, sus);
+    if (l < 2 && !diag) {     // advance the tangents of the two pair chains through double-layer l
+      const double* W = P + L.dbl_w[l];
+      double tr[4], tc[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        tr[m] = kSqrt2 * rec[DC::HP + (((l + 1) * N + e) * N + k) * 4 + m] - rec[DC::HP + ((l * N + e) * N + k) * 4 + m];
+        tc[m] = kSqrt2 * rec[DC::HP + (((l + 1) * N + k) * N + e) * 4 + m] - rec[DC::HP + ((l * N + k) * N + e) * 4 + m];
+      }
+      Tan4 nr, nc;
+      DS::template chain_layer<true>(W, cr, tr, nr);
+      DS::template chain_layer<true>(W, cc, tc, nc);
+      cr = nr; cc = nc;
+    }
+  }
+
+  // ---- determinant: row k of dM reads the tangent of h of electron sigma[k] (quirk Q4)
+  __syncwarp();
+  if (!idle) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { S_A[k * 8 + c] = hd[c]; S_A[k * 8 + 4 + c] = hs[c]; }
+  }
+  __syncwarp();
+  const int ek = sys.sigma[k];
+  double dhd[4], dhs[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { dhd[c] = S_A[ek * 8 + c]; dhs[c] = S_A[ek * 8 + 4 + c]; }
+  double gsum = dJ, l2 = sJ;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const double gm = rec[DC::GMAT + (k * 4 + c) * 2];
+    gsum += dhd[c] * gm;
+    l2 += dhs[c] * gm;
+  }
+  // row e of E = env * Yo as jets (lane e): S1[l] = sum_j P[e,j] dE[e,j] Minv[j,l], S2 = sum_j (2 dP dE + P d2E) Minv[j,e]
+  if (diag && !idle) {
+    const int srow = e < sys.n_up_rows ? 0 : 1;
+    const double* W = P + L.orb_w[srow];
+    const double* Bv = P + L.orb_b[srow];
+    const int eh = sys.sigma[e];
+    double h3[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) h3[c] = rec[DC::H + (2 * N + eh) * 4 + c];
+    cplx S1[N];
+    cplx S2 = {0.0, 0.0};
+#pragma unroll
+    for (int l = 0; l < N; ++l) S1[l] = {0.0, 0.0};
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      J yo = Op::cst(0.0);
+#pragma unroll
+      for (int m = 0; m < 6; ++m) yo = yo + ye[m] * P[L.y_w + m * N + j];
+      const J E = enve * yo;
+      cplx p = {Bv[2 * j], Bv[2 * j + 1]}, dp = {0.0, 0.0};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double wr = W[c * 2 * N + 2 * j], wi = W[c * 2 * N + 2 * j + 1];
+        p.re += h3[c] * wr; p.im += h3[c] * wi;
+        dp.re += dhd[c] * wr; dp.im += dhd[c] * wi;          // lane e's dhd = tangent of h of electron sigma[e]
+      }
+      const cplx pdE = cscale(p, E.d[0]);
+#pragma unroll
+      for (int l = 0; l < N; ++l) {
+        const cplx mjl = {rec[DC::MI + (j * N + l) * 2], rec[DC::MI + (j * N + l) * 2 + 1]};
+        cfma(S1[l], pdE, mjl);
+      }
+      const cplx mje = {rec[DC::MI + (j * N + e) * 2], rec[DC::MI + (j * N + e) * 2 + 1]};
+      const cplx t2 = cadd(cscale(dp, 2.0 * E.d[0]), cscale(p, E.s[0]));
+      cfma(S2, t2, mje);
+    }
+#pragma unroll
+    for (int l = 0; l < N; ++l) S_S1[l] = make_double2(S1[l].re, S1[l].im);
+    l2 += S2.re;
+  }
+  __syncwarp();
+  if (diag) gsum += S_S1[e].x;                               // S1[e].re
+  // X[k][l] = sum_c dh[sigma_k,c] T[k,c,l] + delta_ke S1[l]; tr(X X) needs column k of X: exchange through the scratch
+  cplx X[N];
+#pragma unroll
+  for (int l = 0; l < N; ++l) {
+    cplx acc = {0.0, 0.0};
+    if (diag) { const double2 s1 = S_S1[l]; acc = {s1.x, s1.y}; }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      acc.re += dhd[c] * rec[DC::TT + ((k * 4 + c) * N + l) * 2];
+      acc.im += dhd[c] * rec[DC::TT + ((k * 4 + c) * N + l) * 2 + 1];
+    }
+    X[l] = acc;
+    if (!idle) S_X[k * N + l] = make_double2(acc.re, acc.im);
+  }
+  __syncwarp();
+  double trxx = 0.0;
+#pragma unroll
+  for (int l = 0; l < N; ++l) {
+    const double2 xt = S_X[l * N + k];
+    trxx += X[l].re * xt.x - X[l].im * xt.y;
+  }
+  // ---- fixed-order sum of the lanes' partials
+  if (!idle) { S_R[2 * k] = gsum; S_R[2 * k + 1] = l2 - trxx; }
+  __syncwarp();
+  double g = 0.0, lp = 0.0;
+  for (int r = 0; r < N; ++r) { g += S_R[2 * r]; lp += S_R[2 * r + 1]; }
+  g_out = g;
+  l_out = lp;
+}
 
 template <int NE, int NA>
 __global__ void __launch_bounds__((CoopLapCfg<NE, NA>::T), (CoopLapCfg<NE, NA>::kMinBlocks)) k_lap_coop(
@@ -343,7 +594,26 @@ __global__ void __launch_bounds__((CoopLapCfg<NE, NA>::T), (CoopLapCfg<NE, NA>::
     const int64_t cfg0 = tile * NG;
     const int ncfg = (int)((n_cfg - cfg0) < NG ? (n_cfg - cfg0) : NG);
     const int tid = (int)threadIdx.x - (CF::kPipe ? 32 : 0);      // consumer index
-    if (tid < ncfg * 3 * N) {
+    if constexpr (CF::kCoopTan) {
+      // warp = Cartesian direction, lanes = (configuration g, row k) exactly as in phase 1
+      const int dir = tid >> 5, ln = tid & 31;
+      const bool idle = ln >= GPW * N;
+      const int g = idle ? GPW - 1 : ln / N;
+      const int k = idle ? N - 1 : ln - g * N;
+      const int gg = g < ncfg ? g : ncfg - 1;           // groups past the end of the batch redo the last one, silently
+      double* scr2 = scrs + NG * CF::SCR + (dir * NG + g) * CF::SCR2;
+#pragma unroll 1
+      for (int e = 0; e < N; ++e) {
+        double gq, l2;
+        lap_tangent_coop<NE, NA>(sys, P, recs + gg * CF::REC, scr2, k, idle, dir, gq, l2, e);
+        if (!idle && g < ncfg && k == 0) {
+          const int64_t cfg = cfg0 + g;
+          const int ed = 3 * e + dir;
+          gout[cfg * 3 * N + ed] = gq;
+          lap_parts[(int64_t)ed * lap_stride + cfg] = l2;
+        }
+      }
+    } else if (tid < ncfg * 3 * N) {
       const int cl = tid / (3 * N), ed = tid - cl * 3 * N;
       const int e = ed / 3, dir = ed - 3 * e;
       double gq, l2 = 0.0;
