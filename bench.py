@@ -376,8 +376,9 @@ def measure_fp64_peak(eng, dev):
     return best
 
 
-def ncu_metric(path, metric):
-    """One metric value out of a committed `ncu --page raw --csv` file (the bench line cites it with its source)."""
+def ncu_metric(path, metric, kernel=None):
+    """One metric value (mean over the launches of `kernel`) out of a committed `ncu --page raw --csv` file (the bench
+    line cites it with its source)."""
     full = os.path.join(ROOT, path)
     if not os.path.exists(full):
         return None
@@ -386,7 +387,10 @@ def ncu_metric(path, metric):
         hdr = next(r for r in rows if metric in r)
         col = hdr.index(metric)
         vals = []
+        kcol = hdr.index("Kernel Name") if "Kernel Name" in hdr else None
         for r in rows[rows.index(hdr) + 1:]:
+            if kernel is not None and kcol is not None and kernel not in r[kcol]:
+                continue
             try:
                 vals.append(float(r[col].replace(",", "")))
             except (ValueError, IndexError):
@@ -499,12 +503,12 @@ def run_gpu(args):
                 traffic = json.load(open(tpath)).get("k_ecp_pt_dram_bytes_per_step")
             except Exception:
                 traffic = None
-        ncu_src = "profiles/r1_v17_ecp_pt_raw.csv"
+        ncu_src = "profiles/r2_v2_step_kernels_raw.csv"
         roofline = {"bound": "fp64", "kernel": f"{dom} stage of {head}", "achieved": stages[dom]["algorithmic_tflops"],
                     "peak": peak, "unit": "TFLOP/s", "frac": stages[dom]["frac"], "traffic": traffic,
                     "stages": stages,
                     "whole_step_frac": (res["value"] / D.world) * res["algorithmic_flops_per_walker_step"] / 1e12 / peak if peak else None,
-                    "fp64_pipe_busy_ncu": {"value": ncu_metric(ncu_src, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                    "fp64_pipe_busy_ncu": {"value": ncu_metric(ncu_src, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "k_ecp_pt") if head == "c_ecp" else None,
                                            "source": ncu_src, "note": "parsed from the committed ncu page at run time; not measured live"},
                     "note": "compute-bound on the FP64 pipe (SURVEY 8d), not HBM/tensor: achieved = SURVEY's FIXED algorithmic "
                             "flops per walker (a tanh priced at ~1 flop) x walkers / CUDA-event time of the stage; peak = DFMA "
