@@ -109,9 +109,9 @@ __global__ void __launch_bounds__((CoopGradCfg<NE, NA>::T)) k_grad_coop(
     int pcol) {
   using CF = CoopGradCfg<NE, NA>;
   using PS = Psi<NE, NA>;
-  constexpr int N = NE, A = NA, GPW = CF::GPW, NG = CF::NG, T = CF::T, QM = CF::QM, Q0 = 3 * NA + 2;
+  constexpr int N = NE, A = NA, GPW = CF::GPW, NG = CF::NG, T = CF::T, Q0 = 3 * NA + 2;
   constexpr LayoutC<NE, NA> L{};
-  constexpr double kSqrt2 = 1.41421356237309504880;
+  constexpr unsigned kLaneMask = GPW * N >= 32 ? 0xffffffffu : ((1u << ((GPW * N) % 32)) - 1u);      // lanes that own an electron
   extern __shared__ __align__(16) double smem_cg[];
   __shared__ double red[CF::W];
   const double* P = stage_params<NE, NA>(params, smem_cg);
@@ -121,8 +121,7 @@ __global__ void __launch_bounds__((CoopGradCfg<NE, NA>::T)) k_grad_coop(
   const int k = idle ? N - 1 : lane - g * N;
   const bool act = !idle;
   unsigned gmask = (N >= 32 ? 0xffffffffu : ((1u << N) - 1u)) << (g * N);
-  if (g == GPW - 1 && GPW * N < 32) gmask |= ~((1u << (GPW * N)) - 1u);      // idle lanes ride with the last group
-  const int glane0 = g * N;                                                   // first lane of the group
+  if (g == GPW - 1) gmask |= ~kLaneMask;      // idle lanes ride with the last group
   double* scr = smem_cg + CF::kPar + (warp * GPW + g) * CF::SCR;
   double* X = scr + CF::oX;
   double* RED = scr + CF::oRED;

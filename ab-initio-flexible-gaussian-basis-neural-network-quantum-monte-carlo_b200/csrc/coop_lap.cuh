@@ -334,8 +334,9 @@ __global__ void __launch_bounds__((CoopLapCfg<NE, NA>::T), (CoopLapCfg<NE, NA>::
       const int k = idle ? N - 1 : lane - g * N;
       const bool act = !idle && g < ncfg;              // groups past the end of the batch redo the last configuration, silently
       const int gg = g < ncfg ? g : ncfg - 1;
+      constexpr unsigned kLaneMask = GPW * N >= 32 ? 0xffffffffu : ((1u << ((GPW * N) % 32)) - 1u);
       unsigned gmask = (N >= 32 ? 0xffffffffu : ((1u << N) - 1u)) << (g * N);
-      if (g == GPW - 1 && GPW * N < 32) gmask |= ~((1u << (GPW * N)) - 1u);
+      if (g == GPW - 1) gmask |= ~kLaneMask;                                       // idle lanes ride with the last group
       double* rec = recs + g * CF::REC;
       double* scr = scrs + g * CF::SCR;
       double2* MS = reinterpret_cast<double2*>(scr + CF::oMS);

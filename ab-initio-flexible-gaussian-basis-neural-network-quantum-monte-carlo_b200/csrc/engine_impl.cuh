@@ -1217,7 +1217,6 @@ struct Launch {
     if (ws_bytes < energy_ws_bytes(NE, NA, B, with_ecp)) return AIQMC_E_WORKSPACE;
     EnergyWs w = carve_energy_ws(ws, NE, NA, B, with_ecp);
     const unsigned g1 = (unsigned)((B + kThreads - 1) / kThreads);
-    MovedSrc ms{};
     if (!with_ecp) {
       AQ_CUDA_OK(prep(k_energy_rest<NE, NA, false>));
       const int rc = lap_pass(sys, params, pos, B, w.dcache, nullptr, w.phase, w.logabs, w.grad, w.lap_parts, B, st);

@@ -210,3 +210,19 @@ def test_rebalance_on_one_rank_equals_comb_plus_gather():
         # oracle: the comb of DMC/branch.py on the same weights selects the same walkers (ulp ties aside)
         _, io = O.branch(w.cpu(), 0.61)
         assert float((inds.cpu() != io).double().mean()) < 1e-3
+
+
+def test_n2_large_batch_accept_mask_is_bit_exact():
+    """BASELINE configs[2] (N2, N=10, A=2): one sweep of 4,096 walkers against the oracle run on the same 4,096-walker
+    batch (quirk Q6: the drift limiter sums over the whole per-device batch): 40,960 accept decisions bit for bit."""
+    B = 4096
+    case = Case(**CASES["N2_ecp"], nwalkers=B, width=0.9)
+    eng = engine(case)
+    rand = case.sweep_rand(TSTEP)
+    pos = torch.tensor(case.pos).cuda()
+    out = eng.vmc_sweep(pos, rand["gauss1"].cuda(), rand["gauss2"].cuda(), rand["rnd"].cuda(), TSTEP)
+    new_data, aux = O.walkers_update(O.select_output(case.net.apply, 1), case.params, case.oracle_data(), rand, TSTEP, 3,
+                                     case.n, B, return_aux=True)
+    got, ref = out["accept"].cpu().numpy().astype(bool), aux["accept"].numpy()
+    assert int((got != ref).sum()) == 0, f"{int((got != ref).sum())} of {got.size} accept decisions differ"
+    np.testing.assert_allclose(pos.cpu().numpy(), new_data.positions.numpy(), rtol=1e-10, atol=1e-10)
