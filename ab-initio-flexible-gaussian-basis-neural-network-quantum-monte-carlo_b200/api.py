@@ -448,12 +448,14 @@ def propose_drift_diffusion(f, tstep: float, ndim: int, nelectrons: int, batch_s
 
 
 def compute_tmoves(list_l, tstep: float, nelectrons: int, natoms: int, ndim: int, lognetwork, Rn_non_local,
-                   Non_local_coes, Non_local_exps):
+                   Non_local_coes, Non_local_exps, _ecp=None):
     """DMC/Tmoves.py:32-225 -> calculate_ratio_weight_tmoves(data, params, key) -> (final_configuration, acceptance),
     natively batched over walkers.  `lognetwork` is the `apply` of make_ai_net (its complex log is taken inside the
     kernels); key = dict(rot (B,3,3), u (B,), rnd (B,N)): the three draws the reference makes from its key."""
     zeros = np.zeros((natoms, 3))
-    ecp = make_ecp(natoms, zeros, zeros, zeros, Rn_non_local, Non_local_coes, Non_local_exps, list_l)
+    # the T-move kernels read only the non-local channels and the quadrature grid of the table; dmc_propagate hands in
+    # its full table (_ecp) so that T-moves and local energies share ONE constant-memory upload per step
+    ecp = _ecp if _ecp is not None else make_ecp(natoms, zeros, zeros, zeros, Rn_non_local, Non_local_coes, Non_local_exps, list_l)
 
     def calculate_ratio_weight_tmoves(data: AINetData, params, key):
         eng = _engine_of(lognetwork, params, data)
@@ -493,7 +495,8 @@ def dmc_propagate(signed_network, lognetwork, tstep: float, nelectrons: int, nat
     key = dict(tmove=dict(rot, u, rnd), sweep=dict(gauss1, gauss2, rnd), rot=(B,3,3)): the draws the reference
     makes from its single key, as explicit arrays (parity mode)."""
     tm = compute_tmoves(list_l, tstep, nelectrons, natoms, ndim, lognetwork, rn_non_local, non_local_coes,
-                        non_local_exps)
+                        non_local_exps, _ecp=make_ecp(natoms, rn_local, local_coes, local_exps, rn_non_local, non_local_coes,
+                                                      non_local_exps, list_l))
     dd = propose_drift_diffusion(signed_network, tstep, ndim, nelectrons, batch_size)
     le = local_energy(signed_network, charges, lognetwork=lognetwork, rn_local=rn_local, local_coes=local_coes,
                       local_exps=local_exps, rn_non_local=rn_non_local, non_local_coes=non_local_coes,
