@@ -226,3 +226,23 @@ def test_n2_large_batch_accept_mask_is_bit_exact():
     got, ref = out["accept"].cpu().numpy().astype(bool), aux["accept"].numpy()
     assert int((got != ref).sum()) == 0, f"{int((got != ref).sum())} of {got.size} accept decisions differ"
     np.testing.assert_allclose(pos.cpu().numpy(), new_data.positions.numpy(), rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize("n,a", [(8, 2), (12, 2), (2, 1), (3, 1)])
+def test_lane_per_electron_derivative_kernels_on_every_group_shape(n, a):
+    """coop_grad.cuh / coop_lap.cuh pack floor(32/N) configurations per warp: N = 8 (4 groups, no idle lanes), N = 12
+    (2 groups, 8 idle lanes), N = 2 (16 groups), N = 3 (10 groups, 2 idle lanes) -- C2 with ccECP / all-electron are the
+    reference's own examples.  log|psi|, gradient and Laplacian against autograd on the oracle, ragged batch sizes."""
+    spins = [1.] * ((n + 1) // 2) + [-1.] * (n // 2)
+    for nw in (1, 7):
+        case = Case(n=n, natoms=a, spins=spins, seed=40 + n, nwalkers=nw, width=0.8)
+        eng = engine(case)
+        ph, la, g, lap = eng.psi(torch.tensor(case.pos), mode=2)
+        _, la1, g1 = eng.psi(torch.tensor(case.pos), mode=1)
+        f = lambda x: case.net.apply(case.params, x, case.t_spins, case.t_atoms)[1]
+        lat, gt, d2 = O.grad_and_hess_diag(f, torch.tensor(case.pos))
+        np.testing.assert_allclose(la.cpu().numpy(), lat.detach().numpy(), rtol=1e-10, atol=1e-10)
+        np.testing.assert_allclose(la1.cpu().numpy(), lat.detach().numpy(), rtol=1e-10, atol=1e-10)
+        np.testing.assert_allclose(g.cpu().numpy(), gt.numpy(), rtol=1e-7, atol=1e-8)
+        np.testing.assert_allclose(g1.cpu().numpy(), gt.numpy(), rtol=1e-7, atol=1e-8)
+        np.testing.assert_allclose(lap.cpu().numpy(), d2.sum(-1).numpy(), rtol=1e-6, atol=1e-6)
