@@ -61,8 +61,8 @@ struct StaticFor {
 };
 
 #ifndef AIQMC_GRP_ALIGN
-#define AIQMC_GRP_ALIGN 1
-#endif
+#define AIQMC_GRP_ALIGN -1     // 1: all warps of a CTA walk the point loop in lock step (shared instruction fetches: pays off for the
+#endif                         // 70 kB loop body of N > 16); 0: free-running warps (N2: 133.9 vs 136.1 ms); -1: pick by N
 #ifndef AIQMC_GRP_MINB
 #define AIQMC_GRP_MINB 2
 #endif
@@ -104,7 +104,12 @@ struct GrpCfg {
   }
   static constexpr int PC = pc_raw();                      // points per chunk
   static constexpr int oPIV = (9 * NE + 18 + 8 * NA + 1) & ~1;            // pivot-row buffers inside the group scratch (16 B aligned)
-  static constexpr int SCR = oPIV + 4 * NE;                               // per-group scratch doubles
+  // per-group scratch doubles; the stride between the groups of a warp continues the 9-double row stride of red_in
+  // across groups (SCR = 9 N mod 16, kept even for the double2 pivot rows), so that the GPW * N lanes of a warp spread
+  // evenly over the banks: with the unpadded 164 doubles at N = 10 groups 0 and 1 shared 6 of their 10 bank pairs
+  static constexpr int kScrRaw = oPIV + 4 * NE;
+  static constexpr int kScrWant = ((9 * NE) % 16) & ~1;
+  static constexpr int SCR = kScrRaw + ((kScrWant - kScrRaw % 16) + 16) % 16;
   // shared-memory carve-up (doubles)
   static constexpr int D0 = 12 * NA + 8, Q0 = 3 * NA + 2;
   static constexpr int oCW0 = 0, oCW1 = oCW0 + D0 * NE, oCW2 = oCW1 + 20 * NE;
@@ -270,12 +275,22 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
     }
   }
   for (int t = tid; t < 20 * N; t += CF::T) smem[CF::oOW + t] = params[L.orb_w[0] + t];
-  for (int t = tid; t < 24 * N; t += CF::T) smem[CF::oGS + t] = cache[MC::GS + t];
+  // per-lane rows are stored lane-contiguous ([component][electron]): lane k of a group reads element k, so a group's
+  // access is one contiguous run of N doubles (the [electron][4] layout of the cache put lanes k and k+4 on the same
+  // banks: 16 % of the kernel's excess shared-memory wavefronts in the round-2 ncu source page)
+  for (int t = tid; t < 24 * N; t += CF::T) {             // GS[l][s][j][c] -> [l][s][c][j]
+    const int ls = t / (4 * N), r = t - ls * 4 * N, j = r >> 2, c = r & 3;
+    smem[CF::oGS + (ls * 4 + c) * N + j] = cache[MC::GS + t];
+  }
   for (int t = tid; t < 4 * A * N; t += CF::T) {          // H0[k][q] -> [q][k]
     const int kk = t / (4 * A), q = t - kk * 4 * A;
     smem[CF::oH0T + q * N + kk] = cache[MC::H0 + t];
   }
-  for (int t = tid; t < 8 * A + 9 * N + 4; t += CF::T) smem[CF::oG0M + t] = cache[MC::G0M + t];   // G0M Y ENV JAE JEE MISC
+  for (int t = tid; t < 8 * A + 9 * N + 4; t += CF::T) {   // G0M Y ENV JAE JEE MISC; Y[k][m] -> [m][k]
+    const int ty = t - 8 * A;
+    if (ty >= 0 && ty < 6 * N) smem[CF::oY + (ty % 6) * N + ty / 6] = cache[MC::G0M + t];
+    else smem[CF::oG0M + t] = cache[MC::G0M + t];
+  }
   for (int t = tid; t < 3 * N; t += CF::T) smem[CF::oX + t] = pos[b * 3 * N + t];
   if (tid < kExpTab) g_exp_tab[tid] = exp2((double)tid * (1.0 / kExpTab));
 
@@ -307,9 +322,9 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
   for (int i = 0; i < N; ++i) {
     const int si = i < n_up ? 0 : 1;
     // row i of the pair-chain cache and the (i,k) Jastrow parameters
-    for (int t = tid; t < 12 * N; t += CF::T) {
-      const int l = t / (4 * N), r = t - l * 4 * N;
-      smem[CF::oHP + t] = cache[MC::HP + (l * N + i) * N * 4 + r];
+    for (int t = tid; t < 12 * N; t += CF::T) {           // HP[l][i][k][c] -> [l][c][k]
+      const int l = t / (4 * N), r = t - l * 4 * N, kq = r >> 2, c = r & 3;
+      smem[CF::oHP + (l * 4 + c) * N + kq] = cache[MC::HP + (l * N + i) * N * 4 + r];
     }
     for (int t = tid; t < N; t += CF::T) {
       const int lo = i < t ? i : t, hi = i < t ? t : i;
@@ -354,14 +369,15 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
 #pragma unroll 1
       for (int it = 0;; ++it) {
         const int t0 = warp * GPW + it * NG;
-#if AIQMC_GRP_ALIGN
-        // all warps of the CTA walk the (large, straight-line) loop body together so that they share instruction
-        // fetches; warps past the end of the chunk run a dummy pass instead of leaving early
-        if (it * NG >= npt) break;                                      // CTA-uniform
-        __syncthreads();
-#else
-        if (t0 >= npt) break;                                           // warp-uniform
-#endif
+        constexpr bool kAlign = AIQMC_GRP_ALIGN < 0 ? (NE > 16) : (AIQMC_GRP_ALIGN != 0);
+        if constexpr (kAlign) {
+          // all warps of the CTA walk the (large, straight-line) loop body together so that they share instruction
+          // fetches; warps past the end of the chunk run a dummy pass instead of leaving early
+          if (it * NG >= npt) break;                                      // CTA-uniform
+          __syncthreads();
+        } else {
+          if (t0 >= npt) break;                                           // warp-uniform
+        }
         const bool valid = t0 + g < npt;
         const int t = valid ? t0 + g : npt - 1;
         const double* Lp = smem + CF::oL + t * LSTR;
@@ -386,7 +402,7 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
           if (act) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              red_in[k * 9 + c] = diag ? smem[CF::oHP + (l * N + k) * 4 + c] : cc[c];   // G'_l[s][i] terms
+              red_in[k * 9 + c] = diag ? smem[CF::oHP + (l * 4 + c) * N + k] : cc[c];   // G'_l[s][i] terms
               if (l > 0) red_in[k * 9 + 4 + c] = h[c];
             }
             if (l == 0) {
@@ -418,8 +434,8 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
           double Gu[4], Gd[4], gm0[4], gm1[4];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            double gu = smem[CF::oGS + ((l * 2 + 0) * N + kk) * 4 + c], gd = smem[CF::oGS + ((l * 2 + 1) * N + kk) * 4 + c];
-            const double delta = cr[c] - smem[CF::oHP + (l * N + kk) * 4 + c];
+            double gu = smem[CF::oGS + ((l * 2 + 0) * 4 + c) * N + kk], gd = smem[CF::oGS + ((l * 2 + 1) * 4 + c) * N + kk];
+            const double delta = cr[c] - smem[CF::oHP + (l * 4 + c) * N + kk];
             if (si == 0) gu += delta; else gd += delta;
             Gu[c] = (diag ? red_out[c] : gu) * inv_n[0];
             Gd[c] = (diag ? red_out[9 + c] : gd) * inv_n[1];
@@ -477,7 +493,7 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
 #pragma unroll
           for (int c = 0; c < 4; ++c) hs[c] = red_in[sig * 9 + 4 + c];
 #pragma unroll
-          for (int m = 0; m < 6; ++m) yr[m] = diag ? Lp[10 + m] : smem[CF::oY + kk * 6 + m];
+          for (int m = 0; m < 6; ++m) yr[m] = diag ? Lp[10 + m] : smem[CF::oY + m * N + kk];
           const double envr = diag ? Lp[8] : smem[CF::oENV + kk];
           const double* Wt = smem + CF::oOW + srow * 10 * N;
           const double* Bv = Wt + 8 * N;
