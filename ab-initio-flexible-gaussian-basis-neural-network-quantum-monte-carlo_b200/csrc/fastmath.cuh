@@ -107,8 +107,10 @@ AQF_HD double frsqrt(double x) {
   return fma(y, c, y);
 }
 
-AQF_HD double fexp(double x, const double* __restrict__ tab) {
-  x = fmin(fmax(x, -700.0), 700.0);
+template <bool NONPOS>
+AQF_HD double fexp_t(double x, const double* __restrict__ tab) {
+  if (NONPOS) x = x < -700.0 ? -700.0 : x;               // caller guarantees x <= 0: one compare + select
+  else x = fmin(fmax(x, -700.0), 700.0);
   const double kMagic = 6755399441055744.0;              // 1.5 * 2^52: rint via add
   const FmK& K = fmk();                                  // inv = 16/ln2, ln2hi + ln2lo = ln2/16 (head has 12 zero bits)
   const double t = fma(x, K.inv, kMagic);
@@ -131,6 +133,9 @@ AQF_HD double fexp(double x, const double* __restrict__ tab) {
   return ldexp(res, k);
 #endif
 }
+
+AQF_HD double fexp(double x, const double* __restrict__ tab) { return fexp_t<false>(x, tab); }
+AQF_HD double fexp_nonpos(double x, const double* __restrict__ tab) { return fexp_t<true>(x, tab); }
 
 // n tanh evaluations with the steps interleaved in source order, so the FP64 pipe always has n independent
 // dependency chains in flight (a single ftanh is a 13-deep chain of dependent DFMAs).

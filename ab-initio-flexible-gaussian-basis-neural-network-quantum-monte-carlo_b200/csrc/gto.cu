@@ -13,6 +13,7 @@
 #include <atomic>
 #include <mutex>
 #include <string.h>
+#include <type_traits>
 
 #include "../../include/aiqmc_b200.h"
 #include "fastmath.cuh"
@@ -61,6 +62,21 @@ __device__ __forceinline__ void solid_harmonics(double x, double y, double z, do
     s[4] = c * x * (4 * z2 - x2 - y2);   g[4][0] = c * (4 * z2 - 3 * x2 - y2); g[4][1] = -2 * c * x * y; g[4][2] = 8 * c * x * z;
     s[5] = e * z * (x2 - y2);            g[5][0] = 2 * e * x * z; g[5][1] = -2 * e * y * z; g[5][2] = e * (x2 - y2);
     s[6] = a * x * (x2 - 3 * y2);        g[6][0] = a * (3 * x2 - 3 * y2); g[6][1] = -6 * a * x * y; g[6][2] = 0;
+  }
+}
+
+// radial sums f, f', f'' of one shell at squared distance d2 (arguments of the exponentials are <= 0: one-sided clamp)
+template <int UNR>
+__device__ __forceinline__ void shell_radial(const AiqmcGtoShell& sh, double d2, const double* __restrict__ tab, double& f,
+                                             double& f1, double& f2) {
+  f = 0.0; f1 = 0.0; f2 = 0.0;
+#pragma unroll UNR
+  for (int p = 0; p < sh.n_prim; ++p) {
+    const double a = sh.alpha[p];
+    const double e = sh.coef[p] * fexp_nonpos(-a * d2, tab);
+    f += e;
+    f1 -= a * e;
+    f2 += a * a * e;
   }
 }
 
@@ -115,62 +131,98 @@ __global__ void __launch_bounds__(128) k_gto_eval(const double* __restrict__ poi
     }
   }
 }
-// Tiled variant: a CTA owns 128 consecutive points.  The coordinates arrive by coalesced loads through shared memory,
-// every thread evaluates its point into a shared-memory tile [point][AO] (rows of odd length: conflict-free), and the
-// tile -- a CONTIGUOUS block of val / grad / lap in HBM because the outputs are point-major -- leaves by coalesced
-// 16-byte stores.  The direct kernel above writes 65 doubles per thread at a stride of nao*8 bytes between lanes (one
-// 32-byte sector per store): 24 B in + 520 B out per point at C/cc-pVDZ ran at a few hundred GB/s.
-constexpr int kGtoTile = 128;
-__global__ void __launch_bounds__(kGtoTile) k_gto_eval_tiled(const double* __restrict__ points, int64_t n, int nao,
-                                                             double* __restrict__ val, double* __restrict__ grad,
-                                                             double* __restrict__ lap) {
-  extern __shared__ __align__(16) double s_gto[];
-  double* spts = s_gto;                                 // [128][3]
-  double* sval = spts + 3 * kGtoTile;                   // [128][nao]
-  double* sgrad = sval + kGtoTile * nao;                // [128][nao][3]
-  double* slap = sgrad + 3 * kGtoTile * nao;            // [128][nao]
+// Streaming kernel (the default): PERSISTENT warps, each looping over 32-point tiles with its own shared-memory tile
+// [point][AO] (rows of odd length: conflict-free).  The tile is a CONTIGUOUS block of val / grad / lap in HBM because the
+// outputs are point-major, so it leaves by three TMA bulk stores (cp.async.bulk shared -> global) issued by one lane.
+// The direct kernel above writes 65 doubles per thread at a stride of nao*8 bytes between lanes (one 32-byte sector per
+// store): 24 B in + 520 B out per point at C/cc-pVDZ ran at a few hundred GB/s.  History: a CTA-per-128-point-tile
+// kernel with per-thread 16-byte stores reached 2.9 TB/s, with bulk stores and 32-point tiles 3.7 TB/s; ncu on it: 34 % of the stall samples sat on the first instruction that needs the coordinates (a
+// DRAM round trip queued behind 0.76 GB of stores) and 9 % on the bulk-store drain before the CTA could retire.  Here the
+// NEXT tile's coordinates are fetched into registers before the current tile is evaluated, and a warp waits for its
+// previous bulk store only when it is about to overwrite the tile -- after the next coordinates have been requested.
+template <int UNR>
+__global__ void __launch_bounds__(128) k_gto_eval_stream(const double* __restrict__ points, int64_t n, int nao, int warps,
+                                                         double* __restrict__ val, double* __restrict__ grad,
+                                                         double* __restrict__ lap) {
+  extern __shared__ __align__(128) double s_gto[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < kExpTab) g_exp_tab[threadIdx.x] = exp2((double)threadIdx.x * (1.0 / kExpTab));
-  const int64_t t0 = (int64_t)blockIdx.x * kGtoTile;
-  const int np = (int)((n - t0) < kGtoTile ? (n - t0) : kGtoTile);
-  for (int q = threadIdx.x; q < 3 * np; q += kGtoTile) spts[q] = points[3 * t0 + q];
   __syncthreads();
+  if (warp >= warps) return;
   const double* tab = g_exp_tab;
-  if ((int)threadIdx.x < np) {
-    const double x = spts[3 * threadIdx.x], y = spts[3 * threadIdx.x + 1], z = spts[3 * threadIdx.x + 2];
-    for (int sidx = 0; sidx < c_gto.n_shells; ++sidx) {
-      const AiqmcGtoShell& sh = c_gto.shells[sidx];
-      const double dx = x - c_gto.centres[sh.centre][0], dy = y - c_gto.centres[sh.centre][1],
-                   dz = z - c_gto.centres[sh.centre][2];
-      const double d2 = dx * dx + dy * dy + dz * dz;
-      double f = 0.0, f1 = 0.0, f2 = 0.0;
-      for (int p = 0; p < sh.n_prim; ++p) {
-        const double a = sh.alpha[p];
-        const double e = sh.coef[p] * fexp(-a * d2, tab);
-        f += e;
-        f1 -= a * e;
-        f2 += a * a * e;
-      }
-      switch (sh.l) {            // uniform across the grid
-        case 0: shell_out<0>(sh, dx, dy, dz, f, f1, f2, d2, threadIdx.x, nao, sval, grad ? sgrad : nullptr, lap ? slap : nullptr); break;
-        case 1: shell_out<1>(sh, dx, dy, dz, f, f1, f2, d2, threadIdx.x, nao, sval, grad ? sgrad : nullptr, lap ? slap : nullptr); break;
-        case 2: shell_out<2>(sh, dx, dy, dz, f, f1, f2, d2, threadIdx.x, nao, sval, grad ? sgrad : nullptr, lap ? slap : nullptr); break;
-        default: shell_out<3>(sh, dx, dy, dz, f, f1, f2, d2, threadIdx.x, nao, sval, grad ? sgrad : nullptr, lap ? slap : nullptr); break;
-      }
-    }
-  }
-  __syncthreads();
-  auto stream_out = [&](const double* src, double* dst, int64_t count) {        // dst + t0*... is 16-byte aligned when count is even
-    if ((count & 1) == 0 && (((uintptr_t)dst) & 15) == 0) {
-      const double2* s2 = reinterpret_cast<const double2*>(src);
-      double2* d2p = reinterpret_cast<double2*>(dst);
-      for (int64_t q = threadIdx.x; q < count / 2; q += kGtoTile) d2p[q] = s2[q];
-    } else {
-      for (int64_t q = threadIdx.x; q < count; q += kGtoTile) dst[q] = src[q];
+  const int per_warp = ((160 * nao + 96) + 15) & ~15;   // doubles; keeps every warp's tile 128-byte aligned
+  double* sval = s_gto + (size_t)warp * per_warp;       // [32][nao]
+  double* sgrad = sval + 32 * nao;                      // [32][nao][3]
+  double* slap = sgrad + 96 * nao;                      // [32][nao]
+  double* spts = slap + 32 * nao;                       // [32][3]
+  const int64_t ntiles = (n + 31) / 32;
+  const int64_t stride = (int64_t)gridDim.x * warps;
+  int64_t tile = (int64_t)blockIdx.x * warps + warp;
+  const bool aligned = ((((uintptr_t)val) | ((uintptr_t)grad) | ((uintptr_t)lap)) & 15) == 0 && (nao * 32 % 2 == 0);
+  double pr[3];
+  auto fetch = [&](int64_t t) {
+    const int64_t base = 96 * t;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int64_t q = base + 32 * c + lane;
+      pr[c] = (t < ntiles && q < 3 * n) ? points[q] : 0.0;
     }
   };
-  stream_out(sval, val + t0 * nao, (int64_t)np * nao);
-  if (grad) stream_out(sgrad, grad + t0 * nao * 3, (int64_t)np * nao * 3);
-  if (lap) stream_out(slap, lap + t0 * nao, (int64_t)np * nao);
+  fetch(tile);
+  bool pending = false;
+  for (; tile < ntiles; tile += stride) {
+    const int64_t t0 = tile * 32;
+    const int np = (int)((n - t0) < 32 ? (n - t0) : 32);
+    if (pending) {                                         // the previous tile must have left before it is overwritten
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      pending = false;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 3; ++c) spts[32 * c + lane] = pr[c];
+    __syncwarp();
+    const double x = spts[3 * lane], y = spts[3 * lane + 1], z = spts[3 * lane + 2];
+    fetch(tile + stride);
+    if (lane < np) {
+      for (int sidx = 0; sidx < c_gto.n_shells; ++sidx) {
+        const AiqmcGtoShell& sh = c_gto.shells[sidx];
+        const double dx = x - c_gto.centres[sh.centre][0], dy = y - c_gto.centres[sh.centre][1],
+                     dz = z - c_gto.centres[sh.centre][2];
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        double f, f1, f2;
+        shell_radial<UNR>(sh, d2, tab, f, f1, f2);
+        switch (sh.l) {            // uniform across the grid
+          case 0: shell_out<0>(sh, dx, dy, dz, f, f1, f2, d2, lane, nao, sval, grad ? sgrad : nullptr, lap ? slap : nullptr); break;
+          case 1: shell_out<1>(sh, dx, dy, dz, f, f1, f2, d2, lane, nao, sval, grad ? sgrad : nullptr, lap ? slap : nullptr); break;
+          case 2: shell_out<2>(sh, dx, dy, dz, f, f1, f2, d2, lane, nao, sval, grad ? sgrad : nullptr, lap ? slap : nullptr); break;
+          default: shell_out<3>(sh, dx, dy, dz, f, f1, f2, d2, lane, nao, sval, grad ? sgrad : nullptr, lap ? slap : nullptr); break;
+        }
+      }
+    }
+    if (aligned && np == 32) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy tile writes -> visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        auto bulk = [&](const double* src, double* dst, int count) {
+          const uint32_t s32 = (uint32_t)__cvta_generic_to_shared(src);
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(s32), "r"((uint32_t)(count * 8))
+                       : "memory");
+        };
+        bulk(sval, val + t0 * nao, 32 * nao);
+        if (grad) bulk(sgrad, grad + t0 * nao * 3, 96 * nao);
+        if (lap) bulk(slap, lap + t0 * nao, 32 * nao);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      pending = true;
+    } else {                                               // ragged last tile / unaligned outputs: plain stores
+      __syncwarp();
+      for (int q = lane; q < np * nao; q += 32) val[t0 * nao + q] = sval[q];
+      if (grad) for (int q = lane; q < 3 * np * nao; q += 32) grad[t0 * nao * 3 + q] = sgrad[q];
+      if (lap) for (int q = lane; q < np * nao; q += 32) lap[t0 * nao + q] = slap[q];
+      __syncwarp();
+    }
+  }
+  if (pending && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 }  // namespace aiqmc
 
@@ -210,14 +262,29 @@ extern "C" int aiqmc_gto_eval(const AiqmcGtoShell* shells, int32_t n_shells, con
     valid[dev] = true;
   }
   ++g_launch_count;
-  const size_t smem = (size_t)(3 * kGtoTile + 5 * kGtoTile * nao) * sizeof(double);
-  if (smem <= 200 * 1024) {              // the output tile fits shared memory: coalesced stores
-    const cudaError_t ea = cudaFuncSetAttribute(k_gto_eval_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto go_stream = [&](auto unr_c) -> int {
+    constexpr int kUnr = decltype(unr_c)::value;
+    const size_t per_warp = (size_t)(((160 * nao + 96) + 15) & ~15) * sizeof(double);
+    int warps = (int)((200 * 1024) / per_warp);
+    if (warps < 1) return 1;                              // the tile of one warp does not fit: direct kernel
+    warps = warps > 4 ? 4 : warps;
+    const size_t smem = per_warp * warps;
+    int sms = 148, per_sm = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const cudaError_t ea = cudaFuncSetAttribute(k_gto_eval_stream<kUnr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ea != cudaSuccess) { g_last_cuda_error = (int)ea; return AIQMC_E_CUDA; }
-    k_gto_eval_tiled<<<(unsigned)((n_points + kGtoTile - 1) / kGtoTile), kGtoTile, smem, st>>>(points, n_points, nao, val, grad, lap);
-  } else {
-    k_gto_eval<<<(unsigned)((n_points + 127) / 128), 128, 0, st>>>(points, n_points, nao, val, grad, lap);
-  }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gto_eval_stream<kUnr>, 128, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const int64_t ntiles = (n_points + 31) / 32;
+    int64_t grid = (int64_t)sms * per_sm;                 // persistent: every resident warp loops over tiles
+    if (grid * warps > ntiles) grid = (ntiles + warps - 1) / warps;
+    k_gto_eval_stream<kUnr><<<(unsigned)grid, 128, smem, st>>>(points, n_points, nao, warps, val, grad, lap);
+    return 0;
+  };
+  // short runs are latency-bound (4 primitives in flight per thread: 46 vs 52 us at 393,216 points), long runs are
+  // issue-bound (rolled loop: 544 vs 617 us at 6.3 M points)
+  int rc = n_points <= (1 << 20) ? go_stream(std::integral_constant<int, 4>{}) : go_stream(std::integral_constant<int, 1>{});
+  if (rc < 0) return rc;
+  if (rc == 1) k_gto_eval<<<(unsigned)((n_points + 127) / 128), 128, 0, st>>>(points, n_points, nao, val, grad, lap);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_last_cuda_error = (int)e; return AIQMC_E_CUDA; }
   return AIQMC_OK;

@@ -311,21 +311,46 @@ __global__ void k_unpack_rows(const double* __restrict__ recvbuf, const int32_t*
 }
 
 // gather with 16-byte accesses when the row allows it
-__global__ void k_gather2(const double2* __restrict__ in, const int32_t* __restrict__ idx, int64_t B, int row2,
-                          double2* __restrict__ out) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= B * row2) return;
-  const int64_t b = t / row2;
-  const int c = (int)(t - b * row2);
-  out[t] = in[(int64_t)idx[b] * row2 + c];
+// Row gather out[b] = in[idx[b]] (A29, the reconfiguration of DMC/main_dmc.py:208-242).  HBM-bound: a thread moves
+// kGatherU elements 256 apart (all loads in flight before the first store; coalesced on both sides within a row run),
+// 32-bit index arithmetic (the launcher falls back to one element per thread beyond 2^31 elements).
+constexpr int kGatherU = 4;
+template <class T>
+__global__ void __launch_bounds__(256) k_gather_rows_u(const T* __restrict__ in, const int32_t* __restrict__ idx, uint32_t nt,
+                                                       uint32_t row, T* __restrict__ out) {
+  const uint32_t base = blockIdx.x * (256u * kGatherU) + threadIdx.x;
+  T v[kGatherU];
+#pragma unroll
+  for (int u = 0; u < kGatherU; ++u) {
+    const uint32_t t = base + 256u * u;
+    if (t < nt) {
+      const uint32_t b = t / row, c = t - b * row;
+      v[u] = in[(int64_t)idx[b] * row + c];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kGatherU; ++u) {
+    const uint32_t t = base + 256u * u;
+    if (t < nt) out[t] = v[u];
+  }
 }
-__global__ void k_gather1(const double* __restrict__ in, const int32_t* __restrict__ idx, int64_t B, int row,
-                          double* __restrict__ out) {
+template <class T>
+__global__ void k_gather_rows_1(const T* __restrict__ in, const int32_t* __restrict__ idx, int64_t B, int row, T* __restrict__ out) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= B * row) return;
   const int64_t b = t / row;
   const int c = (int)(t - b * row);
   out[t] = in[(int64_t)idx[b] * row + c];
+}
+template <class T>
+static void launch_gather(const T* in, const int32_t* idx, int64_t B, int row, T* out, cudaStream_t st) {
+  const int64_t nt = B * row;
+  if (nt < (int64_t)1 << 31) {
+    const unsigned per = 256u * kGatherU;
+    k_gather_rows_u<T><<<(unsigned)((nt + per - 1) / per), 256, 0, st>>>(in, idx, (uint32_t)nt, (uint32_t)row, out);
+  } else {
+    k_gather_rows_1<T><<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(in, idx, B, row, out);
+  }
 }
 
 // ------------------------------------------------------------------ NCCL, bound at run time
@@ -426,14 +451,10 @@ int aiqmc_gather_walkers(const double* pos_in, const int32_t* newinds, int64_t n
   if (!pos_in || !newinds || !pos_out || n_walkers < 0 || row_doubles < 1) return AIQMC_E_BADARG;
   if (n_walkers == 0) return AIQMC_OK;
   ++g_launch_count;
-  if (row_doubles % 2 == 0 && (((uintptr_t)pos_in | (uintptr_t)pos_out) & 15) == 0) {
-    const int64_t nt = n_walkers * (row_doubles / 2);
-    k_gather2<<<(unsigned)((nt + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const double2*)pos_in, newinds, n_walkers,
-                                                                             row_doubles / 2, (double2*)pos_out);
-  } else {
-    const int64_t nt = n_walkers * row_doubles;
-    k_gather1<<<(unsigned)((nt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pos_in, newinds, n_walkers, row_doubles, pos_out);
-  }
+  if (row_doubles % 2 == 0 && (((uintptr_t)pos_in | (uintptr_t)pos_out) & 15) == 0)
+    launch_gather<double2>((const double2*)pos_in, newinds, n_walkers, row_doubles / 2, (double2*)pos_out, (cudaStream_t)stream);
+  else
+    launch_gather<double>(pos_in, newinds, n_walkers, row_doubles, pos_out, (cudaStream_t)stream);
   AQ_CUDA_OK(cudaGetLastError());
   return AIQMC_OK;
 }

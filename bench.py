@@ -413,6 +413,8 @@ def time_hbm_kernels(eng, B, n, dev, flush):
         ts = []
         for _ in range(reps):
             flush.zero_()
+            flush.sum()                 # then READ it: L2 is left full of clean lines, so the write-back of the flush itself
+                                        # (up to 126 MB of dirty lines) is not charged to a 12-200 MB kernel
             a0, a1 = _events(2)
             a0.record(); fn(); a1.record(); torch.cuda.synchronize()
             ts.append(a0.elapsed_time(a1))
@@ -433,6 +435,24 @@ def time_hbm_kernels(eng, B, n, dev, flush):
     nbytes = B * 6 * (24 + 65 * 8)
     out["gto_eval_A0"] = {"ms": ms, "GB_per_s": nbytes / (ms * 1e-3) / 1e9, "bytes": nbytes, "points": B * 6,
                           "points_per_s": B * 6 / (ms * 1e-3), "what": "C cc-pVDZ, 13 AOs, value + gradient + Laplacian"}
+    # the same kernels on a 16x batch: at the BASELINE size gather / statistics / comb move 1-13 MB and are bounded by
+    # launch latency (~10 us), not by HBM; these rows show what the kernels sustain once the batch is HBM-sized
+    Bl = 16 * B
+    posl = torch.randn((Bl, 3 * n), dtype=torch.float64, device=dev)
+    indl = torch.randint(0, Bl, (Bl,), dtype=torch.int32, device=dev)
+    ms = timed(lambda: eng.gather_walkers(posl, indl))
+    out["gather_walkers_x16"] = {"ms": ms, "GB_per_s": (Bl * (48 * n + 4)) / (ms * 1e-3) / 1e9, "bytes": Bl * (48 * n + 4)}
+    del posl, indl
+    el = torch.randn((Bl, 2), dtype=torch.float64, device=dev)
+    ms = timed(lambda: eng.energy_stats(torch.view_as_complex(el)))
+    out["energy_stats_x16"] = {"ms": ms, "GB_per_s": (Bl * 16) / (ms * 1e-3) / 1e9, "bytes": Bl * 16}
+    del el
+    ptl = torch.randn((Bl * 6, 3), dtype=torch.float64, device=dev)
+    ms = timed(lambda: basis.eval(ptl))
+    nbl = Bl * 6 * (24 + 65 * 8)
+    out["gto_eval_A0_x16"] = {"ms": ms, "GB_per_s": nbl / (ms * 1e-3) / 1e9, "bytes": nbl, "points": Bl * 6}
+    del ptl
+    torch.cuda.empty_cache()
     return out
 
 

@@ -112,6 +112,28 @@ def test_kernel_matches_oracle_on_carbon_cc_pvdz(natoms):
 
 
 @pytest.mark.gpu
+def test_streaming_kernel_many_tiles_per_warp_matches_oracle():
+    """More 32-point tiles than resident warps (every persistent warp loops, prefetches and re-uses its shared-memory tile)
+    plus a ragged tail; also the rolled-loop instantiation used beyond 2^20 points agrees with the unrolled one."""
+    import aiqmc_b200
+    rng = np.random.default_rng(7)
+    atoms = np.zeros((1, 3))
+    basis = aiqmc_b200.GaussianBasis.from_nwchem(C_CC_PVDZ, atoms)
+    n = 32 * 4 * 148 * 4 + 17
+    pts = rng.normal(size=(n, 3)) * 2.0
+    val, grad, lap = (t.cpu().numpy() for t in basis.eval(pts))
+    shells = [(0, l, al, co) for _, l, al, co in G.parse_nwchem_basis(C_CC_PVDZ)]
+    v0, g0, l0 = G.eval_gto_with_derivatives(torch.tensor(pts), shells, torch.tensor(atoms))
+    np.testing.assert_allclose(val, v0.numpy(), rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(grad, g0.numpy(), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(lap, l0.numpy(), rtol=1e-9, atol=1e-11)
+    big = np.tile(pts[:65536], (17, 1))                                    # 1,114,112 points > 2^20
+    vb = basis.eval(big, want_grad=False, want_lap=False).cpu().numpy()
+    np.testing.assert_allclose(vb[-65536:], val[:65536], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(vb[:65536], val[:65536], rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.gpu
 def test_kernel_f_shell_and_bad_arguments():
     import aiqmc_b200
     rng = np.random.default_rng(6)
