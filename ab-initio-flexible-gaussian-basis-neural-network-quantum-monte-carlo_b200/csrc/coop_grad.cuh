@@ -102,8 +102,11 @@ __device__ __forceinline__ void coop_row_reverse(const double* __restrict__ P, i
 // SRC / OUT as k_grad_reverse (engine_impl.cuh): SRC == 1: configuration t = (walker b, moved electron i) built from
 // x1, the drift at x1 and gauss1; OUT == 1: only electron i's components are written, gnew (n_cfg,3).
 // Always: per-CTA partial of sum g^2 over ALL 3N components -> partials[blockIdx.x * 4 + pcol] (quirk Q6).
+#ifndef AIQMC_GRADCOOP_MINB
+#define AIQMC_GRADCOOP_MINB 1      // 3 (168 registers, ~100 B of spills, 12 warps/SM) measured: sweep 0.678 ms either way
+#endif
 template <int NE, int NA, int SRC, int OUT>
-__global__ void __launch_bounds__((CoopGradCfg<NE, NA>::T)) k_grad_coop(
+__global__ void __launch_bounds__((CoopGradCfg<NE, NA>::T), (NE <= 6 ? AIQMC_GRADCOOP_MINB : 1)) k_grad_coop(
     AiqmcSystem sys, const double* __restrict__ params, const double* __restrict__ pos, int64_t n_cfg, MovedSrc ms,
     double* __restrict__ phase, double* __restrict__ logabs, double* __restrict__ gout, double* __restrict__ partials,
     int pcol) {
