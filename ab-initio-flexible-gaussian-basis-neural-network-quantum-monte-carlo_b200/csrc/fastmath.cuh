@@ -7,11 +7,13 @@
 //              The table has 16 doubles = exactly one 128-byte row of shared-memory banks, so a warp's
 //              divergent lookups are conflict-free by construction (a 64-entry table measured 4-6
 //              wavefronts per LDS).  10 FP64 ops.  Relative error < 1e-15.
-//   ftanh(x):  2/(1+e) - 1 with e = exp(-2|x|) (degree-5 polynomial, single-constant reduction),
-//              reciprocal from the MUFU.RCP64H seed + one cubic step.  13 FP64 ops + one DMUL for -2|x| (the |.| is
-//              an operand modifier; the integer-op form cost three more issue slots), sign by integer ops on the high word.  ABSOLUTE error < 2e-13 (relative accuracy is lost for
-//              |x| < 1e-8 by design: only absolute accuracy enters log|psi| and E_L).
-//   ftanh_n<NV, ACC>: NV of them with interleaved steps (ILP); ACC = 1 is an 11-op variant (< 5e-11).
+//   ftanh(x):  1 - 2/(1 + exp(2x)) for either sign of x: no |x|, no sign fix-up (only ABSOLUTE accuracy enters log|psi|
+//              and E_L; the sign of a result below 1e-13 is not defined).  The reduction works on x itself
+//              (2x = n ln2/T + 2 r2, single constant) and the polynomial is exp(2 r2) in r2; reciprocal from the
+//              MUFU.RCP64H seed + one cubic step.  13 FP64 ops, absolute error < 2e-13.  (Round 1: exp(-2|x|), 14 ops
+//              plus two integer ops for the sign.)
+//   ftanh_n<NV, ACC>: NV of them with interleaved steps (ILP); ACC = 1 is the 9-op variant of the quadrature kernels
+//              (512-entry table, quadratic, one Newton step: < 5e-11).
 //   frcp(d), frsqrt(x): MUFU.RCP64H / MUFU.RSQ64H seed + one cubic step (3 / 5 FP64 ops), ~1 ulp.
 // Everything is __host__ __device__ so the host test build exercises the same arithmetic (the host
 // replaces the MUFU seeds by a float-precision division / sqrt).
@@ -40,11 +42,46 @@ __shared__ double g_exp_tab[kExpTab];
 #define AQF_TAB(tab, j) (tab)[j]
 #endif
 
+// ACC = 1 tanh of the quadrature kernels: a 512-entry table 2^(j/512) (4 kB) shrinks the reduced argument to
+// |2 r2| <= ln2/1024, where a QUADRATIC is enough for the same accuracy ((ln2/1024)^3/6 < 5.2e-11 on the exponential,
+// half of that on tanh): two polynomial terms fewer than with the 16-entry table.  The lookup is no longer
+// conflict-free (32 lanes over 16 bank pairs: ~4-5 wavefronts), but those kernels leave the shared-memory pipe mostly
+// idle and are bound by the FP64 pipe.  Measured on k_ecp_pt (carbon, 65,536 walkers): 16 entries / quartic 4.92 ms,
+// 64 entries / cubic 4.81 ms.
+#ifndef AIQMC_TANH_TAB64
+#define AIQMC_TANH_TAB64 1
+#endif
+#ifndef AIQMC_TANH_I2F
+#define AIQMC_TANH_I2F 0      // 1: rint(u*inv) back to double by I2F.F64 instead of `t - magic` (measured: 4.85 vs 4.81 ms, no gain)
+#endif
+constexpr int kExpTab64 = 512;       // (the name dates from the 64-entry version)
+constexpr int kExpTab64Log2 = 9;
+#ifdef __CUDACC__
+__shared__ double g_exp_tab64[kExpTab64];            // filled by the prologue of every kernel that evaluates ACC = 1 tanh
+#endif
+inline const double* host_exp_table64() {
+  static double tab[kExpTab64];
+  static bool init = false;
+  if (!init) {
+    for (int j = 0; j < kExpTab64; ++j) tab[j] = exp2((double)j / kExpTab64);
+    init = true;
+  }
+  return tab;
+}
+#ifdef __CUDA_ARCH__
+#define AQF_TAB64(j) g_exp_tab64[j]
+#else
+#define AQF_TAB64(j) host_exp_table64()[j]
+#endif
+
 // Polynomial / reduction constants.  On the device they live in constant memory so that each one is a
 // c[3][imm] operand of the DFMA that uses it (as 64-bit literals every use costs two IMAD.MOVs).
-struct FmK { double inv, ln2, ln2hi, ln2lo, c2, c3, c4, c5, c6; };
+// tanh: inv16x2 = 2*16/ln2, hl16 = ln2/32, inv64x2 = 2*512/ln2, hl64 = ln2/1024, e3..e5 = 2^k/k! (exp(2 r) coefficients)
+struct FmK { double inv, ln2, ln2hi, ln2lo, c2, c3, c4, c5, c6, inv16x2, hl16, inv64x2, hl64, e3, e4, e5; };
 #define AQF_FMK_INIT {23.083120654223414, 0.04332169878499658, 0.043321698784978935, 1.7647056601894736e-14, \
-                      0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0}
+                      0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, \
+                      46.166241308446828, 0.021660849392498290, 1477.3197218702985, 0.0006769015435155716, \
+                      4.0 / 3.0, 2.0 / 3.0, 4.0 / 15.0}
 #ifdef __CUDACC__
 static __constant__ FmK c_fmk = AQF_FMK_INIT;
 #endif
@@ -139,34 +176,25 @@ AQF_HD double fexp_nonpos(double x, const double* __restrict__ tab) { return fex
 
 // n tanh evaluations with the steps interleaved in source order, so the FP64 pipe always has n independent
 // dependency chains in flight (a single ftanh is a 13-deep chain of dependent DFMAs).
-//   ACC = 0: degree-5 polynomial, cubic reciprocal step:     13 FP64 ops, absolute error < 2e-13
-//   ACC = 1: degree-4 polynomial, quadratic reciprocal step: 11 FP64 ops, absolute error < 5e-11
+//   ACC = 0: 16-entry table, degree-5 polynomial, cubic reciprocal step:  13 FP64 ops, absolute error < 2e-13
+//   ACC = 1: 512-entry table, quadratic, quadratic reciprocal step:         9 FP64 ops, absolute error < 5e-11
 //            (value-only quadrature kernels: 1e-10 on log psi is 5 orders below the 1e-5 Ha tolerance)
-// Domain: |x| < 4e7 (beyond that the int32 reduction index overflows; tanh saturates at |x| ~ 19).
+// Domain: |x| < 1e6 (beyond that the int32 reduction index overflows; tanh saturates at |x| ~ 19).
 template <int NV, int ACC>
 AQF_HD void ftanh_n(const double* __restrict__ x, double* __restrict__ out, const double* __restrict__ tab) {
+  // tanh(x) = 1 - 2/(1 + exp(2x)) for either sign of x (no |x|, no sign fix-up: for x << 0 the exponential vanishes, for
+  // x >> 0 the reciprocal does; ABSOLUTE accuracy is what log|psi| and E_L see).  The reduction works on x itself:
+  // 2x = n ln2/T + 2 r2 with n = rint(2x T/ln2), |r2| <= ln2/(4T), and the polynomial is exp(2 r2) in r2, so the doubling
+  // costs nothing.  T = 16 (conflict-free table) or 64 (ACC = 1, see above).
   const double kMagic = 6755399441055744.0;
   const FmK& K = fmk();
-  double u[NV], t[NV], r[NV], p[NV], d[NV], y[NV];
+  constexpr bool kT64 = (ACC == 1) && (AIQMC_TANH_TAB64 != 0);
+  double t[NV], r[NV], p[NV], d[NV], y[NV];
   int n[NV];
-  uint32_t sg[NV];               // sign of x, taken first so that x itself is dead once u exists (one register, not two)
 #ifdef __CUDACC__
 #pragma unroll
 #endif
-  for (int i = 0; i < NV; ++i) {
-    const uint32_t hx = (uint32_t)hi_word(x[i]);
-    sg[i] = hx & 0x80000000u;
-#if !defined(AIQMC_TANH_INTABS) && defined(__CUDA_ARCH__)
-    u[i] = -2.0 * fabs(x[i]);    // one DMUL with the |.| operand modifier instead of three integer ops and a move
-#else
-    // u = -2|x| by integer ops (exponent + 1, sign set); x = 0 gives a harmless |u| <= 2^-1021
-    u[i] = make_double((int32_t)(((hx & 0x7fffffffu) + 0x00100000u) | 0x80000000u), lo_word(x[i]));
-#endif
-  }
-#ifdef __CUDACC__
-#pragma unroll
-#endif
-  for (int i = 0; i < NV; ++i) t[i] = fma(u[i], K.inv, kMagic);
+  for (int i = 0; i < NV; ++i) t[i] = fma(x[i], kT64 ? K.inv64x2 : K.inv16x2, kMagic);
 #ifdef __CUDACC__
 #pragma unroll
 #endif
@@ -174,42 +202,50 @@ AQF_HD void ftanh_n(const double* __restrict__ x, double* __restrict__ out, cons
 #ifdef __CUDACC__
 #pragma unroll
 #endif
-  for (int i = 0; i < NV; ++i) r[i] = fma(-t[i], K.ln2, u[i]);
-  if (ACC == 0) {
+  for (int i = 0; i < NV; ++i) r[i] = fma(-t[i], kT64 ? K.hl64 : K.hl16, x[i]);       // r2 = x - n ln2/(2T)
+  // exp(2 r2) = 1 + 2 r2 + 2 r2^2 + 4/3 r2^3 + 2/3 r2^4 + 4/15 r2^5
+  if (kT64) {
 #ifdef __CUDACC__
 #pragma unroll
 #endif
-    for (int i = 0; i < NV; ++i) p[i] = fma(r[i], K.c5, K.c4);
-#ifdef __CUDACC__
-#pragma unroll
-#endif
-    for (int i = 0; i < NV; ++i) p[i] = fma(r[i], p[i], K.c3);
+    for (int i = 0; i < NV; ++i) p[i] = 2.0;
   } else {
+    if (ACC == 0) {
 #ifdef __CUDACC__
 #pragma unroll
 #endif
-    for (int i = 0; i < NV; ++i) p[i] = fma(r[i], K.c4, K.c3);
+      for (int i = 0; i < NV; ++i) p[i] = fma(r[i], K.e5, K.e4);
+#ifdef __CUDACC__
+#pragma unroll
+#endif
+      for (int i = 0; i < NV; ++i) p[i] = fma(r[i], p[i], K.e3);
+    } else {
+#ifdef __CUDACC__
+#pragma unroll
+#endif
+      for (int i = 0; i < NV; ++i) p[i] = fma(r[i], K.e4, K.e3);
+    }
+#ifdef __CUDACC__
+#pragma unroll
+#endif
+    for (int i = 0; i < NV; ++i) p[i] = fma(r[i], p[i], 2.0);
   }
 #ifdef __CUDACC__
 #pragma unroll
 #endif
-  for (int i = 0; i < NV; ++i) p[i] = fma(r[i], p[i], 0.5);
+  for (int i = 0; i < NV; ++i) p[i] = fma(r[i], p[i], 2.0);
 #ifdef __CUDACC__
 #pragma unroll
 #endif
-  for (int i = 0; i < NV; ++i) p[i] = fma(r[i], p[i], 1.0);
-#ifdef __CUDACC__
-#pragma unroll
-#endif
-  for (int i = 0; i < NV; ++i) p[i] = fma(r[i], p[i], 1.0);              // exp(r), |r| <= ln2/32
+  for (int i = 0; i < NV; ++i) p[i] = fma(r[i], p[i], 1.0);              // exp(2 r2)
 #ifdef __CUDACC__
 #pragma unroll
 #endif
   for (int i = 0; i < NV; ++i) {
-    const double tj = AQF_TAB(tab, n[i] & (kExpTab - 1));
-    int k = n[i] >> 4;
-    k = k < -64 ? -64 : k;                                               // e < 2^-64 no longer changes 1 + e
-    d[i] = fma(make_double(hi_word(tj) + (k << 20), lo_word(tj)), p[i], 1.0);   // 1 + exp(-2|x|) in (1, 2]
+    const double tj = kT64 ? AQF_TAB64(n[i] & (kExpTab64 - 1)) : AQF_TAB(tab, n[i] & (kExpTab - 1));
+    int k = kT64 ? (n[i] >> kExpTab64Log2) : (n[i] >> 4);
+    k = k < -64 ? -64 : (k > 64 ? 64 : k);                               // beyond 2^+-64 the result is +-1 to the last bit
+    d[i] = fma(make_double(hi_word(tj) + (k << 20), lo_word(tj)), p[i], 1.0);   // 1 + exp(2x)
   }
 #ifdef __CUDACC__
 #pragma unroll
@@ -238,10 +274,7 @@ AQF_HD void ftanh_n(const double* __restrict__ x, double* __restrict__ out, cons
 #ifdef __CUDACC__
 #pragma unroll
 #endif
-  for (int i = 0; i < NV; ++i) {
-    const double th = fma(2.0, y[i], -1.0);
-    out[i] = make_double((int32_t)((uint32_t)hi_word(th) | sg[i]), lo_word(th));
-  }
+  for (int i = 0; i < NV; ++i) out[i] = fma(-2.0, y[i], 1.0);
 }
 
 AQF_HD double ftanh(double x, const double* __restrict__ tab) {

@@ -448,8 +448,9 @@ int aiqmc_branch_comb(const double* weights, int64_t n_walkers, double u, int32_
 
 int aiqmc_gather_walkers(const double* pos_in, const int32_t* newinds, int64_t n_walkers, int32_t row_doubles,
                          double* pos_out, void* stream) {
-  if (!pos_in || !newinds || !pos_out || n_walkers < 0 || row_doubles < 1) return AIQMC_E_BADARG;
-  if (n_walkers == 0) return AIQMC_OK;
+  if (n_walkers < 0 || row_doubles < 1) return AIQMC_E_BADARG;
+  if (n_walkers == 0) return AIQMC_OK;                               // an empty selection may come with null buffers
+  if (!pos_in || !newinds || !pos_out) return AIQMC_E_BADARG;
   ++g_launch_count;
   if (row_doubles % 2 == 0 && (((uintptr_t)pos_in | (uintptr_t)pos_out) & 15) == 0)
     launch_gather<double2>((const double2*)pos_in, newinds, n_walkers, row_doubles / 2, (double2*)pos_out, (cudaStream_t)stream);

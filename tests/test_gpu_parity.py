@@ -196,6 +196,19 @@ def test_branch_comb_bit_exact_on_dyadic_weights_and_gather(B):
     assert np.mean(ig.cpu().numpy() != ir.numpy()) < 1e-3
 
 
+@pytest.mark.parametrize("rows,width,picks", [(1, 9, 1), (1025, 9, 1023), (4099, 27, 5000), (3000, 90, 1024 * 4 + 1), (777, 12, 0)])
+def test_gather_walkers_ragged_sizes_and_odd_row_widths(rows, width, picks):
+    """The gather moves 4 elements per thread 256 apart: sizes that are not multiples of 1024 elements, odd row widths
+    (8-byte path), fewer / more picks than rows, and an empty selection."""
+    rng = np.random.default_rng(rows * 31 + width)
+    eng = engine(Case(**CASES["C_ecp"], nwalkers=2))
+    pos = torch.tensor(rng.normal(size=(rows, width))).cuda()
+    inds = torch.tensor(rng.integers(0, rows, size=picks), dtype=torch.int32).cuda()
+    out = eng.gather_walkers(pos, inds)
+    assert out.shape == (picks, width)
+    np.testing.assert_array_equal(out.cpu().numpy(), pos.cpu().numpy()[inds.cpu().numpy()])
+
+
 def test_unsupported_system_and_bad_args_fail_loudly(monkeypatch):
     monkeypatch.setenv("AIQMC_NO_AUTOBUILD", "1")          # (7,3) is not in the prebuilt set; do not compile it here
     case = Case(n=7, natoms=3, spins=[1.] * 4 + [-1.] * 3, seed=3)
