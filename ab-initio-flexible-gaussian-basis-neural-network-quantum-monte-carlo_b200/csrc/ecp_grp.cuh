@@ -294,7 +294,7 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
   for (int t = tid; t < 3 * N; t += CF::T) smem[CF::oX + t] = pos[b * 3 * N + t];
   if (tid < kExpTab) g_exp_tab[tid] = exp2((double)tid * (1.0 / kExpTab));
   if (kAcc == 1 && AIQMC_TANH_TAB64)
-      for (int j = tid; j < kExpTab64; j += (int)blockDim.x) g_exp_tab64[j] = exp2((double)j * (1.0 / kExpTab64));
+      for (int j = tid; j < kExpTab64; j += (int)blockDim.x) g_exp_tab64[j] = exp2((double)j * (1.0 / kExpTab64) - 64.0);
 
   // ---- lane roles
   const int lane = tid & 31, warp = tid >> 5;

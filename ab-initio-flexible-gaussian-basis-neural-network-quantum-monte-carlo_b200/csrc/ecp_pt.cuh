@@ -162,7 +162,7 @@ k_ecp_pt(AiqmcSystem sys, const double* __restrict__ pos, const double* __restri
     }
     if (tid < kExpTab) g_exp_tab[tid] = exp2((double)tid * (1.0 / kExpTab));
     if (kAcc == 1 && AIQMC_TANH_TAB64)
-      for (int j = tid; j < kExpTab64; j += (int)blockDim.x) g_exp_tab64[j] = exp2((double)j * (1.0 / kExpTab64));
+      for (int j = tid; j < kExpTab64; j += (int)blockDim.x) g_exp_tab64[j] = exp2((double)j * (1.0 / kExpTab64) - 64.0);
     __syncthreads();                     // publishes the mbarrier initialisation to the waiting threads
     asm volatile(
         "{\n"

@@ -63,7 +63,7 @@ inline const double* host_exp_table64() {
   static double tab[kExpTab64];
   static bool init = false;
   if (!init) {
-    for (int j = 0; j < kExpTab64; ++j) tab[j] = exp2((double)j / kExpTab64);
+    for (int j = 0; j < kExpTab64; ++j) tab[j] = exp2((double)j / kExpTab64 - 64.0);
     init = true;
   }
   return tab;
@@ -186,7 +186,7 @@ AQF_HD void ftanh_n(const double* __restrict__ x, double* __restrict__ out, cons
   // x >> 0 the reciprocal does; ABSOLUTE accuracy is what log|psi| and E_L see).  The reduction works on x itself:
   // 2x = n ln2/T + 2 r2 with n = rint(2x T/ln2), |r2| <= ln2/(4T), and the polynomial is exp(2 r2) in r2, so the doubling
   // costs nothing.  T = 16 (conflict-free table) or 64 (ACC = 1, see above).
-  const double kMagic = 6755399441055744.0;
+  constexpr double kMagic = 6755399441055744.0;
   const FmK& K = fmk();
   constexpr bool kT64 = (ACC == 1) && (AIQMC_TANH_TAB64 != 0);
   double t[NV], r[NV], p[NV], d[NV], y[NV];
@@ -194,11 +194,14 @@ AQF_HD void ftanh_n(const double* __restrict__ x, double* __restrict__ out, cons
 #ifdef __CUDACC__
 #pragma unroll
 #endif
-  for (int i = 0; i < NV; ++i) t[i] = fma(x[i], kT64 ? K.inv64x2 : K.inv16x2, kMagic);
+  // kT64: the magic constant carries a bias of 64 * 512, so the exponent k arrives as k + 64 >= 0 for every argument
+  // that matters and ONE relu-min clamps it to [0, 128]; the table holds 2^(j/512 - 64) to take the bias out again
+  constexpr double kMagicB = kT64 ? kMagic + 64.0 * kExpTab64 : kMagic;
+  for (int i = 0; i < NV; ++i) t[i] = fma(x[i], kT64 ? K.inv64x2 : K.inv16x2, kMagicB);
 #ifdef __CUDACC__
 #pragma unroll
 #endif
-  for (int i = 0; i < NV; ++i) { n[i] = lo_word(t[i]); t[i] = t[i] - kMagic; }
+  for (int i = 0; i < NV; ++i) { n[i] = lo_word(t[i]); t[i] = t[i] - kMagicB; }
 #ifdef __CUDACC__
 #pragma unroll
 #endif
@@ -244,7 +247,15 @@ AQF_HD void ftanh_n(const double* __restrict__ x, double* __restrict__ out, cons
   for (int i = 0; i < NV; ++i) {
     const double tj = kT64 ? AQF_TAB64(n[i] & (kExpTab64 - 1)) : AQF_TAB(tab, n[i] & (kExpTab - 1));
     int k = kT64 ? (n[i] >> kExpTab64Log2) : (n[i] >> 4);
-    k = k < -64 ? -64 : (k > 64 ? 64 : k);                               // beyond 2^+-64 the result is +-1 to the last bit
+    if (kT64) {
+#ifdef __CUDA_ARCH__
+      k = __vimin_s32_relu(k, 128);                                      // max(min(k + 64, 128), 0) in one VIMNMX.RELU
+#else
+      k = k < 0 ? 0 : (k > 128 ? 128 : k);
+#endif
+    } else {
+      k = k < -64 ? -64 : (k > 64 ? 64 : k);                             // beyond 2^+-64 the result is +-1 to the last bit
+    }
     d[i] = fma(make_double(hi_word(tj) + (k << 20), lo_word(tj)), p[i], 1.0);   // 1 + exp(2x)
   }
 #ifdef __CUDACC__
