@@ -61,7 +61,8 @@ def _extra_flags():
 
 
 def plugin_path(n: int, a: int) -> str:
-    return os.path.join(HERE, f"libaiqmc_sys_{n}_{a}.so")
+    """$AIQMC_PLUGIN_DIR (the directory the loader searches first) also redirects where plugins are built: A/B variants."""
+    return os.path.join(os.environ.get("AIQMC_PLUGIN_DIR") or HERE, f"libaiqmc_sys_{n}_{a}.so")
 
 
 def _inst_source(n: int, a: int) -> str:

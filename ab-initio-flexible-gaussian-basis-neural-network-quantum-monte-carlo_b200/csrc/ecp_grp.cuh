@@ -169,10 +169,14 @@ __device__ __forceinline__ void grp_one_layer(const double* __restrict__ cw, con
       }
     }
   }
-  double tz[4];
-  tanhv<4, kAcc>(z, tz);
+  if (DIN == 4) {                                                    // residual only if shapes match (Q5)
+    double hin[4];
 #pragma unroll
-  for (int m = 0; m < 4; ++m) hout[m] = (DIN == 4) ? (in(m) + tz[m]) * kInvSqrt2 : tz[m];   // residual only if shapes match (Q5)
+    for (int m = 0; m < 4; ++m) hin[m] = in(m);
+    tanh_res<4, kAcc>(z, hin, hout);
+  } else {
+    tanhv<4, kAcc>(z, hout);
+  }
 }
 
 
@@ -293,8 +297,7 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
   }
   for (int t = tid; t < 3 * N; t += CF::T) smem[CF::oX + t] = pos[b * 3 * N + t];
   if (tid < kExpTab) g_exp_tab[tid] = exp2((double)tid * (1.0 / kExpTab));
-  if (kAcc == 1 && AIQMC_TANH_TAB64)
-      for (int j = tid; j < kExpTab64; j += (int)blockDim.x) g_exp_tab64[j] = exp2((double)j * (1.0 / kExpTab64) - 64.0);
+  if (kAcc == 1 && AIQMC_TANH_TAB64) fill_tanh_table(tid, (int)blockDim.x);
 
   // ---- lane roles
   const int lane = tid & 31, warp = tid >> 5;
@@ -474,12 +477,11 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
             for (int q = 0; q < 4; ++q)
 #pragma unroll
               for (int m = 0; m < 4; ++m) { z[m] += cr[q] * c_uni[WO + q * 4 + m]; z[4 + m] += cc[q] * c_uni[WO + q * 4 + m]; }
-            tanhv<8, kAcc>(z, tt);
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-              cr[m] = (cr[m] + tt[m]) * kInvSqrt2;
-              cc[m] = (cc[m] + tt[4 + m]) * kInvSqrt2;
-            }
+            for (int m = 0; m < 4; ++m) { tt[m] = cr[m]; tt[4 + m] = cc[m]; }
+            tanh_res<8, kAcc>(z, tt, tt);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) { cr[m] = tt[m]; cc[m] = tt[4 + m]; }
           }
         }
 

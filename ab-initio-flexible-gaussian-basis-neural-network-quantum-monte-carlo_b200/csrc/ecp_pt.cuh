@@ -161,8 +161,7 @@ k_ecp_pt(AiqmcSystem sys, const double* __restrict__ pos, const double* __restri
                    ::"r"(dst), "l"(cache_all + b0 * MC::SIZE), "r"(bytes), "r"(bar) : "memory");
     }
     if (tid < kExpTab) g_exp_tab[tid] = exp2((double)tid * (1.0 / kExpTab));
-    if (kAcc == 1 && AIQMC_TANH_TAB64)
-      for (int j = tid; j < kExpTab64; j += (int)blockDim.x) g_exp_tab64[j] = exp2((double)j * (1.0 / kExpTab64) - 64.0);
+    if (kAcc == 1 && AIQMC_TANH_TAB64) fill_tanh_table(tid, (int)blockDim.x);
     __syncthreads();                     // publishes the mbarrier initialisation to the waiting threads
     asm volatile(
         "{\n"
@@ -306,12 +305,11 @@ k_ecp_pt(AiqmcSystem sys, const double* __restrict__ pos, const double* __restri
               for (int q = 0; q < 4; ++q)
 #pragma unroll
                 for (int m = 0; m < 4; ++m) { z[m] += cr[k][q] * W[q * 4 + m]; z[4 + m] += cc[k][q] * W[q * 4 + m]; }
-              tanhv<8, kAcc>(z, t);
 #pragma unroll
-              for (int m = 0; m < 4; ++m) {
-                cr[k][m] = (cr[k][m] + t[m]) * kInvSqrt2;
-                cc[k][m] = (cc[k][m] + t[4 + m]) * kInvSqrt2;
-              }
+              for (int m = 0; m < 4; ++m) { t[m] = cr[k][m]; t[4 + m] = cc[k][m]; }
+              tanh_res<8, kAcc>(z, t, t);
+#pragma unroll
+              for (int m = 0; m < 4; ++m) { cr[k][m] = t[m]; cc[k][m] = t[4 + m]; }
             }
           }
         }

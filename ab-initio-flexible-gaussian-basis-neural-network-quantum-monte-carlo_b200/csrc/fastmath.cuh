@@ -68,6 +68,31 @@ inline const double* host_exp_table64() {
   }
   return tab;
 }
+#ifdef __CUDACC__
+// Prologue fill of g_exp_tab64 = 2^(j/512 - 64): 2^(a/16 - 64) from 16 literals (index uniform per warp: a broadcast
+// constant load) times exp((j & 31) ln2/512) by a degree-7 polynomial -- a dozen instructions per entry instead of a
+// libm exp2 (the exp2 fill was 1.9 % of k_ecp_pt's instructions).
+static __constant__ double c_exp16_m64[16] = {
+    0x1.0000000000000p-64, 0x1.0b5586cf9890fp-64, 0x1.172b83c7d517bp-64, 0x1.2387a6e756238p-64, 0x1.306fe0a31b715p-64,
+    0x1.3dea64c123422p-64, 0x1.4bfdad5362a27p-64, 0x1.5ab07dd485429p-64, 0x1.6a09e667f3bcdp-64, 0x1.7a11473eb0187p-64,
+    0x1.8ace5422aa0dbp-64, 0x1.9c49182a3f090p-64, 0x1.ae89f995ad3adp-64, 0x1.c199bdd85529cp-64, 0x1.d5818dcfba487p-64,
+    0x1.ea4afa2a490dap-64};
+__device__ __forceinline__ void fill_tanh_table(int tid, int nthreads) {
+  static_assert(kExpTab64 == 512, "16 x 32 factorisation");
+  for (int j = tid; j < kExpTab64; j += nthreads) {
+    const double x = (double)(j & 31) * (0.69314718055994530942 / 512.0);      // <= 0.042: x^8/8! < 3e-16
+    double p = 1.0 / 5040.0;
+    p = fma(x, p, 1.0 / 720.0);
+    p = fma(x, p, 1.0 / 120.0);
+    p = fma(x, p, 1.0 / 24.0);
+    p = fma(x, p, 1.0 / 6.0);
+    p = fma(x, p, 0.5);
+    p = fma(x, p, 1.0);
+    p = fma(x, p, 1.0);
+    g_exp_tab64[j] = c_exp16_m64[j >> 5] * p;
+  }
+}
+#endif
 #ifdef __CUDA_ARCH__
 #define AQF_TAB64(j) g_exp_tab64[j]
 #else
@@ -180,7 +205,9 @@ AQF_HD double fexp_nonpos(double x, const double* __restrict__ tab) { return fex
 //   ACC = 1: 512-entry table, quadratic, quadratic reciprocal step:         9 FP64 ops, absolute error < 5e-11
 //            (value-only quadrature kernels: 1e-10 on log psi is 5 orders below the 1e-5 Ha tolerance)
 // Domain: |x| < 1e6 (beyond that the int32 reduction index overflows; tanh saturates at |x| ~ 19).
-template <int NV, int ACC>
+// RAW = true returns y = 1/(1 + exp(2x)) instead of tanh(x) = 1 - 2y, for callers that fold the affine map into their
+// own next FMA (tanh_res in psi_core.cuh: (h + tanh z)/sqrt2 = fma(y, -sqrt2, fma(h, 1/sqrt2, 1/sqrt2)), one op fewer).
+template <int NV, int ACC, bool RAW = false>
 AQF_HD void ftanh_n(const double* __restrict__ x, double* __restrict__ out, const double* __restrict__ tab) {
   // tanh(x) = 1 - 2/(1 + exp(2x)) for either sign of x (no |x|, no sign fix-up: for x << 0 the exponential vanishes, for
   // x >> 0 the reciprocal does; ABSOLUTE accuracy is what log|psi| and E_L see).  The reduction works on x itself:
@@ -191,12 +218,12 @@ AQF_HD void ftanh_n(const double* __restrict__ x, double* __restrict__ out, cons
   constexpr bool kT64 = (ACC == 1) && (AIQMC_TANH_TAB64 != 0);
   double t[NV], r[NV], p[NV], d[NV], y[NV];
   int n[NV];
-#ifdef __CUDACC__
-#pragma unroll
-#endif
   // kT64: the magic constant carries a bias of 64 * 512, so the exponent k arrives as k + 64 >= 0 for every argument
   // that matters and ONE relu-min clamps it to [0, 128]; the table holds 2^(j/512 - 64) to take the bias out again
   constexpr double kMagicB = kT64 ? kMagic + 64.0 * kExpTab64 : kMagic;
+#ifdef __CUDACC__
+#pragma unroll
+#endif
   for (int i = 0; i < NV; ++i) t[i] = fma(x[i], kT64 ? K.inv64x2 : K.inv16x2, kMagicB);
 #ifdef __CUDACC__
 #pragma unroll
@@ -285,7 +312,7 @@ AQF_HD void ftanh_n(const double* __restrict__ x, double* __restrict__ out, cons
 #ifdef __CUDACC__
 #pragma unroll
 #endif
-  for (int i = 0; i < NV; ++i) out[i] = fma(-2.0, y[i], 1.0);
+  for (int i = 0; i < NV; ++i) out[i] = RAW ? y[i] : fma(-2.0, y[i], 1.0);
 }
 
 AQF_HD double ftanh(double x, const double* __restrict__ tab) {

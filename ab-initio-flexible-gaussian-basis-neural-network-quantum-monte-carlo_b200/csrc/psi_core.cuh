@@ -247,6 +247,39 @@ template <int NV, int ACC, bool L, int ND>
 AQ_HD void tanhv(const Jet<L, ND>* __restrict__ z, Jet<L, ND>* __restrict__ out) {
   for (int i = 0; i < NV; ++i) out[i] = s_tanh(z[i]);
 }
+#ifndef AIQMC_TANH_RESFUSE
+#define AIQMC_TANH_RESFUSE 0   // measured A/B on one box: k_ecp_pt 4.54 ms fused vs 4.50 ms unfused (fewer FP64 ops, but more
+#endif                         // spill traffic at the 128-register cap); k_ecp_grp<10,2> 131.5 vs 132.4 ms.  Off by default.
+// out[i] = (h[i] + tanh(z[i])) / sqrt(2): the residual update of every stream (nn.py:305-309, 327-341).  On plain
+// doubles the tanh's last FMA (1 - 2y) is folded into the update: 2 FP64 ops after the reciprocal instead of 3.
+// `out` may alias `h`.
+template <int NV, int ACC>
+AQ_HD void tanh_res(const double* __restrict__ z, const double* h, double* out) {
+#if defined(AIQMC_LIBM) || (defined(AIQMC_TANH_OOL) && defined(__CUDA_ARCH__)) || !AIQMC_TANH_RESFUSE
+  double t[NV];
+  tanhv<NV, ACC>(z, t);
+  for (int i = 0; i < NV; ++i) out[i] = (h[i] + t[i]) * kInvSqrt2;
+#else
+  constexpr double kSqrt2 = 1.41421356237309504880;
+  constexpr int CH = 8;
+  double y[NV];
+  if constexpr (NV <= CH) {
+    ftanh_n<NV, ACC, true>(z, y, exp_tab());
+  } else {
+    ftanh_n<CH, ACC, true>(z, y, exp_tab());
+    ftanh_n<NV - CH, ACC, true>(z + CH, y + CH, exp_tab());
+    static_assert(NV <= 2 * CH, "tanh_res: at most 16 values");
+  }
+#ifdef __CUDACC__
+#pragma unroll
+#endif
+  for (int i = 0; i < NV; ++i) out[i] = fma(y[i], -kSqrt2, fma(h[i], kInvSqrt2, kInvSqrt2));
+#endif
+}
+template <int NV, int ACC, bool L, int ND>
+AQ_HD void tanh_res(const Jet<L, ND>* __restrict__ z, const Jet<L, ND>* h, Jet<L, ND>* out) {
+  for (int i = 0; i < NV; ++i) out[i] = (h[i] + s_tanh(z[i])) * kInvSqrt2;
+}
 
 struct cplx { double re, im; };
 AQ_HD cplx cmul(cplx a, cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
@@ -343,20 +376,15 @@ struct Psi {
     S mdf = sum_df * (1.0 / (12.0 * A)), msp = sum_sp * (1.0 / (4.0 * A));
     for (int m = 0; m < 6; ++m) z[m] = z[m] + mdf * W0[(4 * A) * 6 + m] + msp * W0[(4 * A + 1) * 6 + m];
     if (A == 1) { y0keep[4] = mdf; y0keep[5] = msp; }
-    {
-      S t[6];
-      tanhv<6, ACC>(z, t);
-      for (int m = 0; m < 6; ++m) y[m] = (A == 1) ? (y0keep[m] + t[m]) * kInvSqrt2 : t[m];   // residual only if 4A+2 == 6 (quirk Q5)
-    }
+    if (A == 1) tanh_res<6, ACC>(z, y0keep, y);                      // residual only if 4A+2 == 6 (quirk Q5)
+    else tanhv<6, ACC>(z, y);
     for (int l = 1; l < 3; ++l) {
       const double* W = P + L.yn_w[l];
       S zz[6];
       for (int m = 0; m < 6; ++m) zz[m] = Op::cst(P[L.yn_b[l] + m]);
       for (int q = 0; q < 6; ++q)
         for (int m = 0; m < 6; ++m) zz[m] = zz[m] + y[q] * W[q * 6 + m];
-      S t[6];
-      tanhv<6, ACC>(zz, t);
-      for (int m = 0; m < 6; ++m) y[m] = (y[m] + t[m]) * kInvSqrt2;
+      tanh_res<6, ACC>(zz, y, y);
     }
   }
 
@@ -379,9 +407,7 @@ struct Psi {
       for (int m = 0; m < 4; ++m) z[m] = Op::cst(P[L.dbl_b[l] + m]);
       for (int q = 0; q < 4; ++q)
         for (int m = 0; m < 4; ++m) z[m] = z[m] + in[q] * W[q * 4 + m];
-      S t[4];
-      tanhv<4, ACC>(z, t);
-      for (int m = 0; m < 4; ++m) out[m] = (in[m] + t[m]) * kInvSqrt2;
+      tanh_res<4, ACC>(z, in, out);
       in = h1;
       out = h2;
     }
@@ -416,9 +442,8 @@ struct Psi {
       for (int q = 0; q < Q; ++q) rec[q * rec_stride] = Op::val(t[q]);   // first-stage tanh outputs (deriv_split.cuh)
     for (int q = 0; q < Q; ++q)
       for (int m = 0; m < 4; ++m) z[m] = z[m] + t[q] * sw[q * 4 + m];
-    S tz[4];
-    tanhv<4, ACC>(z, tz);
-    for (int m = 0; m < 4; ++m) hout[m] = (DIN == 4) ? (hk[m] + tz[m]) * kInvSqrt2 : tz[m];   // residual only if shapes match (Q5)
+    if (DIN == 4) tanh_res<4, ACC>(z, hk, hout);                     // residual only if shapes match (Q5)
+    else tanhv<4, ACC>(z, hout);
   }
 
   // ---- complex LU (value only): log|det| and phase; destroys m
