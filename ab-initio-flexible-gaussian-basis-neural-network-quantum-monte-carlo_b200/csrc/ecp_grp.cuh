@@ -66,6 +66,12 @@ struct StaticFor {
 #ifndef AIQMC_GRP_MINB
 #define AIQMC_GRP_MINB 2
 #endif
+#ifndef AIQMC_GRP_FLAT
+#define AIQMC_GRP_FLAT 1
+#endif
+#ifndef AIQMC_GRP_PIVW
+#define AIQMC_GRP_PIVW 0       // 1: per-warp interleaved pivot buffers (see GrpCfg); A/B on N2: 132.3 ms either way
+#endif
 #ifndef AIQMC_GRP_WARPS
 #define AIQMC_GRP_WARPS 0      // 0 = pick per system
 #endif
@@ -102,12 +108,28 @@ struct GrpCfg {
     if (pc * LSTR > kLocalBudget) pc = (kLocalBudget / LSTR) / NG * NG;
     return pc < NG ? NG : pc;
   }
-  static constexpr int PC = pc_raw();                      // points per chunk
+  // Flat mode (N <= 16): the point loop runs over ALL (electron, atom, point) triples of the walker in chunks of 4 NG
+  // points, with row i of the pair-chain cache staged for every i at once.  Per electron the N2 loop had 100 points on
+  // 36 groups (3 passes, the last one 78 % full, three CTA barriers per electron); flat it is 1000 points in 7 chunks
+  // of 144 (99 % full).  Beyond N = 16 a row set would not fit next to the point records and PW is large anyway.
+  static constexpr bool kFlat = (AIQMC_GRP_FLAT != 0) && NE <= 16;
+  static constexpr int kRows = kFlat ? NE : 1;             // rows i of the cache staged at a time
+  static constexpr int PC = kFlat ? 4 * NG : pc_raw();     // points per chunk
+  static constexpr int ETOT = NE * PW;                     // points per walker
   static constexpr int oPIV = (9 * NE + 18 + 8 * NA + 1) & ~1;            // pivot-row buffers inside the group scratch (16 B aligned)
   // per-group scratch doubles; the stride between the groups of a warp continues the 9-double row stride of red_in
   // across groups (SCR = 9 N mod 16, kept even for the double2 pivot rows), so that the GPW * N lanes of a warp spread
   // evenly over the banks: with the unpadded 164 doubles at N = 10 groups 0 and 1 shared 6 of their 10 bank pairs
-  static constexpr int kScrRaw = oPIV + 4 * NE;
+  // Pivot rows live in a per-WARP buffer [2][N][GS] of (re, im) with the warp's groups interleaved (GS = GPW rounded up
+  // to a power of two): element j of all groups shares one 16*GS-byte segment of a 128-byte line, so the broadcast read
+  // of a pivot element by the whole warp and the write of it by one lane per group are single wavefronts (per-group
+  // buffers put the 3 groups of N2 in 3 different lines: 2 wavefronts per read, 3 per write; the elimination was 44 %
+  // of the kernel's shared-memory wavefronts).  Measured: no effect on the run time (N2 quadrature 132.3 ms either way),
+  // so the per-group buffers (less shared memory) stay the default.
+  static constexpr bool kPivW = (AIQMC_GRP_PIVW != 0) && GPW > 1;
+  static constexpr int GS = !kPivW ? 1 : (GPW <= 2 ? 2 : (GPW <= 4 ? 4 : 8));
+  static constexpr int kPivWarp = kPivW ? 4 * NE * GS : 0;                  // doubles per warp
+  static constexpr int kScrRaw = oPIV + (kPivW ? 0 : 4 * NE);
   static constexpr int kScrWant = ((9 * NE) % 16) & ~1;
   static constexpr int SCR = kScrRaw + ((kScrWant - kScrRaw % 16) + 16) % 16;
   // shared-memory carve-up (doubles)
@@ -120,13 +142,14 @@ struct GrpCfg {
   static constexpr int oG0M = oH0T + 4 * NA * NE;          // [8A]
   static constexpr int oY = oG0M + 8 * NA;                 // [N][6]
   static constexpr int oENV = oY + 6 * NE, oJAE = oENV + NE, oJEE = oJAE + NE, oMISC = oJEE + NE;
-  static constexpr int oHP = oMISC + 4;                    // [3][N][4] row i of the pair-chain cache
-  static constexpr int oJA = oHP + 12 * NE, oJC = oJA + NE;
-  static constexpr int oX = oJC + NE;                      // [3N]
+  static constexpr int oHP = oMISC + 4;                    // [kRows][3][4][N] row(s) i of the pair-chain cache
+  static constexpr int oJA = oHP + 12 * NE * kRows, oJC = oJA + NE * kRows;     // [kRows][N] each
+  static constexpr int oX = oJC + NE * kRows;              // [3N]
   static constexpr int oL = (oX + 3 * NE + 1) & ~1;        // [PC][LSTR]
   static constexpr int oACC = oL + PC * LSTR;              // [PC][2]
   static constexpr int oSCR = oACC + 2 * PC;               // [NG][SCR]
-  static constexpr int kDoubles = oSCR + NG * SCR;
+  static constexpr int oPIVW = (oSCR + NG * SCR + 15) & ~15;        // [W][2][N][GS][2], 128-byte aligned
+  static constexpr int kDoubles = oPIVW + W * kPivWarp;
   static constexpr int kBytes = kDoubles * 8;
   static constexpr int cw(int l) { return l == 0 ? oCW0 : (l == 1 ? oCW1 : oCW2); }
   static constexpr int cb(int l) { return l == 0 ? oCB0 : (l == 1 ? oCB1 : oCB2); }
@@ -194,7 +217,7 @@ struct LuState {
 };
 constexpr int kLuSeg = 6;
 
-template <int NE, int WD>
+template <int NE, int WD, int GS>
 __device__ __forceinline__ void lu_step(LuState& st, double (&rre)[NE], double (&rim)[NE], double2* __restrict__ pivb,
                                         int k, unsigned mask) {
   const double m2 = rre[0] * rre[0] + rim[0] * rim[0];
@@ -202,10 +225,10 @@ __device__ __forceinline__ void lu_step(LuState& st, double (&rre)[NE], double (
   const unsigned key = st.used ? 0u : (((((unsigned)hi_word(m2)) >> 5) + 1u) << 5) | (31u - (unsigned)k);
   const unsigned kmax = __reduce_max_sync(mask, key);
   const unsigned best = 31u - (kmax & 31u);
-  double2* pb = pivb + st.parity_buf * NE;
+  double2* pb = pivb + st.parity_buf * NE * GS;               // element j of this group at pb[j * GS]
   st.parity_buf ^= 1;
   if ((unsigned)k == best) {
-    StaticFor<0, WD>::run([&](auto jc) { constexpr int j = decltype(jc)::value; pb[j] = make_double2(rre[j], rim[j]); });
+    StaticFor<0, WD>::run([&](auto jc) { constexpr int j = decltype(jc)::value; pb[j * GS] = make_double2(rre[j], rim[j]); });
     st.used = true;
   }
   __syncwarp();
@@ -227,25 +250,25 @@ __device__ __forceinline__ void lu_step(LuState& st, double (&rre)[NE], double (
   const cplx f = cmul(cplx{rre[0], rim[0]}, pinv);
   StaticFor<1, WD>::run([&](auto jc) {                      // finished rows compute garbage nobody reads
     constexpr int j = decltype(jc)::value;
-    const double2 pj = pb[j];
+    const double2 pj = pb[j * GS];
     rre[j - 1] = fma(f.im, pj.y, fma(-f.re, pj.x, rre[j]));        // 4 DFMA per complex update
     rim[j - 1] = fma(-f.im, pj.x, fma(-f.re, pj.y, rim[j]));
   });
   rre[WD - 1] = 0.0; rim[WD - 1] = 0.0;
 }
 
-template <int NE, int C0>
+template <int NE, int C0, int GS>
 __device__ __forceinline__ void lu_run(LuState& st, double (&rre)[NE], double (&rim)[NE], double2* __restrict__ pivb,
                                        int k, unsigned mask) {
   if constexpr (C0 < NE) {
     if constexpr (NE <= 16) {
-      lu_step<NE, NE - C0>(st, rre, rim, pivb, k, mask);
-      lu_run<NE, C0 + 1>(st, rre, rim, pivb, k, mask);
+      lu_step<NE, NE - C0, GS>(st, rre, rim, pivb, k, mask);
+      lu_run<NE, C0 + 1, GS>(st, rre, rim, pivb, k, mask);
     } else {
       constexpr int WD = NE - C0, ST = WD < kLuSeg ? WD : kLuSeg;
 #pragma unroll 1
-      for (int s = 0; s < ST; ++s) lu_step<NE, WD>(st, rre, rim, pivb, k, mask);
-      lu_run<NE, C0 + ST>(st, rre, rim, pivb, k, mask);
+      for (int s = 0; s < ST; ++s) lu_step<NE, WD, GS>(st, rre, rim, pivb, k, mask);
+      lu_run<NE, C0 + ST, GS>(st, rre, rim, pivb, k, mask);
     }
   }
 }
@@ -316,32 +339,47 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
   double* red_in = scr;                                    // [N][9]
   double* red_out = scr + 9 * N;                           // [18]: up sums (9), down sums (9)
   double* g0 = red_out + 18;                               // [8A]
-  double2* pivb = reinterpret_cast<double2*>(scr + CF::oPIV);   // [2][N] (re, im)
+  double2* pivb = CF::kPivW ? reinterpret_cast<double2*>(smem + CF::oPIVW + warp * CF::kPivWarp) + g      // [2][N][GS] (re, im)
+                            : reinterpret_cast<double2*>(scr + CF::oPIV);                               // [2][N]
   __syncthreads();
   const double xk[3] = {smem[CF::oX + 3 * kk], smem[CF::oX + 3 * kk + 1], smem[CF::oX + 3 * kk + 2]};
   const double den_r = smem[CF::oMISC + 1], den_i = smem[CF::oMISC + 2];
   const double den_inv = 1.0 / (den_r * den_r + den_i * den_i);
   double acc_re = 0.0, acc_im = 0.0;                       // warp 0: fixed-order accumulation of the contributions
 
-#pragma unroll 1
-  for (int i = 0; i < N; ++i) {
-    const int si = i < n_up ? 0 : 1;
-    // row i of the pair-chain cache and the (i,k) Jastrow parameters
+  // stage row `i` of the pair-chain cache and the (i,k) Jastrow parameters into row slot `slot`
+  auto stage_row = [&](int i, int slot) {
     for (int t = tid; t < 12 * N; t += CF::T) {           // HP[l][i][k][c] -> [l][c][k]
       const int l = t / (4 * N), r = t - l * 4 * N, kq = r >> 2, c = r & 3;
-      smem[CF::oHP + (l * 4 + c) * N + kq] = cache[MC::HP + (l * N + i) * N * 4 + r];
+      smem[CF::oHP + slot * 12 * N + (l * 4 + c) * N + kq] = cache[MC::HP + (l * N + i) * N * 4 + r];
     }
     for (int t = tid; t < N; t += CF::T) {
       const int lo = i < t ? i : t, hi = i < t ? t : i;
-      smem[CF::oJA + t] = params[L.jas_alpha + lo * N + hi];
-      smem[CF::oJC + t] = (t == i) ? 0.0 : params[L.jas_cusp + lo * N + hi];
+      smem[CF::oJA + slot * N + t] = params[L.jas_alpha + lo * N + hi];
+      smem[CF::oJC + slot * N + t] = (t == i) ? 0.0 : params[L.jas_cusp + lo * N + hi];
     }
+  };
+  if constexpr (CF::kFlat)
+    for (int i = 0; i < N; ++i) stage_row(i, i);          // published by the barrier after the first phase 0
+
+  constexpr int kChunksPerI = (PW + PC - 1) / PC;         // non-flat: chunks never straddle electrons
+  constexpr int kChunks = CF::kFlat ? (CF::ETOT + PC - 1) / PC : N * kChunksPerI;
 #pragma unroll 1
-    for (int c0 = 0; c0 < PW; c0 += PC) {
-      const int npt = (PW - c0 < PC) ? PW - c0 : PC;
+  for (int ch = 0; ch < kChunks; ++ch) {
+    int e0, npt;
+    if constexpr (CF::kFlat) {
+      e0 = ch * PC;
+      npt = (CF::ETOT - e0 < PC) ? CF::ETOT - e0 : PC;
+    } else {
+      const int iu = ch / kChunksPerI, c0 = (ch - iu * kChunksPerI) * PC;
+      e0 = iu * PW + c0;
+      npt = (PW - c0 < PC) ? PW - c0 : PC;
+      if (c0 == 0) stage_row(iu, 0);                      // the previous electron's readers passed the chunk-end barrier
+    }
+    {
       // ---- phase 0: thread per point -- rotated point, cos(theta) (quirks Q13, Q14), electron i's local part
       for (int t = tid; t < npt; t += CF::T) {
-        const int e = c0 + t, a = e / AIQMC_NQUAD, p = e - a * AIQMC_NQUAD;
+        const int e = e0 + t, i = e / PW, ew = e - i * PW, a = ew / AIQMC_NQUAD, p = ew - a * AIQMC_NQUAD;
         double* Lp = smem + CF::oL + t * LSTR;
         double ae[3], xn[3];
 #pragma unroll
@@ -370,7 +408,6 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
       __syncthreads();
 
       // ---- main phase: one group per point, lane = electron
-      const bool diag = act && (k == i);
 #pragma unroll 1
       for (int it = 0;; ++it) {
         const int t0 = warp * GPW + it * NG;
@@ -385,6 +422,12 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
         }
         const bool valid = t0 + g < npt;
         const int t = valid ? t0 + g : npt - 1;
+        const int i = (e0 + t) / PW;                                      // the point's displaced electron (group-uniform)
+        const int si = i < n_up ? 0 : 1;
+        const bool diag = act && (k == i);
+        const double* hp_i = smem + CF::oHP + (CF::kFlat ? i : 0) * 12 * N;   // row i of the pair-chain cache [3][4][N]
+        const double* ja_i = smem + CF::oJA + (CF::kFlat ? i : 0) * N;
+        const double* jc_i = smem + CF::oJC + (CF::kFlat ? i : 0) * N;
         const double* Lp = smem + CF::oL + t * LSTR;
         // level-0 pair features through i: row (i,k): d = x_k - x_i', column (k,i): -d; e-e Jastrow term
         double cr[4], cc[4], h[4];
@@ -398,7 +441,7 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
           cr[0] = rik; cc[0] = rik;
 #pragma unroll
           for (int c = 0; c < 3; ++c) { cr[1 + c] = d[c]; cc[1 + c] = -d[c]; }
-          ju = smem[CF::oJC + kk] * rik * s_inv(1.0 + smem[CF::oJA + kk] * rik);     // 0 on the diagonal
+          ju = jc_i[kk] * rik * s_inv(1.0 + ja_i[kk] * rik);     // 0 on the diagonal
         }
         double jee_tot = 0.0;
 #pragma unroll
@@ -407,7 +450,7 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
           if (act) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              red_in[k * 9 + c] = diag ? smem[CF::oHP + (l * 4 + c) * N + k] : cc[c];   // G'_l[s][i] terms
+              red_in[k * 9 + c] = diag ? hp_i[(l * 4 + c) * N + k] : cc[c];   // G'_l[s][i] terms
               if (l > 0) red_in[k * 9 + 4 + c] = h[c];
             }
             if (l == 0) {
@@ -440,7 +483,7 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             double gu = smem[CF::oGS + ((l * 2 + 0) * 4 + c) * N + kk], gd = smem[CF::oGS + ((l * 2 + 1) * 4 + c) * N + kk];
-            const double delta = cr[c] - smem[CF::oHP + (l * 4 + c) * N + kk];
+            const double delta = cr[c] - hp_i[(l * 4 + c) * N + kk];
             if (si == 0) gu += delta; else gd += delta;
             Gu[c] = (diag ? red_out[c] : gu) * inv_n[0];
             Gd[c] = (diag ? red_out[9 + c] : gd) * inv_n[1];
@@ -522,7 +565,7 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
         lu.unused = N >= 32 ? 0xffffffffu : ((1u << N) - 1u);
         lu.par = 0; lu.ex = 0; lu.parity_buf = 0;
         lu.prod = {1.0, 0.0};
-        lu_run<NE, 0>(lu, rre, rim, pivb, k, GPW == 1 ? 0xffffffffu : gmask);
+        lu_run<NE, 0, CF::GS>(lu, rre, rim, pivb, k, GPW == 1 ? 0xffffffffu : gmask);
         int par = lu.par, ex = lu.ex;
         cplx prod = lu.prod;
         if (valid && act && k == 0) {
@@ -544,7 +587,7 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
         const double pr = Lp[0], pi = Lp[1];
         const double la = 0.5 * log(pr * pr + pi * pi) + Lp[2] * 0.69314718055994530942 + smem[CF::oMISC + 0] + Lp[10];
         const double pha = atan2(pi, pr);
-        const int e = c0 + t, a = e / AIQMC_NQUAD, p = e - a * AIQMC_NQUAD;
+        const int e = e0 + t, i = e / PW, ew = e - i * PW, a = ew / AIQMC_NQUAD, p = ew - a * AIQMC_NQUAD;
         const double wq = c_ecp.quad_wts[p] * den_inv;
         const double rr = (la * den_r + pha * den_i) * wq, ri = (pha * den_r - la * den_i) * wq;
         const double v0 = Lp[4], v1 = Lp[5], v2 = Lp[6], v3 = Lp[7], cs = Lp[3];
