@@ -366,20 +366,22 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
   constexpr int kChunks = CF::kFlat ? (CF::ETOT + PC - 1) / PC : N * kChunksPerI;
 #pragma unroll 1
   for (int ch = 0; ch < kChunks; ++ch) {
-    int e0, npt;
+    int e0, npt, iu = 0, c0u = 0;                          // non-flat: the chunk's electron (CTA-uniform) and offset
     if constexpr (CF::kFlat) {
       e0 = ch * PC;
       npt = (CF::ETOT - e0 < PC) ? CF::ETOT - e0 : PC;
     } else {
-      const int iu = ch / kChunksPerI, c0 = (ch - iu * kChunksPerI) * PC;
-      e0 = iu * PW + c0;
-      npt = (PW - c0 < PC) ? PW - c0 : PC;
-      if (c0 == 0) stage_row(iu, 0);                      // the previous electron's readers passed the chunk-end barrier
+      iu = ch / kChunksPerI;
+      c0u = (ch - iu * kChunksPerI) * PC;
+      e0 = iu * PW + c0u;
+      npt = (PW - c0u < PC) ? PW - c0u : PC;
+      if (c0u == 0) stage_row(iu, 0);                     // the previous electron's readers passed the chunk-end barrier
     }
     {
       // ---- phase 0: thread per point -- rotated point, cos(theta) (quirks Q13, Q14), electron i's local part
       for (int t = tid; t < npt; t += CF::T) {
-        const int e = e0 + t, i = e / PW, ew = e - i * PW, a = ew / AIQMC_NQUAD, p = ew - a * AIQMC_NQUAD;
+        const int i = CF::kFlat ? (e0 + t) / PW : iu, ew = CF::kFlat ? e0 + t - i * PW : c0u + t;
+        const int a = ew / AIQMC_NQUAD, p = ew - a * AIQMC_NQUAD;
         double* Lp = smem + CF::oL + t * LSTR;
         double ae[3], xn[3];
 #pragma unroll
@@ -408,6 +410,8 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
       __syncthreads();
 
       // ---- main phase: one group per point, lane = electron
+      const bool diag_u = act && (k == iu);               // non-flat: the chunk's electron is CTA-uniform
+      const int si_u = iu < n_up ? 0 : 1;
 #pragma unroll 1
       for (int it = 0;; ++it) {
         const int t0 = warp * GPW + it * NG;
@@ -422,12 +426,13 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
         }
         const bool valid = t0 + g < npt;
         const int t = valid ? t0 + g : npt - 1;
-        const int i = (e0 + t) / PW;                                      // the point's displaced electron (group-uniform)
-        const int si = i < n_up ? 0 : 1;
-        const bool diag = act && (k == i);
-        const double* hp_i = smem + CF::oHP + (CF::kFlat ? i : 0) * 12 * N;   // row i of the pair-chain cache [3][4][N]
-        const double* ja_i = smem + CF::oJA + (CF::kFlat ? i : 0) * N;
-        const double* jc_i = smem + CF::oJC + (CF::kFlat ? i : 0) * N;
+        const int i = CF::kFlat ? (e0 + t) / PW : iu;                     // the point's displaced electron (group-uniform)
+        const int si = CF::kFlat ? (i < n_up ? 0 : 1) : si_u;
+        const bool diag = CF::kFlat ? (act && (k == i)) : diag_u;
+        const int row_off = CF::kFlat ? i : 0;                            // row i of the pair-chain cache [3][4][N]
+#define AQ_HP_I(idx) smem[CF::oHP + row_off * 12 * N + (idx)]
+#define AQ_JA_I(idx) smem[CF::oJA + row_off * N + (idx)]
+#define AQ_JC_I(idx) smem[CF::oJC + row_off * N + (idx)]
         const double* Lp = smem + CF::oL + t * LSTR;
         // level-0 pair features through i: row (i,k): d = x_k - x_i', column (k,i): -d; e-e Jastrow term
         double cr[4], cc[4], h[4];
@@ -441,7 +446,7 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
           cr[0] = rik; cc[0] = rik;
 #pragma unroll
           for (int c = 0; c < 3; ++c) { cr[1 + c] = d[c]; cc[1 + c] = -d[c]; }
-          ju = jc_i[kk] * rik * s_inv(1.0 + ja_i[kk] * rik);     // 0 on the diagonal
+          ju = AQ_JC_I(kk) * rik * s_inv(1.0 + AQ_JA_I(kk) * rik);     // 0 on the diagonal
         }
         double jee_tot = 0.0;
 #pragma unroll
@@ -450,7 +455,7 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
           if (act) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              red_in[k * 9 + c] = diag ? hp_i[(l * 4 + c) * N + k] : cc[c];   // G'_l[s][i] terms
+              red_in[k * 9 + c] = diag ? AQ_HP_I((l * 4 + c) * N + k) : cc[c];   // G'_l[s][i] terms
               if (l > 0) red_in[k * 9 + 4 + c] = h[c];
             }
             if (l == 0) {
@@ -483,7 +488,7 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             double gu = smem[CF::oGS + ((l * 2 + 0) * 4 + c) * N + kk], gd = smem[CF::oGS + ((l * 2 + 1) * 4 + c) * N + kk];
-            const double delta = cr[c] - hp_i[(l * 4 + c) * N + kk];
+            const double delta = cr[c] - AQ_HP_I((l * 4 + c) * N + kk);
             if (si == 0) gu += delta; else gd += delta;
             Gu[c] = (diag ? red_out[c] : gu) * inv_n[0];
             Gd[c] = (diag ? red_out[9 + c] : gd) * inv_n[1];
@@ -587,7 +592,335 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
         const double pr = Lp[0], pi = Lp[1];
         const double la = 0.5 * log(pr * pr + pi * pi) + Lp[2] * 0.69314718055994530942 + smem[CF::oMISC + 0] + Lp[10];
         const double pha = atan2(pi, pr);
-        const int e = e0 + t, i = e / PW, ew = e - i * PW, a = ew / AIQMC_NQUAD, p = ew - a * AIQMC_NQUAD;
+        const int i = CF::kFlat ? (e0 + t) / PW : iu, ew = CF::kFlat ? e0 + t - i * PW : c0u + t;
+        const int a = ew / AIQMC_NQUAD, p = ew - a * AIQMC_NQUAD;
+        const double wq = c_ecp.quad_wts[p] * den_inv;
+        const double rr = (la * den_r + pha * den_i) * wq, ri = (pha * den_r - la * den_i) * wq;
+        const double v0 = Lp[4], v1 = Lp[5], v2 = Lp[6], v3 = Lp[7], cs = Lp[3];
+        const double k4 = 0.07957747154594767;   // 1/(4 pi)
+        const double f = v0 * k4 + v1 * (3.0 * k4 * cs) + v2 * (2.5 * k4 * (3.0 * cs * cs - 1.0)) +
+                         v3 * (3.5 * k4 * (5.0 * cs * cs * cs - 3.0 * cs));
+        smem[CF::oACC + 2 * t] = f * rr;
+        smem[CF::oACC + 2 * t + 1] = f * ri;
+        if (tm_out) tmove_point_out(tm_out + (((b * N + i) * A + a) * AIQMC_NQUAD + p) * 4, v0, v1, v2, v3, cs, rr, ri, tm_tau);
+      }
+      __syncthreads();                                   // the records are rewritten by the next chunk's phase 0
+      if (warp == 0 && !tm_out) {
+#pragma unroll 1
+        for (int q = lane; q < npt; q += 32) { acc_re += smem[CF::oACC + 2 * q]; acc_im += smem[CF::oACC + 2 * q + 1]; }
+      }
+    }
+  }
+  if (warp == 0 && !tm_out) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      acc_re += __shfl_xor_sync(0xffffffffu, acc_re, o);
+      acc_im += __shfl_xor_sync(0xffffffffu, acc_im, o);
+    }
+    if (lane == 0) { w.epp[2 * b] = acc_re; w.epp[2 * b + 1] = acc_im; }
+  }
+}
+
+// ---- N > 16 (C6H6): the per-electron form of the point loop -- electron i's cache row staged, its A * 50 points walked in
+//      chunks, next electron.  The flat loop above is the same arithmetic; this copy is kept because the 70 kB loop body
+//      of N = 30 is fetch-bound and lost 3.5 % (849 -> 880 ms per 2,368 walkers) when it was compiled through the
+//      generalised loop nest, for no gain (600 points per electron already fill the 12 groups evenly).
+template <int NE, int NA>
+__global__ void __launch_bounds__((GrpCfg<NE, NA>::T), (NE <= 16 ? AIQMC_GRP_MINB : 1))
+k_ecp_grp_rows(AiqmcSystem sys, const double* __restrict__ params, const double* __restrict__ pos,
+          const double* __restrict__ rot, int64_t B, const double* __restrict__ cache_all, EnergyWs w,
+          double* __restrict__ tm_out, double tm_tau) {
+  using CF = GrpCfg<NE, NA>;
+  using MC = MoveCache<NE, NA>;
+  using U = UniLayout<NE, NA>;
+  constexpr int N = NE, A = NA, GPW = CF::GPW, NG = CF::NG, PW = CF::PW, PC = CF::PC, LSTR = CF::LSTR;
+  constexpr LayoutC<NE, NA> L{};
+  extern __shared__ __align__(16) double smem_grp[];
+  double* const smem = smem_grp;
+  const int tid = threadIdx.x;
+  const int64_t b = blockIdx.x;
+  const double* cache = cache_all + b * MC::SIZE;
+
+  // ---- stage the walker-constant data
+  for (int l = 0; l < 3; ++l) {
+    const int dtot = l == 0 ? CF::D0 : 20, q = dtot / 4;
+    for (int t = tid; t < dtot * N; t += CF::T) {         // conv_w[l][k][idx] -> [idx][k]
+      const int kk = t / dtot, idx = t - kk * dtot;
+      smem[CF::cw(l) + idx * N + kk] = params[L.conv_w[l] + t];
+    }
+    for (int t = tid; t < q * N; t += CF::T) {
+      const int kk = t / q, qq = t - kk * q;
+      smem[CF::cb(l) + qq * N + kk] = params[L.conv_b[l] + t];
+    }
+  }
+  for (int t = tid; t < 20 * N; t += CF::T) smem[CF::oOW + t] = params[L.orb_w[0] + t];
+  // per-lane rows are stored lane-contiguous ([component][electron]): lane k of a group reads element k, so a group's
+  // access is one contiguous run of N doubles (the [electron][4] layout of the cache put lanes k and k+4 on the same
+  // banks: 16 % of the kernel's excess shared-memory wavefronts in the round-2 ncu source page)
+  for (int t = tid; t < 24 * N; t += CF::T) {             // GS[l][s][j][c] -> [l][s][c][j]
+    const int ls = t / (4 * N), r = t - ls * 4 * N, j = r >> 2, c = r & 3;
+    smem[CF::oGS + (ls * 4 + c) * N + j] = cache[MC::GS + t];
+  }
+  for (int t = tid; t < 4 * A * N; t += CF::T) {          // H0[k][q] -> [q][k]
+    const int kk = t / (4 * A), q = t - kk * 4 * A;
+    smem[CF::oH0T + q * N + kk] = cache[MC::H0 + t];
+  }
+  for (int t = tid; t < 8 * A + 9 * N + 4; t += CF::T) {   // G0M Y ENV JAE JEE MISC; Y[k][m] -> [m][k]
+    const int ty = t - 8 * A;
+    if (ty >= 0 && ty < 6 * N) smem[CF::oY + (ty % 6) * N + ty / 6] = cache[MC::G0M + t];
+    else smem[CF::oG0M + t] = cache[MC::G0M + t];
+  }
+  for (int t = tid; t < 3 * N; t += CF::T) smem[CF::oX + t] = pos[b * 3 * N + t];
+  if (tid < kExpTab) g_exp_tab[tid] = exp2((double)tid * (1.0 / kExpTab));
+  if (kAcc == 1 && AIQMC_TANH_TAB64) fill_tanh_table(tid, (int)blockDim.x);
+
+  // ---- lane roles
+  const int lane = tid & 31, warp = tid >> 5;
+  const bool idle = lane >= GPW * N;
+  const int g = idle ? GPW - 1 : lane / N;                 // group within the warp
+  const int k = idle ? N + (lane - GPW * N) : lane - g * N;
+  const bool act = !idle;
+  const int kk = act ? k : N - 1;
+  unsigned gmask = (N >= 32 ? 0xffffffffu : ((1u << N) - 1u)) << (g * N);
+  if (g == GPW - 1 && GPW * N < 32) gmask |= ~((GPW * N >= 32) ? 0xffffffffu : ((1u << (GPW * N)) - 1u));
+  const int n_up = sys.n_up;
+  const double inv_n[2] = {1.0 / sys.n_up, 1.0 / sys.n_dn};
+  const int sig = sys.sigma[kk];
+  const int srow = kk < sys.n_up_rows ? 0 : 1;
+  double* scr = smem + CF::oSCR + (warp * GPW + g) * CF::SCR;
+  double* red_in = scr;                                    // [N][9]
+  double* red_out = scr + 9 * N;                           // [18]: up sums (9), down sums (9)
+  double* g0 = red_out + 18;                               // [8A]
+  double2* pivb = CF::kPivW ? reinterpret_cast<double2*>(smem + CF::oPIVW + warp * CF::kPivWarp) + g      // [2][N][GS] (re, im)
+                            : reinterpret_cast<double2*>(scr + CF::oPIV);                               // [2][N]
+  __syncthreads();
+  const double xk[3] = {smem[CF::oX + 3 * kk], smem[CF::oX + 3 * kk + 1], smem[CF::oX + 3 * kk + 2]};
+  const double den_r = smem[CF::oMISC + 1], den_i = smem[CF::oMISC + 2];
+  const double den_inv = 1.0 / (den_r * den_r + den_i * den_i);
+  double acc_re = 0.0, acc_im = 0.0;                       // warp 0: fixed-order accumulation of the contributions
+
+#pragma unroll 1
+  for (int i = 0; i < N; ++i) {
+    const int si = i < n_up ? 0 : 1;
+    // row i of the pair-chain cache and the (i,k) Jastrow parameters
+    for (int t = tid; t < 12 * N; t += CF::T) {           // HP[l][i][k][c] -> [l][c][k]
+      const int l = t / (4 * N), r = t - l * 4 * N, kq = r >> 2, c = r & 3;
+      smem[CF::oHP + (l * 4 + c) * N + kq] = cache[MC::HP + (l * N + i) * N * 4 + r];
+    }
+    for (int t = tid; t < N; t += CF::T) {
+      const int lo = i < t ? i : t, hi = i < t ? t : i;
+      smem[CF::oJA + t] = params[L.jas_alpha + lo * N + hi];
+      smem[CF::oJC + t] = (t == i) ? 0.0 : params[L.jas_cusp + lo * N + hi];
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < PW; c0 += PC) {
+      const int npt = (PW - c0 < PC) ? PW - c0 : PC;
+      // ---- phase 0: thread per point -- rotated point, cos(theta) (quirks Q13, Q14), electron i's local part
+      for (int t = tid; t < npt; t += CF::T) {
+        const int e = c0 + t, a = e / AIQMC_NQUAD, p = e - a * AIQMC_NQUAD;
+        double* Lp = smem + CF::oL + t * LSTR;
+        double ae[3], xn[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) ae[c] = smem[CF::oX + 3 * i + c] - params[L.atoms + 3 * a + c];
+        const double r = sqrt(ae[0] * ae[0] + ae[1] * ae[1] + ae[2] * ae[2]);
+        double dot = 0.0;
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+          const double nh = c_ecp.quad_pts[p][0] * rot[b * 9 + l] + c_ecp.quad_pts[p][1] * rot[b * 9 + 3 + l] +
+                            c_ecp.quad_pts[p][2] * rot[b * 9 + 6 + l];
+          xn[l] = r * nh;
+          dot += ae[l] * xn[l];
+        }
+        const double cs = dot / (r * (r * w.gnorm[4 * b + quad_group(p)]));
+        double h0n[4 * A], yn[6], envn, jaen;
+        Psi<NE, NA>::template electron_local<double, kAcc>(params, i, xn, h0n, yn, envn, jaen);
+        const double* vl = w.vl + ((b * N + i) * A + a) * 4;
+        Lp[0] = xn[0]; Lp[1] = xn[1]; Lp[2] = xn[2]; Lp[3] = cs;
+        Lp[4] = vl[0]; Lp[5] = vl[1]; Lp[6] = vl[2]; Lp[7] = vl[3];
+        Lp[8] = envn; Lp[9] = jaen;
+#pragma unroll
+        for (int m = 0; m < 6; ++m) Lp[10 + m] = yn[m];
+#pragma unroll
+        for (int q = 0; q < 4 * A; ++q) Lp[16 + q] = h0n[q];
+      }
+      __syncthreads();
+
+      // ---- main phase: one group per point, lane = electron
+      const bool diag = act && (k == i);
+#pragma unroll 1
+      for (int it = 0;; ++it) {
+        const int t0 = warp * GPW + it * NG;
+        constexpr bool kAlign = AIQMC_GRP_ALIGN < 0 ? (NE > 16) : (AIQMC_GRP_ALIGN != 0);
+        if constexpr (kAlign) {
+          // all warps of the CTA walk the (large, straight-line) loop body together so that they share instruction
+          // fetches; warps past the end of the chunk run a dummy pass instead of leaving early
+          if (it * NG >= npt) break;                                      // CTA-uniform
+          __syncthreads();
+        } else {
+          if (t0 >= npt) break;                                           // warp-uniform
+        }
+        const bool valid = t0 + g < npt;
+        const int t = valid ? t0 + g : npt - 1;
+        const double* Lp = smem + CF::oL + t * LSTR;
+        // level-0 pair features through i: row (i,k): d = x_k - x_i', column (k,i): -d; e-e Jastrow term
+        double cr[4], cc[4], h[4];
+        double ju;
+        {
+          double d[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) d[c] = diag ? 0.0 : xk[c] - Lp[c];
+          const double r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+          const double rik = diag ? 0.0 : r2 * s_rsqrt(diag ? 1.0 : r2);
+          cr[0] = rik; cc[0] = rik;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { cr[1 + c] = d[c]; cc[1 + c] = -d[c]; }
+          ju = smem[CF::oJC + kk] * rik * s_inv(1.0 + smem[CF::oJA + kk] * rik);     // 0 on the diagonal
+        }
+        double jee_tot = 0.0;
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+          // ---- deposit the terms of the block sums
+          if (act) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              red_in[k * 9 + c] = diag ? smem[CF::oHP + (l * 4 + c) * N + k] : cc[c];   // G'_l[s][i] terms
+              if (l > 0) red_in[k * 9 + 4 + c] = h[c];
+            }
+            if (l == 0) {
+              red_in[k * 9 + 8] = ju;
+              for (int q = k; q < 8 * A; q += N) {                       // block means of the layer-0 features
+                const int s = q >= 4 * A, qq = q - s * 4 * A;
+                const double dh = Lp[16 + qq] - smem[CF::oH0T + qq * N + i];
+                g0[q] = smem[CF::oG0M + q] + (s == si ? dh * inv_n[s] : 0.0);
+              }
+            }
+          }
+          __syncwarp();
+          if (act) {
+            constexpr int kCols = 9;
+            for (int col = k; col < (l == 0 ? kCols : 8); col += N) {
+              if (l == 0 && col >= 4 && col < 8) continue;               // no h sums before the first layer
+              double u = 0.0, dsum = 0.0;
+#pragma unroll
+              for (int q = 0; q < N; ++q) {                               // fixed order: deterministic
+                const double v = red_in[q * 9 + col];
+                u += q < n_up ? v : 0.0;
+                dsum += q < n_up ? 0.0 : v;
+              }
+              red_out[col] = u;
+              red_out[9 + col] = dsum;
+            }
+          }
+          __syncwarp();
+          double Gu[4], Gd[4], gm0[4], gm1[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            double gu = smem[CF::oGS + ((l * 2 + 0) * 4 + c) * N + kk], gd = smem[CF::oGS + ((l * 2 + 1) * 4 + c) * N + kk];
+            const double delta = cr[c] - smem[CF::oHP + (l * 4 + c) * N + kk];
+            if (si == 0) gu += delta; else gd += delta;
+            Gu[c] = (diag ? red_out[c] : gu) * inv_n[0];
+            Gd[c] = (diag ? red_out[9 + c] : gd) * inv_n[1];
+            if (l > 0) { gm0[c] = red_out[4 + c] * inv_n[0]; gm1[c] = red_out[13 + c] * inv_n[1]; }
+          }
+          if (l == 0) jee_tot = red_out[8] + red_out[17];
+          const double* cw = smem + CF::cw(l) + kk;
+          const double* cb = smem + CF::cb(l) + kk;
+          if (l == 0) {
+            const double* hp = diag ? Lp + 16 : smem + CF::oH0T + kk;
+            const int hstr = diag ? 1 : N;
+            auto in0 = [&](int idx) -> double {
+              return idx < 4 * A ? hp[idx * hstr] : idx < 12 * A ? g0[idx - 4 * A]
+                     : idx < 12 * A + 4 ? Gu[idx - 12 * A] : Gd[idx - 12 * A - 4];
+            };
+            grp_one_layer<NE, NA, 0, 4 * A>(cw, cb, in0, h);
+          } else {
+            auto inl = [&](int idx) -> double {
+              return idx < 4 ? h[idx] : idx < 8 ? gm0[idx - 4] : idx < 12 ? gm1[idx - 8] : idx < 16 ? Gu[idx - 12] : Gd[idx - 16];
+            };
+            double hn[4];
+            if (l == 1) grp_one_layer<NE, NA, 1, 4>(cw, cb, inl, hn);
+            else grp_one_layer<NE, NA, 2, 4>(cw, cb, inl, hn);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) h[c] = hn[c];
+          }
+          if (l < 2) {   // advance both pair chains through double-layer l (nn.py:305-309)
+            const int WO = l == 0 ? U::at(0, U::K.dbl_w[0]) : U::at(1, U::K.dbl_w[1]);
+            const int BO = l == 0 ? U::at(0, U::K.dbl_b[0]) : U::at(1, U::K.dbl_b[1]);
+            double z[8], tt[8];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) { z[m] = c_uni[BO + m]; z[4 + m] = z[m]; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+              for (int m = 0; m < 4; ++m) { z[m] += cr[q] * c_uni[WO + q * 4 + m]; z[4 + m] += cc[q] * c_uni[WO + q * 4 + m]; }
+#pragma unroll
+            for (int m = 0; m < 4; ++m) { tt[m] = cr[m]; tt[4 + m] = cc[m]; }
+            tanh_res<8, kAcc>(z, tt, tt);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) { cr[m] = tt[m]; cc[m] = tt[4 + m]; }
+          }
+        }
+
+        // ---- orbital-matrix row of lane k: reads h of electron sigma[k], envelope / Ynlm of electron k (quirk Q4)
+        if (act) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) red_in[k * 9 + 4 + c] = h[c];
+        }
+        __syncwarp();
+        double rre[N], rim[N];
+        {
+          double hs[4], yr[6];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) hs[c] = red_in[sig * 9 + 4 + c];
+#pragma unroll
+          for (int m = 0; m < 6; ++m) yr[m] = diag ? Lp[10 + m] : smem[CF::oY + m * N + kk];
+          const double envr = diag ? Lp[8] : smem[CF::oENV + kk];
+          const double* Wt = smem + CF::oOW + srow * 10 * N;
+          const double* Bv = Wt + 8 * N;
+          StaticFor<0, N>::run([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            const double2* W2 = reinterpret_cast<const double2*>(Wt);        // (re, im) pairs: one LDS.128 each
+            const double2 b2 = reinterpret_cast<const double2*>(Bv)[j];
+            double pre = b2.x, pim = b2.y;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { const double2 w2 = W2[c * N + j]; pre += hs[c] * w2.x; pim += hs[c] * w2.y; }
+            double yo = 0.0;
+#pragma unroll
+            for (int m = 0; m < 6; ++m) yo += yr[m] * c_uni[U::y_w + m * N + j];
+            const double evv = envr * yo;
+            rre[j] = pre * evv; rim[j] = pim * evv;
+          });
+        }
+
+        // ---- complex LU across the group's lanes with partial pivoting (lu_step / lu_run above)
+        LuState lu;
+        lu.used = !act;
+        lu.unused = N >= 32 ? 0xffffffffu : ((1u << N) - 1u);
+        lu.par = 0; lu.ex = 0; lu.parity_buf = 0;
+        lu.prod = {1.0, 0.0};
+        lu_run<NE, 0, CF::GS>(lu, rre, rim, pivb, k, GPW == 1 ? 0xffffffffu : gmask);
+        int par = lu.par, ex = lu.ex;
+        cplx prod = lu.prod;
+        if (valid && act && k == 0) {
+          // leave the determinant (mantissa product, exponent, parity) and the Jastrow change in the point's record;
+          // the log / atan2 / quadrature weight are applied by the thread-per-point epilogue below (one lane per
+          // point instead of a whole warp walking through libm for GPW results)
+          double* Lw = smem + CF::oL + t * LSTR;
+          Lw[0] = (par & 1) ? -prod.re : prod.re;
+          Lw[1] = (par & 1) ? -prod.im : prod.im;
+          Lw[2] = (double)ex;
+          Lw[10] = (jee_tot - smem[CF::oJEE + i]) + (Lp[9] - smem[CF::oJAE + i]);
+        }
+        __syncwarp();
+      }
+      __syncthreads();
+      // ---- epilogue: thread per point -- log|det|, phase, the ratio of complex logs (quirk Q12), angular weights
+      for (int t = tid; t < npt; t += CF::T) {
+        const double* Lp = smem + CF::oL + t * LSTR;
+        const double pr = Lp[0], pi = Lp[1];
+        const double la = 0.5 * log(pr * pr + pi * pi) + Lp[2] * 0.69314718055994530942 + smem[CF::oMISC + 0] + Lp[10];
+        const double pha = atan2(pi, pr);
+        const int e = c0 + t, a = e / AIQMC_NQUAD, p = e - a * AIQMC_NQUAD;
         const double wq = c_ecp.quad_wts[p] * den_inv;
         const double rr = (la * den_r + pha * den_i) * wq, ri = (pha * den_r - la * den_i) * wq;
         const double v0 = Lp[4], v1 = Lp[5], v2 = Lp[6], v3 = Lp[7], cs = Lp[3];
@@ -613,4 +946,7 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
   }
 }
 
+#undef AQ_HP_I
+#undef AQ_JA_I
+#undef AQ_JC_I
 }  // namespace aiqmc

@@ -1084,11 +1084,17 @@ struct Launch {
                                            U::seg_dst(l) * sizeof(double), cudaMemcpyDeviceToDevice, st));
       AQ_CUDA_OK(cudaMemcpyToSymbolAsync(c_uni, params + U::K.y_w, 6 * NE * sizeof(double), U::y_w * sizeof(double),
                                          cudaMemcpyDeviceToDevice, st));
-      AQ_CUDA_OK(cudaFuncSetAttribute(k_ecp_grp<NE, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::kBytes));
-      AQ_CUDA_OK(cudaFuncSetAttribute(k_ecp_grp<NE, NA>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      cudaSharedmemCarveoutMaxShared));
-      ++g_launch_count;
-      k_ecp_grp<NE, NA><<<(unsigned)B, CF::T, CF::kBytes, st>>>(*sys, params, pos, rot, B, w.cache, w, tm_out, tm_tau);
+      auto launch = [&](auto kern) -> int {
+        AQ_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::kBytes));
+        AQ_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        ++g_launch_count;
+        kern<<<(unsigned)B, CF::T, CF::kBytes, st>>>(*sys, params, pos, rot, B, w.cache, w, tm_out, tm_tau);
+        return AIQMC_OK;
+      };
+      int rc;
+      if constexpr (CF::kFlat) rc = launch(k_ecp_grp<NE, NA>);             // flat point loop for N <= 16
+      else rc = launch(k_ecp_grp_rows<NE, NA>);                            // per-electron loop beyond (C6H6)
+      if (rc != AIQMC_OK) return rc;
       AQ_CUDA_OK(cudaGetLastError());
     }
     return AIQMC_OK;
