@@ -523,7 +523,7 @@ def run_gpu(args):
                 traffic = json.load(open(tpath)).get("k_ecp_pt_dram_bytes_per_step")
             except Exception:
                 traffic = None
-        ncu_src = "profiles/r2_v2_step_kernels_raw.csv"
+        ncu_src = "profiles/r2_v6_ecp_pt_raw.csv"
         roofline = {"bound": "fp64", "kernel": f"{dom} stage of {head}", "achieved": stages[dom]["algorithmic_tflops"],
                     "peak": peak, "unit": "TFLOP/s", "frac": stages[dom]["frac"], "traffic": traffic,
                     "stages": stages,
