@@ -30,9 +30,9 @@ template <int NE, int NA>
 struct CoopGradCfg {
   static constexpr int N = NE, A = NA;
   static constexpr int GPW = 32 / NE;                        // configurations per warp
-  static constexpr int W = NE <= 6 ? 4 : (NE <= 10 ? 4 : 2); // warps per CTA
-  static constexpr int T = 32 * W;
-  static constexpr int NG = W * GPW;                         // configurations per CTA pass
+#ifndef AIQMC_GRADCOOP_W
+#define AIQMC_GRADCOOP_W 0                                   // 0 = pick per system
+#endif
   static constexpr int QM = Psi<NE, NA>::QM;
   static constexpr int RW = 8 * NA > 8 ? 8 * NA : 8;         // doubles a lane deposits for a block reduction
   // per-group scratch (doubles)
@@ -49,6 +49,14 @@ struct CoopGradCfg {
   static constexpr int SCR = kScrRaw + ((2 - kScrRaw % 16) + 16) % 16;
   static constexpr int TAPE = 9 * NE;                        // per thread: [N pairs][r, h1[4], h2[4]]
   static constexpr int kPar = (make_layout(NE, NA).total + 1) & ~1;
+  // warps per CTA.  N <= 6: 4 (two or more CTAs per SM).  Beyond that the pair tape (9 N doubles per thread) lets only
+  // ONE CTA fit an SM, so the CTA takes as many warps as shared memory holds (N2: 4 warps = 156 kB left the SM at 4
+  // resident warps, FP64 pipe 21 %, half the stall samples on instruction fetch; 6 warps = 227 kB).
+  static constexpr int kWarpDoubles = GPW * SCR + 32 * TAPE;
+  static constexpr int fit_warps(int w) { return w <= 2 ? 2 : ((kPar + w * kWarpDoubles) * 8 <= 227 * 1024 ? w : fit_warps(w - 1)); }
+  static constexpr int W = AIQMC_GRADCOOP_W > 0 ? AIQMC_GRADCOOP_W : (NE <= 6 ? 4 : fit_warps(8));
+  static constexpr int T = 32 * W;
+  static constexpr int NG = W * GPW;                         // configurations per CTA pass
   static constexpr int kDoubles = kPar + NG * SCR + T * TAPE;
   static constexpr int kBytes = kDoubles * 8;
 };
