@@ -16,7 +16,7 @@
 //                 REDUX arg-max + a double-buffered scratch row, 1 __syncwarp per step), the scatter of the pair
 //                 adjoints onto the OTHER electron of each pair (rotated pair order i = (k+t) mod N: every lane writes a
 //                 different row of the accumulator in every step -- no atomics, fixed order).
-// The pair-chain tape (r, h_two^1, h_two^2 per pair: 9 doubles) sits in shared memory [slot][thread] (conflict-free),
+// The pair-chain tape (h_two^1, h_two^2 per off-diagonal pair: 8 doubles) sits in shared memory [slot][thread] (conflict-free),
 // everything else in registers with compile-time indices.  The mathematics is grad_reverse's (deriv_split.cuh):
 // d log|det| = Re tr(M^-1 dM), layers walked backwards, chains walked backwards, electron-local parts contracted
 // through a 3-direction jet.  Reference semantics: jax.grad(logabs_f) of VMC/VMCmcstep.py:41,79 (A10-A12).
@@ -37,21 +37,31 @@ struct CoopGradCfg {
   static constexpr int RW = 8 * NA > 8 ? 8 * NA : 8;         // doubles a lane deposits for a block reduction
   // per-group scratch (doubles)
   static constexpr int oX = 0;                               // [3N] positions
-  static constexpr int oRED = oX + 3 * NE;                   // [N][RW]
-  static constexpr int oHS = oRED + NE * RW;                 // [N][4]   4-vector exchange (h levels, h_bar)
+  // Two pairs of buffers are never live at the same time (every hand-over is separated by a __syncwarp) and share
+  // their storage -- the scratch and the tape decide how many warps fit an SM (N2: 514 -> 306 doubles per group):
+  //   RED (layer-0 block sums in the forward pass, the block adjoints in the reverse pass) with MS (orbital matrix ->
+  //   inverse, in between);  HS (4-vector exchanges before and after the inverse) with PIV (pivot rows, during it).
+  static constexpr int oRED = (oX + 3 * NE + 1) & ~1;        // [N][RW]   |  [N][N][2] matrix transpose / inverse exchange
+  static constexpr int oMS = oRED;
+  static constexpr int kRedMs = NE * RW > 2 * NE * NE ? NE * RW : 2 * NE * NE;
+  static constexpr int oHS = oRED + kRedMs;                  // [N][4]   4-vector exchange (h levels, h_bar)  |  [2][N][2] pivot rows
+  static constexpr int oPIV = oHS;
   static constexpr int oGACC = oHS + 4 * NE;                 // [N][3]   gradient contributions to the other electron
-  static constexpr int oMS = (oGACC + 3 * NE + 1) & ~1;      // [N][N][2] matrix transpose / inverse exchange
-  static constexpr int oPIV = oMS + 2 * NE * NE;             // [2][N][2] pivot rows (double buffered)
   // group stride: even (double2 rows stay 16-byte aligned) and = 2 mod 16 doubles, so that the <= 8 groups of a warp
   // start 4 banks apart: the scratch accesses of different groups never collide (a stride of 120 doubles put groups
   // 0,2,4,6 on the same banks: 20 M conflicts per sweep in the first ncu capture)
-  static constexpr int kScrRaw = (oPIV + 4 * NE + 1) & ~1;
+  static constexpr int kScrRaw = (oGACC + 3 * NE + 1) & ~1;
   static constexpr int SCR = kScrRaw + ((2 - kScrRaw % 16) + 16) % 16;
-  static constexpr int TAPE = 9 * NE;                        // per thread: [N pairs][r, h1[4], h2[4]]
+  // per thread: [N-1 off-diagonal pairs][h1[4], h2[4] (, r)].  Where shared memory decides the number of resident warps
+  // (N > 6) the pair distance is recomputed in the reverse pass instead of taped (carbon: taped 0.67 ms, recomputed 0.69)
+  static constexpr bool kTapeR = NE <= 6;
+  static constexpr int TSLOT = kTapeR ? 9 : 8;
+  static constexpr int TAPE = TSLOT * (NE - 1);
   static constexpr int kPar = (make_layout(NE, NA).total + 1) & ~1;
-  // warps per CTA.  N <= 6: 4 (two or more CTAs per SM).  Beyond that the pair tape (9 N doubles per thread) lets only
-  // ONE CTA fit an SM, so the CTA takes as many warps as shared memory holds (N2: 4 warps = 156 kB left the SM at 4
-  // resident warps, FP64 pipe 21 %, half the stall samples on instruction fetch; 6 warps = 227 kB).
+  // warps per CTA.  N <= 6: 4 (two or more CTAs per SM).  Beyond that the pair tape (8 (N-1) doubles per thread) lets
+  // only ONE CTA fit an SM, so the CTA takes as many warps as shared memory (and 254 registers x 256 threads) hold.
+  // N2 history: 4 warps (156 kB) left the SM at 4 resident warps, FP64 pipe 21 %, half the stall samples on instruction
+  // fetch: sweep 16.4 ms; 6 warps (227 kB): 11.1 ms; aliased scratch + slimmer tape: 8 warps.
   static constexpr int kWarpDoubles = GPW * SCR + 32 * TAPE;
   static constexpr int fit_warps(int w) { return w <= 2 ? 2 : ((kPar + w * kWarpDoubles) * 8 <= 227 * 1024 ? w : fit_warps(w - 1)); }
   static constexpr int W = AIQMC_GRADCOOP_W > 0 ? AIQMC_GRADCOOP_W : (NE <= 6 ? 4 : fit_warps(8));
@@ -214,9 +224,11 @@ __global__ void __launch_bounds__((CoopGradCfg<NE, NA>::T), (NE <= 6 ? AIQMC_GRA
         Gf[1][0][c] += iu ? a1[c] : 0.0; Gf[1][1][c] += iu ? 0.0 : a1[c];
         Gf[2][0][c] += iu ? a2[c] : 0.0; Gf[2][1][c] += iu ? 0.0 : a2[c];
       }
-      tape[(t * 9) * T] = a0[0];
+      if (t > 0) {                                                             // the diagonal chain carries no position adjoint
 #pragma unroll
-      for (int c = 0; c < 4; ++c) { tape[(t * 9 + 1 + c) * T] = a1[c]; tape[(t * 9 + 5 + c) * T] = a2[c]; }
+        for (int c = 0; c < 4; ++c) { tape[((t - 1) * CF::TSLOT + c) * T] = a1[c]; tape[((t - 1) * CF::TSLOT + 4 + c) * T] = a2[c]; }
+        if (CF::kTapeR) tape[((t - 1) * CF::TSLOT + 8) * T] = a0[0];
+      }
       if (t > 0 && i < k) {                                                    // e-e Pade term, pairs i < j (Jastrow.py:23-41)
         const double r = a0[0];
         jas += P[L.jas_cusp + i * N + k] * r * s_inv(1.0 + P[L.jas_alpha + i * N + k] * r);
@@ -448,13 +460,14 @@ __global__ void __launch_bounds__((CoopGradCfg<NE, NA>::T), (NE <= 6 ? AIQMC_GRA
       i = i >= N ? i - N : i;
       const bool iu = i < n_up;
       double a0[4], a1[4], a2[4], ob2[4], ex1[4], ex0[4];
-      a0[0] = tape[(t * 9) * T];
 #pragma unroll
       for (int c = 0; c < 3; ++c) a0[1 + c] = xk[c] - X[3 * i + c];
+      a0[0] = CF::kTapeR ? tape[((t - 1) * CF::TSLOT + 8) * T]
+                         : s_sqrt(a0[1] * a0[1] + a0[2] * a0[2] + a0[3] * a0[3]);   // as pair_chain computed it
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        a1[c] = tape[(t * 9 + 1 + c) * T];
-        a2[c] = tape[(t * 9 + 5 + c) * T];
+        a1[c] = tape[((t - 1) * CF::TSLOT + c) * T];
+        a2[c] = tape[((t - 1) * CF::TSLOT + 4 + c) * T];
         ob2[c] = iu ? Gb[2][0][c] : Gb[2][1][c];
         ex1[c] = iu ? Gb[1][0][c] : Gb[1][1][c];
         ex0[c] = iu ? Gb[0][0][c] : Gb[0][1][c];
