@@ -20,7 +20,7 @@
 //     pivot row broadcast through a double-buffered scratch (1 __syncwarp per step), permutation parity from a
 //     Lehmer code (popc), determinant carried as a complex product with integer exponent renormalisation (one
 //     log and one atan2 per point);
-//   * tanh in interleaved batches of up to 8 (fastmath.cuh, ACC = 1: the value-only 11-op variant).
+//   * tanh in interleaved batches of up to 8 (fastmath.cuh, ACC = 1: the value-only 9-op variant).
 // One CTA = one walker; the CTA walks the walker's electrons i, and for each the A*50 points in chunks.
 // Per-point contributions are staged and summed in a fixed order (deterministic, no atomics).
 #pragma once

@@ -28,7 +28,7 @@ namespace aiqmc {
 #define AIQMC_PT_MINB 2            // resident CTAs/SM the register allocator must allow
 #endif
 #ifndef AIQMC_PT_ACC
-#define AIQMC_PT_ACC 1             // tanh variant of the value-only quadrature (fastmath.cuh: 1 = 11-op, < 5e-11)
+#define AIQMC_PT_ACC 1             // tanh variant of the value-only quadrature (fastmath.cuh: 1 = 9-op, < 5e-11)
 #endif
 constexpr int kAcc = AIQMC_PT_ACC;
 constexpr int kConstParMax = 3072;           // doubles of packed parameters kept in constant memory (24 kB)

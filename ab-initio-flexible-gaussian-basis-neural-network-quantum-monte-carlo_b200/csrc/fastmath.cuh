@@ -45,9 +45,11 @@ __shared__ double g_exp_tab[kExpTab];
 // ACC = 1 tanh of the quadrature kernels: a 512-entry table 2^(j/512) (4 kB) shrinks the reduced argument to
 // |2 r2| <= ln2/1024, where a QUADRATIC is enough for the same accuracy ((ln2/1024)^3/6 < 5.2e-11 on the exponential,
 // half of that on tanh): two polynomial terms fewer than with the 16-entry table.  The lookup is no longer
-// conflict-free (32 lanes over 16 bank pairs: ~4-5 wavefronts), but those kernels leave the shared-memory pipe mostly
-// idle and are bound by the FP64 pipe.  Measured on k_ecp_pt (carbon, 65,536 walkers): 16 entries / quartic 4.92 ms,
-// 64 entries / cubic 4.81 ms.
+// conflict-free (32 lanes over 16 bank pairs: ~4-5 wavefronts).  k_ecp_pt leaves the shared-memory pipe mostly idle
+// (LSU wavefronts 47 % with the table) and is bound by the FP64 pipe and the issue slots: 16 entries / quartic 4.92 ms,
+// 64 entries / cubic 4.81 ms, sign-free form 4.63, 512 entries / quadratic 4.56, one-instruction clamp 4.48 (carbon,
+// 65,536 walkers).  k_ecp_grp<10,2> is closer to its shared-memory limit (LSU wavefronts 84 % with the table): there
+// the big table is worth 1.2 % (122.8 vs 124.3 ms, A/B on one box).
 #ifndef AIQMC_TANH_TAB64
 #define AIQMC_TANH_TAB64 1
 #endif
