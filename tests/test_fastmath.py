@@ -36,10 +36,14 @@ def test_ftanh_absolute_error_and_sign():
 
 def test_ftanh_batched_variants():
     rng = np.random.default_rng(4)
-    x = np.concatenate([rng.uniform(-25, 25, 200000), rng.normal(0, 1, 200000)])
+    x = np.concatenate([rng.uniform(-25, 25, 200000), rng.normal(0, 1, 200000), rng.uniform(-400, 400, 3996),
+                        [1e3, -1e3, 1e5, -1e5]])                       # saturation far beyond the exponent clamp
+    assert x.size % 4 == 0
     assert np.array_equal(_run(4, x), _run(1, x))                     # ACC=0 batched == scalar, bit for bit
-    err = np.abs(_run(5, x) - np.tanh(x))
+    got = _run(5, x)                                                  # ACC=1: 512-entry table, quadratic, one Newton step
+    err = np.abs(got - np.tanh(x))
     assert err.max() < 5e-11, err.max()
+    assert (np.abs(got) <= 1.0).all() and np.isfinite(got).all()
 
 
 def test_frcp_frsqrt():

@@ -122,6 +122,39 @@ def test_local_energy_ecp(name, rich):
     np.testing.assert_allclose(stats, [e.real.sum(), e.imag.sum(), (np.abs(e) ** 2).sum(), len(e)], rtol=1e-12)
 
 
+@pytest.mark.parametrize("name,scale", [("C_ecp", 30.0), ("N2_ecp", 12.0)])
+def test_saturated_tanh_network_value_and_ecp_energy(name, scale):
+    """Weights scaled until most tanh arguments sit far in the saturated tails (|z| up to a few hundred): the in-house
+    tanh bodies (sign-free 1 - 2/(1 + exp(2z)); the quadrature kernels' 512-entry-table variant with the clamped, biased
+    exponent) must stay finite and agree with torch.tanh through log|psi| and the ccECP local energy."""
+    case = Case(**CASES[name], nwalkers=16, width=0.9)
+
+    def blow(t):
+        for lp in t['layers']['streams']:
+            for key in ('convolutional', 'single', 'double'):
+                if key in lp:
+                    lp[key]['w'] = lp[key]['w'] * scale
+        for lp in t['layers']['streams_y']:
+            lp['single_Ynlm']['w'] = lp['single_Ynlm']['w'] * scale
+        return t
+    case.params = blow(case.params)
+    tabs = ecp_tables(case.a, rich=True)
+    eng = engine(case, ecp=aiqmc_b200.make_ecp(case.a, list_l=2, **tabs))
+    phase, la = eng.psi(torch.tensor(case.pos), mode=0)
+    p0, l0 = case.net.apply(case.params, torch.tensor(case.pos), case.t_spins, case.t_atoms)
+    assert np.isfinite(la.cpu().numpy()).all()
+    np.testing.assert_allclose(la.cpu().numpy(), l0.numpy(), rtol=1e-9, atol=1e-9)
+    rot = torch.tensor(O.random_rotations(case.rng, case.B))
+    e = eng.local_energy(torch.tensor(case.pos), rot).cpu().numpy()
+    le = O.local_energy_ecp(case.net.apply, O.make_log_network(case.net.apply), case.charges, None,
+                            tabs['rn_local'], tabs['local_coes'], tabs['local_exps'], tabs['rn_non_local'],
+                            tabs['non_local_coes'], tabs['non_local_exps'], case.a, case.n, 3, 2)
+    ref, _ = le(case.params, rot, case.oracle_data(batched_static=False))
+    assert np.isfinite(e).all()
+    scale_e = np.maximum(1.0, np.abs(ref.numpy()))
+    assert (np.abs(e - ref.numpy()) / scale_e).max() < 1e-6              # derivatives of a saturated network are large
+
+
 def test_local_energy_dropin_factory():
     case = Case(**CASES["C_ecp"], nwalkers=8)
     tabs = ecp_tables(1)
