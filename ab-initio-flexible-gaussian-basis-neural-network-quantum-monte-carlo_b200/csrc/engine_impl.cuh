@@ -773,11 +773,25 @@ __global__ void __launch_bounds__(kThreads) k_tmove_select(const double* __restr
   int trips = 0;
   for (int v = NMOV; v > 0; v >>= 1) ++trips;     // bit length of NMOV == ceil(log2(NMOV + 1))
   // running prefix for the bisection: recomputing the prefix is O(NMOV) per probe; NMOV <= 1 + 50 A
-  for (int it = 0; it < trips; ++it) {
-    const int mid = (low + high) / 2;
-    const cplx c = cdf_at(mid < NMOV ? mid : NMOV - 1);
-    const bool le = (r < c.re) || (r == c.re && 0.0 <= c.im);     // r + 0j <= cdf[mid], lexicographic
-    if (le) high = mid; else low = mid;
+  if constexpr (NMOV <= 128) {
+    // the whole running sum once (same sequential association as cdf_at), then the probes read it: the bisection made
+    // ~8 probes of ~NMOV/2 complex multiply-adds each
+    cplx cdf[NMOV];
+    cplx run = {0.0, 0.0};
+    for (int k = 0; k < NMOV; ++k) { run = cadd(run, cmul(total(i, k), ninv)); cdf[k] = run; }
+    for (int it = 0; it < trips; ++it) {
+      const int mid = (low + high) / 2;
+      const cplx c = cdf[mid < NMOV ? mid : NMOV - 1];
+      const bool le = (r < c.re) || (r == c.re && 0.0 <= c.im);   // r + 0j <= cdf[mid], lexicographic
+      if (le) high = mid; else low = mid;
+    }
+  } else {
+    for (int it = 0; it < trips; ++it) {
+      const int mid = (low + high) / 2;
+      const cplx c = cdf_at(mid < NMOV ? mid : NMOV - 1);
+      const bool le = (r < c.re) || (r == c.re && 0.0 <= c.im);   // r + 0j <= cdf[mid], lexicographic
+      if (le) high = mid; else low = mid;
+    }
   }
   int mv = high < NMOV ? high : 0;
   if (selected) selected[t] = mv;
