@@ -85,6 +85,48 @@ k_energy_stats_cl(const double* __restrict__ e, int stride, int64_t B, double* _
   }
 }
 
+// Large batches (beyond what one 8-CTA cluster can stream): fixed chunks of kStatChunk walkers per CTA -> partials
+// [chunk][3] in the caller's workspace, then one CTA adds the partials in a fixed order.  The result depends on the
+// batch size only (not on the GPU), like the single-cluster form.
+constexpr int kStatChunk = 4096;
+constexpr int64_t kStatSmall = (int64_t)1 << 18;           // up to here the single-cluster kernel is used
+__global__ void __launch_bounds__(256) k_energy_partials(const double* __restrict__ e, int stride, int64_t B,
+                                                         double* __restrict__ part) {
+  __shared__ double red[3][8];
+  const int64_t lo = (int64_t)blockIdx.x * kStatChunk, hi = lo + kStatChunk < B ? lo + kStatChunk : B;
+  double sr = 0.0, si = 0.0, s2 = 0.0;
+  if (stride == 2) {
+    const double2* e2 = reinterpret_cast<const double2*>(e);
+    for (int64_t b = lo + threadIdx.x; b < hi; b += 256) { const double2 v = e2[b]; sr += v.x; si += v.y; s2 += v.x * v.x + v.y * v.y; }
+  } else {
+    for (int64_t b = lo + threadIdx.x; b < hi; b += 256) { const double v = e[b]; sr += v; s2 += v * v; }
+  }
+  sr = wsum(sr); si = wsum(si); s2 = wsum(s2);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sr; red[1][threadIdx.x >> 5] = si; red[2][threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double a = 0.0;
+    for (int i = 0; i < 8; ++i) a += red[threadIdx.x][i];
+    part[(int64_t)blockIdx.x * 3 + threadIdx.x] = a;
+  }
+}
+__global__ void __launch_bounds__(1024) k_energy_partials_sum(const double* __restrict__ part, int nchunk, int64_t B,
+                                                              double* __restrict__ out) {
+  __shared__ double red[3][32];
+  double a[3] = {0.0, 0.0, 0.0};
+  for (int c = threadIdx.x; c < nchunk; c += 1024)
+    for (int q = 0; q < 3; ++q) a[q] += part[(int64_t)c * 3 + q];
+  for (int q = 0; q < 3; ++q) a[q] = wsum(a[q]);
+  if ((threadIdx.x & 31) == 0) for (int q = 0; q < 3; ++q) red[q][threadIdx.x >> 5] = a[q];
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int i = 0; i < 32; ++i) t += red[threadIdx.x][i];
+    out[threadIdx.x] = t;
+  }
+  if (threadIdx.x == 3) out[3] = (double)B;
+}
+
 // min over walkers of min(|E_est - Re E_L|, branchcut): step 1 of comput_S (DMC/S_matrix.py:22-23, quirk Q20)
 __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kClThreads)
 k_ecut_min_cl(const double* __restrict__ e, int stride, int64_t B, double e_est, const double* __restrict__ branchcut,
@@ -269,7 +311,7 @@ __global__ void __launch_bounds__(kOwnChunk) k_owned_count(const int32_t* __rest
 }
 // in-place exclusive scan of v[0..n) by one CTA
 __global__ void __launch_bounds__(1024) k_scan_i32(int32_t* __restrict__ v, int n) {
-  __shared__ int wsum[32];
+  __shared__ int wtot[32];
   __shared__ int carry;
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   if (threadIdx.x == 0) carry = 0;
@@ -280,16 +322,16 @@ __global__ void __launch_bounds__(1024) k_scan_i32(int32_t* __restrict__ v, int 
     int inc = x;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    if (lane == 31) wsum[wp] = inc;
+    if (lane == 31) wtot[wp] = inc;
     __syncthreads();
     if (wp == 0) {
-      int w = wsum[lane], wi = w;
+      int w = wtot[lane], wi = w;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
-      wsum[lane] = wi - w;                                   // exclusive warp offsets
+      wtot[lane] = wi - w;                                   // exclusive warp offsets
     }
     __syncthreads();
-    const int excl = carry + wsum[wp] + inc - x;
+    const int excl = carry + wtot[wp] + inc - x;
     if (i < n) v[i] = excl;
     __syncthreads();
     if (threadIdx.x == 1023) carry = excl + x;
@@ -449,6 +491,24 @@ int aiqmc_energy_stats(const double* e_l, int32_t e_l_stride, int64_t n_walkers,
   if (!e_l || !stats || n_walkers < 0 || (e_l_stride != 1 && e_l_stride != 2)) return AIQMC_E_BADARG;
   ++g_launch_count;
   k_energy_stats_cl<<<kCl, kClThreads, 0, (cudaStream_t)stream>>>(e_l, e_l_stride, n_walkers, stats);
+  AQ_CUDA_OK(cudaGetLastError());
+  return AIQMC_OK;
+}
+
+int64_t aiqmc_energy_stats_workspace_bytes(int64_t n_walkers) {
+  if (n_walkers < 0) return AIQMC_E_BADARG;
+  return n_walkers <= kStatSmall ? 0 : al256(((n_walkers + kStatChunk - 1) / kStatChunk) * 3 * 8);
+}
+int aiqmc_energy_stats_ws(const double* e_l, int32_t e_l_stride, int64_t n_walkers, double* stats, void* workspace,
+                          int64_t workspace_bytes, void* stream) {
+  if (!e_l || !stats || n_walkers < 0 || (e_l_stride != 1 && e_l_stride != 2)) return AIQMC_E_BADARG;
+  if (n_walkers <= kStatSmall) return aiqmc_energy_stats(e_l, e_l_stride, n_walkers, stats, stream);
+  if (!workspace || workspace_bytes < aiqmc_energy_stats_workspace_bytes(n_walkers)) return AIQMC_E_WORKSPACE;
+  if (e_l_stride == 2 && ((uintptr_t)e_l & 15) != 0) return AIQMC_E_BADARG;
+  const int nchunk = (int)((n_walkers + kStatChunk - 1) / kStatChunk);
+  g_launch_count += 2;
+  k_energy_partials<<<nchunk, 256, 0, (cudaStream_t)stream>>>(e_l, e_l_stride, n_walkers, (double*)workspace);
+  k_energy_partials_sum<<<1, 1024, 0, (cudaStream_t)stream>>>((const double*)workspace, nchunk, n_walkers, stats);
   AQ_CUDA_OK(cudaGetLastError());
   return AIQMC_OK;
 }

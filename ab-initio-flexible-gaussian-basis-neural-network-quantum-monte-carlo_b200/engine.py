@@ -219,9 +219,15 @@ class WalkerEngine:
         else:
             raw, stride = e_l.contiguous(), 1
         out = torch.empty(4, dtype=torch.float64, device=self.device)
+        nbytes = _nbytes(self.lib.aiqmc_energy_stats_workspace_bytes(e_l.shape[0]), "aiqmc_energy_stats_workspace_bytes")
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.aiqmc_energy_stats(_ptr(raw), stride, e_l.shape[0], _ptr(out), _stream()),
-                       "aiqmc_energy_stats")
+            if nbytes > 0:                 # beyond 2^18 walkers: chunk partials in a workspace, fixed-order sum
+                ws = self._workspace("stats", nbytes)
+                _lib.check(self.lib.aiqmc_energy_stats_ws(_ptr(raw), stride, e_l.shape[0], _ptr(out), _ptr(ws), ws.numel(),
+                                                          _stream()), "aiqmc_energy_stats_ws")
+            else:
+                _lib.check(self.lib.aiqmc_energy_stats(_ptr(raw), stride, e_l.shape[0], _ptr(out), _stream()),
+                           "aiqmc_energy_stats")
         return out
 
     # ---- DMC pieces -------------------------------------------------------------------

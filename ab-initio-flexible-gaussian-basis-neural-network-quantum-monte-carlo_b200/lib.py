@@ -25,7 +25,8 @@ EXPORTS = ["aiqmc_param_layout", "aiqmc_supported", "aiqmc_rescan_systems", "aiq
            "aiqmc_psi_param_grad", "aiqmc_mh_workspace_bytes", "aiqmc_mh_step", "aiqmc_correlated_samples",
            "aiqmc_weights_jacobian", "aiqmc_vmc_sweep_compact", "aiqmc_rng_sweep", "aiqmc_rng_rotations", "aiqmc_rng_uniform",
            "aiqmc_nccl_available", "aiqmc_nccl_unique_id", "aiqmc_nccl_comm_init", "aiqmc_nccl_comm_destroy", "aiqmc_energy_allreduce",
-           "aiqmc_ecut_allreduce_min", "aiqmc_rebalance_workspace_bytes", "aiqmc_rebalance_nccl"]
+           "aiqmc_ecut_allreduce_min", "aiqmc_rebalance_workspace_bytes", "aiqmc_rebalance_nccl",
+           "aiqmc_energy_stats_workspace_bytes", "aiqmc_energy_stats_ws"]
 
 _lib = None
 
@@ -85,6 +86,8 @@ def load() -> C.CDLL:
         "aiqmc_gto_eval": (C.c_int, [vp, i32, vp, i32, vp, i64, i32, vp, vp, vp, vp]),
         "aiqmc_bench_dfma": (C.c_int, [i64, vp, C.POINTER(C.c_double), vp]),
         "aiqmc_energy_stats": (C.c_int, [vp, i32, i64, vp, vp]),
+        "aiqmc_energy_stats_workspace_bytes": (i64, [i64]),
+        "aiqmc_energy_stats_ws": (C.c_int, [vp, i32, i64, vp, vp, i64, vp]),
         "aiqmc_dmc_ecut_min": (C.c_int, [vp, i32, i64, f64, vp, vp, vp]),
         "aiqmc_dmc_s": (C.c_int, [vp, i32, vp, i64, i32, f64, f64, vp, f64, vp, vp]),
         "aiqmc_dmc_weights": (C.c_int, [vp, vp, vp, i64, f64, f64, vp]),

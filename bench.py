@@ -445,7 +445,8 @@ def time_hbm_kernels(eng, B, n, dev, flush):
     del posl, indl
     el = torch.randn((Bl, 2), dtype=torch.float64, device=dev)
     ms = timed(lambda: eng.energy_stats(torch.view_as_complex(el)))
-    out["energy_stats_x16"] = {"ms": ms, "GB_per_s": (Bl * 16) / (ms * 1e-3) / 1e9, "bytes": Bl * 16}
+    out["energy_stats_x16"] = {"ms": ms, "GB_per_s": (Bl * 16) / (ms * 1e-3) / 1e9, "bytes": Bl * 16,
+                               "what": "aiqmc_energy_stats_ws: chunk partials + fixed-order sum (beyond 2^18 walkers)"}
     del el
     ptl = torch.randn((Bl * 6, 3), dtype=torch.float64, device=dev)
     ms = timed(lambda: basis.eval(ptl))

@@ -207,6 +207,12 @@ int aiqmc_dmc_tmove(const AiqmcSystem* sys, const AiqmcEcp* ecp, const double* p
  * (NCCL sum of 4 doubles).  e_l_stride = 1 (real) or 2 (complex interleaved). */
 int aiqmc_energy_stats(const double* e_l, int32_t e_l_stride, int64_t n_walkers, double* stats,
                        void* stream);
+/* The same statistics for batches beyond 2^18 walkers (one 8-CTA cluster cannot stream them at HBM rate): partial sums of
+ * fixed 4096-walker chunks in the caller's workspace, added in a fixed order -- the result depends on the batch size
+ * only.  Up to 2^18 walkers it forwards to aiqmc_energy_stats (workspace may be NULL: the size query returns 0). */
+int64_t aiqmc_energy_stats_workspace_bytes(int64_t n_walkers);
+int aiqmc_energy_stats_ws(const double* e_l, int32_t e_l_stride, int64_t n_walkers, double* stats, void* workspace,
+                          int64_t workspace_bytes, void* stream);
 
 /* ---- parameter side of the loss gradient: replaces the `jax.jvp(batch_network, primals, tangents)`
  * of make_loss.total_energy_jvp (Loss/pploss.py:186-223) as seen through jax.grad.

@@ -246,3 +246,22 @@ def test_lane_per_electron_derivative_kernels_on_every_group_shape(n, a):
         np.testing.assert_allclose(g.cpu().numpy(), gt.numpy(), rtol=1e-7, atol=1e-8)
         np.testing.assert_allclose(g1.cpu().numpy(), gt.numpy(), rtol=1e-7, atol=1e-8)
         np.testing.assert_allclose(lap.cpu().numpy(), d2.sum(-1).numpy(), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_energy_stats_large_batch_workspace_path():
+    """Beyond 2^18 walkers the statistics go through chunk partials in a workspace (aiqmc_energy_stats_ws): same numbers
+    as a float64 reference sum to round-off, deterministic, and identical to the single-cluster kernel at its size limit."""
+    import aiqmc_b200
+    from aiqmc_b200 import workloads as W
+    eng = W.build("c_ecp", 2).engine()
+    rng = np.random.default_rng(3)
+    for B in (1 << 18, (1 << 18) + 1, 1_000_003):
+        e = torch.tensor(rng.normal(size=(B, 2)) * 3.0 - 5.0).cuda()
+        ec = torch.view_as_complex(e)
+        got = eng.energy_stats(ec).cpu().numpy()
+        ref = np.array([float(e[:, 0].sum()), float(e[:, 1].sum()), float((e * e).sum()), B])
+        np.testing.assert_allclose(got, ref, rtol=1e-12)
+        assert np.array_equal(got, eng.energy_stats(ec).cpu().numpy())                 # run-to-run identical
+        gr = eng.energy_stats(e[:, 0].contiguous()).cpu().numpy()                      # real input (stride 1)
+        np.testing.assert_allclose(gr, [ref[0], 0.0, float((e[:, 0] ** 2).sum()), B], rtol=1e-12, atol=1e-9)
