@@ -225,6 +225,9 @@ static __device__ __noinline__ void tanh_ool(const double* __restrict__ z, doubl
   ftanh_n<NV, ACC>(z, out, g_exp_tab);
 }
 #endif
+#ifndef AIQMC_TANH_CH
+#define AIQMC_TANH_CH 8            // tanh evaluations interleaved per batch (ILP against register pressure)
+#endif
 // NV tanh at once: doubles go through the interleaved ftanh_n (ILP), jets one by one.
 template <int NV, int ACC>
 AQ_HD void tanhv(const double* __restrict__ z, double* __restrict__ out) {
@@ -234,7 +237,7 @@ AQ_HD void tanhv(const double* __restrict__ z, double* __restrict__ out) {
 #ifdef AIQMC_LIBM
   for (int i = 0; i < NV; ++i) out[i] = tanh(z[i]);
 #else
-  constexpr int CH = 8;
+  constexpr int CH = AIQMC_TANH_CH;
   if constexpr (NV <= CH) {
     ftanh_n<NV, ACC>(z, out, exp_tab());
   } else {
