@@ -248,6 +248,24 @@ def test_lane_per_electron_derivative_kernels_on_every_group_shape(n, a):
         np.testing.assert_allclose(lap.cpu().numpy(), d2.sum(-1).numpy(), rtol=1e-6, atol=1e-6)
 
 
+@pytest.mark.parametrize("n,a", [(5, 2), (6, 1), (8, 2), (12, 2)])
+def test_group_quadrature_kernel_on_every_group_shape(n, a):
+    """k_ecp_grp packs floor(32/N) quadrature points per warp and, for N <= 16, walks ALL N*A*50 points of a walker in
+    chunks of 4 NG: N = 5 (6 groups, 2 idle lanes), 6 (5 groups), 8 (4 groups, none idle), 12 (2 groups, 8 idle lanes);
+    chunk sizes 4 NG that do and do not divide N*A*50.  ccECP local energy against the oracle, ragged batch."""
+    spins = [1.] * ((n + 1) // 2) + [-1.] * (n // 2)
+    case = Case(n=n, natoms=a, spins=spins, seed=70 + n, nwalkers=3, width=0.8)
+    tabs = ecp_tables(a, rich=True)
+    eng = engine(case, ecp=aiqmc_b200.make_ecp(a, list_l=2, **tabs))
+    rot = torch.tensor(O.random_rotations(case.rng, case.B))
+    e = eng.local_energy(torch.tensor(case.pos), rot).cpu().numpy()
+    le = O.local_energy_ecp(case.net.apply, O.make_log_network(case.net.apply), case.charges, None,
+                            tabs['rn_local'], tabs['local_coes'], tabs['local_exps'], tabs['rn_non_local'],
+                            tabs['non_local_coes'], tabs['non_local_exps'], a, n, 3, 2)
+    ref, _ = le(case.params, rot, case.oracle_data(batched_static=False))
+    np.testing.assert_allclose(e, ref.numpy(), atol=1e-7, rtol=1e-8)
+
+
 @pytest.mark.gpu
 def test_energy_stats_large_batch_workspace_path():
     """Beyond 2^18 walkers the statistics go through chunk partials in a workspace (aiqmc_energy_stats_ws): same numbers
