@@ -359,28 +359,18 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
       smem[CF::oJC + slot * N + t] = (t == i) ? 0.0 : params[L.jas_cusp + lo * N + hi];
     }
   };
-  if constexpr (CF::kFlat)
-    for (int i = 0; i < N; ++i) stage_row(i, i);          // published by the barrier after the first phase 0
+  static_assert(CF::kFlat, "k_ecp_grp is the flat point loop (N <= 16); k_ecp_grp_rows handles the rest");
+  for (int i = 0; i < N; ++i) stage_row(i, i);            // published by the barrier after the first phase 0
 
-  constexpr int kChunksPerI = (PW + PC - 1) / PC;         // non-flat: chunks never straddle electrons
-  constexpr int kChunks = CF::kFlat ? (CF::ETOT + PC - 1) / PC : N * kChunksPerI;
+  constexpr int kChunks = (CF::ETOT + PC - 1) / PC;
 #pragma unroll 1
   for (int ch = 0; ch < kChunks; ++ch) {
-    int e0, npt, iu = 0, c0u = 0;                          // non-flat: the chunk's electron (CTA-uniform) and offset
-    if constexpr (CF::kFlat) {
-      e0 = ch * PC;
-      npt = (CF::ETOT - e0 < PC) ? CF::ETOT - e0 : PC;
-    } else {
-      iu = ch / kChunksPerI;
-      c0u = (ch - iu * kChunksPerI) * PC;
-      e0 = iu * PW + c0u;
-      npt = (PW - c0u < PC) ? PW - c0u : PC;
-      if (c0u == 0) stage_row(iu, 0);                     // the previous electron's readers passed the chunk-end barrier
-    }
+    const int e0 = ch * PC;
+    const int npt = (CF::ETOT - e0 < PC) ? CF::ETOT - e0 : PC;
     {
       // ---- phase 0: thread per point -- rotated point, cos(theta) (quirks Q13, Q14), electron i's local part
       for (int t = tid; t < npt; t += CF::T) {
-        const int i = CF::kFlat ? (e0 + t) / PW : iu, ew = CF::kFlat ? e0 + t - i * PW : c0u + t;
+        const int i = (e0 + t) / PW, ew = e0 + t - i * PW;
         const int a = ew / AIQMC_NQUAD, p = ew - a * AIQMC_NQUAD;
         double* Lp = smem + CF::oL + t * LSTR;
         double ae[3], xn[3];
@@ -410,8 +400,6 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
       __syncthreads();
 
       // ---- main phase: one group per point, lane = electron
-      const bool diag_u = act && (k == iu);               // non-flat: the chunk's electron is CTA-uniform
-      const int si_u = iu < n_up ? 0 : 1;
 #pragma unroll 1
       for (int it = 0;; ++it) {
         const int t0 = warp * GPW + it * NG;
@@ -426,10 +414,10 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
         }
         const bool valid = t0 + g < npt;
         const int t = valid ? t0 + g : npt - 1;
-        const int i = CF::kFlat ? (e0 + t) / PW : iu;                     // the point's displaced electron (group-uniform)
-        const int si = CF::kFlat ? (i < n_up ? 0 : 1) : si_u;
-        const bool diag = CF::kFlat ? (act && (k == i)) : diag_u;
-        const int row_off = CF::kFlat ? i : 0;                            // row i of the pair-chain cache [3][4][N]
+        const int i = (e0 + t) / PW;                                      // the point's displaced electron (group-uniform)
+        const int si = i < n_up ? 0 : 1;
+        const bool diag = act && (k == i);
+        const int row_off = i;                                            // row i of the pair-chain cache [3][4][N]
 #define AQ_HP_I(idx) smem[CF::oHP + row_off * 12 * N + (idx)]
 #define AQ_JA_I(idx) smem[CF::oJA + row_off * N + (idx)]
 #define AQ_JC_I(idx) smem[CF::oJC + row_off * N + (idx)]
@@ -592,7 +580,7 @@ k_ecp_grp(AiqmcSystem sys, const double* __restrict__ params, const double* __re
         const double pr = Lp[0], pi = Lp[1];
         const double la = 0.5 * log(pr * pr + pi * pi) + Lp[2] * 0.69314718055994530942 + smem[CF::oMISC + 0] + Lp[10];
         const double pha = atan2(pi, pr);
-        const int i = CF::kFlat ? (e0 + t) / PW : iu, ew = CF::kFlat ? e0 + t - i * PW : c0u + t;
+        const int i = (e0 + t) / PW, ew = e0 + t - i * PW;
         const int a = ew / AIQMC_NQUAD, p = ew - a * AIQMC_NQUAD;
         const double wq = c_ecp.quad_wts[p] * den_inv;
         const double rr = (la * den_r + pha * den_i) * wq, ri = (pha * den_r - la * den_i) * wq;
