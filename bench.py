@@ -552,7 +552,8 @@ def run_gpu(args):
                     "frac": res["algorithmic_tflops_per_gpu"] / peak if peak else None, "traffic": None,
                     "note": "algorithmic flops (150NA + 9N + 11) F(N,A) per walker (SURVEY 8d) / CUDA-event step time / DFMA microbenchmark"}
     if D.world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(head if head != "dmc" else "c_ecp", args.cpu_walkers, 5, 1)
+        cw, cs = cpu_sample(head, args.cpu_walkers)
+        cpu = cpu_baseline(head if head != "dmc" else "c_ecp", cw, cs, 1)
 
     line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": D.world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
@@ -644,6 +645,17 @@ def reference_step_fn(name, nwalkers):
         return None, f"the reference failed to build or run: {exc!r}"
 
 
+# bounded CPU samples (about 10-30 s of host work per workload: the oracle's ccECP energy is 50 N A psi evaluations per
+# walker -- 2,048 benzene walkers would be 37 M evaluations of a 30-electron network and ran the host out of memory)
+CPU_SAMPLE = {"c_ecp": (2048, 5), "c_ae": (2048, 5), "dmc": (2048, 5), "n2": (96, 3), "c6h6": (2, 2)}
+
+
+def cpu_sample(head, cpu_walkers):
+    """(walkers, steps) of the CPU leg: --cpu-walkers if given, else the workload's bounded default."""
+    w, st = CPU_SAMPLE[head]
+    return (cpu_walkers if cpu_walkers > 0 else w), st
+
+
 def cpu_baseline(name, nwalkers, steps, warmup):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -671,7 +683,7 @@ def run_reference(args):
     from aiqmc_b200 import workloads as W
     head = args.workload if args.workload != "dmc" else "c_ecp"
     B = args.walkers if args.walkers else W.SYSTEMS[args.workload]["walkers"]
-    nwalk = args.cpu_walkers
+    nwalk, _ = cpu_sample(args.workload, args.cpu_walkers)
     cpu = cpu_baseline(head, nwalk, args.steps, args.warmup)
     value = cpu["value"]
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -691,7 +703,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c_ecp", choices=["c_ecp", "c_ae", "n2", "c6h6", "dmc"])
     ap.add_argument("--walkers", type=int, default=0, help="walkers per GPU (default: the workload's BASELINE size)")
-    ap.add_argument("--cpu-walkers", type=int, default=2048, help="walkers in the bounded CPU sample")
+    ap.add_argument("--cpu-walkers", type=int, default=0,
+                    help="walkers in the bounded CPU sample (0: per-workload default, e.g. 2,048 for carbon, 2 for benzene)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side", "--no-other-systems", dest="no_side", action="store_true",
                     help="skip the other BASELINE configurations measured next to the headline")
